@@ -1,0 +1,159 @@
+/* rma_b200.h — C ABI of the B200-native RMA-Net hot path (chamfer NN search + backward, se(3) exp-map warp).
+ *
+ * This is the drop-in boundary.  The reference has no native entry points for this path: chamfer is
+ * pure torch (model/loss.py:45-70) and the warp is pure torch + one autograd.Function (model/LieAlgebra/se3.py:51-154).
+ * The convention copied here is the one of the reference's only native extension, model/exfunc: a Python
+ * torch.autograd.Function (functions/point_render_func.py:19-32) calls `ext.forward / ext.backward`, which unwrap
+ * tensors to raw `float* / int*` + `int` sizes (expackages/point_render/point_render.cpp:29-38, 40-99, 101-133).
+ * Every function below is the raw-pointer layer of that pattern for one reference symbol, cited per function.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers on the current CUDA device unless the name ends in `_host`;
+ *   - fp32 data, int32 indices, element (not byte) strides, 64-bit;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (0 = legacy default stream); all calls are asynchronous on it,
+ *     never synchronise the device, never allocate, and keep no state between calls (re-entrant, graph-capturable)
+ *     — unlike the reference wrapper, which brackets every launch group with cudaDeviceSynchronize
+ *     (point_render.cpp:54-55, 78-79, 95-96);
+ *   - return value: 0 on success, a `cudaError_t` value (> 0) for CUDA failures, or a negative RMA_E_* code for
+ *     argument errors.  Nothing calls exit() (the reference does: point_render.cpp:10-18).
+ */
+#ifndef RMA_B200_H_
+#define RMA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMA_B200_ABI_VERSION 1
+
+#define RMA_OK 0
+#define RMA_E_BADARG (-1)     /* null pointer / non-positive size / size overflow */
+#define RMA_E_WORKSPACE (-2)  /* workspace too small or misaligned (256 B) */
+#define RMA_E_ARCH (-3)       /* device is not sm_100 */
+
+int rma_b200_abi_version(void);
+const char* rma_b200_error_string(int code);
+/* SM count and max SM clock (kHz) of the current device; used for the FP32 roofline denominator. */
+int rma_b200_device_info(int* sm_count, int* clock_khz, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Chamfer nearest-neighbour search, both directions.   Replaces compute_sqrdis_map + chamfer_dist
+ * (model/loss.py:45-58, 60-70; callers loss.py:203, train_view.py:285-286, 379-380).
+ *
+ *   dist1[b,i] = min_j |x[b,i]-y[b,j]|^2     idx1[b,i] = first j attaining it      (i < N, j < M)
+ *   dist2[b,j] = min_i |x[b,i]-y[b,j]|^2     idx2[b,j] = first i attaining it
+ *
+ * x is [B,N,3] with element strides (xsb, xsn, xsc); y is [B,M,3] with (ysb, ysn, ysc) — any strides, so the
+ * batch-strided slices (train_view.py:369-370) and transposed stage outputs (loss.py:264) are taken as they are.
+ * dist1/idx1 are contiguous [B,N]; dist2/idx2 contiguous [B,M].  idx1/idx2 may be NULL (forward-only metric calls).
+ * Distances are evaluated in fp32 DIFFERENCE form (dx*dx, fma(dy,dy,.), fma(dz,dz,.)), never the expanded form;
+ * the [B,N,M] matrix is never materialised.  workspace: rma_chamfer_workspace_bytes(B,N,M) bytes, 256-B aligned.
+ */
+size_t rma_chamfer_workspace_bytes(int B, int N, int M);
+int rma_chamfer_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                        const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
+                        int B, int N, int M,
+                        float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* The three stages of rma_chamfer_forward as separate calls on the same workspace (prep -> search -> finalize).
+ * rma_chamfer_forward is exactly their composition; they exist so that a harness can bracket the dominant kernel
+ * (search) with its own events (bench.py roofline leg) or capture the stages in a graph individually. */
+int rma_chamfer_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                     const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
+                     int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream);
+int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream);
+int rma_chamfer_finalize(int B, int N, int M, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* Launch shape the search kernel will use for (B,N,M) on the current device (reporting only). */
+int rma_chamfer_search_config(int B, int N, int M, int* ctas, int* threads, int* splits, int* ctas_per_sm);
+
+/* Backward of the above.  Replaces the implicit torch autograd of loss.py:45-70 (MinBackward x2, BmmBackward,
+ * MulBackward — SURVEY.md §8a row a4).  g1 [B,N], g2 [B,M] contiguous upstream gradients (either may be NULL = 0).
+ *   grad_x[b,i] = 2 g1[b,i] (x_i - y_idx1[b,i]) + sum_{j: idx2[b,j]=i} 2 g2[b,j] (x_i - y_j)
+ *   grad_y[b,j] = 2 g2[b,j] (y_j - x_idx2[b,j]) + sum_{i: idx1[b,i]=j} 2 g1[b,i] (y_j - x_i)
+ * grad_x [B,N,3], grad_y [B,M,3] contiguous; they are OVERWRITTEN (zeroed inside the call, then accumulated with
+ * warp-aggregated atomics).  Either may be NULL when that cloud needs no gradient. */
+int rma_chamfer_backward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                         const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
+                         int B, int N, int M,
+                         const float* g1, const float* g2, const int32_t* idx1, const int32_t* idx2,
+                         float* grad_x, float* grad_y, void* stream);
+
+/* Full squared-distance map, difference form: out[b,i,j] = |x[b,i]-y[b,j]|^2, contiguous [B,N,M].
+ * Kept only so that `compute_sqrdis_map` (loss.py:45-58) stays callable; the hot path never uses it. */
+int rma_sqrdis_map(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                   const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
+                   int B, int N, int M, float* out, void* stream);
+
+/* Packed (distance,index) keys for the source-sharded huge-pair mode: key = float_bits(d) << 32 |
+ * (idx + idx_offset).  d >= 0, so unsigned (and signed int64) order == (distance, then index) order and an
+ * all-reduce-MIN over ranks merges the target->source direction with torch's lowest-index tie break. */
+int rma_pack_min_keys(const float* dist, const int32_t* idx, int64_t n, int32_t idx_offset, uint64_t* keys,
+                      void* stream);
+int rma_unpack_min_keys(const uint64_t* keys, int64_t n, float* dist, int32_t* idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * se(3) exponential map.  Replaces LieAlgebra.se3.exp / ExpMap.forward (model/LieAlgebra/se3.py:51-74, 123-131)
+ * with sinc1/2/3 and their |t| < 0.01 Taylor branches (sinc.py:5-17, 91-103, 120-132).
+ * x [n,6] contiguous (w1,w2,w3,v1,v2,v3) -> g [n,4,4] contiguous, bottom row (0,0,0,1). */
+int rma_se3_exp_forward(const float* x, int64_t n, float* g, void* stream);
+
+/* ExpMap.backward (se3.py:133-152): grad_x[k] = sum_ij grad_g[i,j] (gen_k g)[i,j] — the left-perturbation derivative,
+ * NOT the Jacobian of exp.  Closed form: grad_w = sum_c g[:3,c] x grad_g[:3,c],
+ * grad_v = grad_g[:3,3].  x [n,6], grad_g [n,4,4] contiguous -> grad_x [n,6]. */
+int rma_se3_exp_backward(const float* x, const float* grad_g, int64_t n, float* grad_x, void* stream);
+
+/* se3.transform (se3.py:102-112): out = R a + p with R = g[:3,:3], p = g[:3,3].
+ * g [G,4,4] contiguous; point (t, k) for t < G, k < P uses transform t.  a / out / grads are addressed as
+ * base + t*s_t + k*s_k + c*s_c (c = coordinate), which covers both reference branches:
+ *   g.dim()==a.dim():  a [*,3,N]  -> s_t = 3N, s_k = 1, s_c = N        (se3.py:108-109)
+ *   else:              a [*,3]    -> g broadcast over P points: s_k = 3, s_c = 1 (hot call: g [B,1,4,4], a [B,N,3],
+ *                                    network.py:569, 654, 843) or per-point transforms with P = 1. */
+int rma_se3_transform_forward(const float* g, const float* a, int64_t a_st, int64_t a_sk, int64_t a_sc,
+                              int64_t G, int64_t P, float* out, int64_t o_st, int64_t o_sk, int64_t o_sc,
+                              void* stream);
+/* Backward of transform (torch matmul autograd in the reference): grad_a = R^T go; grad_g[:3,:3] = sum_k go a^T;
+ * grad_g[:3,3] = sum_k go; grad_g[3,:] = 0.  grad_g [G,4,4] contiguous (overwritten), grad_a strided like a.
+ * Either output may be NULL. */
+int rma_se3_transform_backward(const float* g, const float* a, int64_t a_st, int64_t a_sk, int64_t a_sc,
+                               const float* go, int64_t go_st, int64_t go_sk, int64_t go_sc,
+                               int64_t G, int64_t P, float* grad_g,
+                               float* grad_a, int64_t ga_st, int64_t ga_sk, int64_t ga_sc, void* stream);
+
+/* Fused recurrent-loop warp (model/network.py:652-655; stage 0: 567-570; rigid net: 840-843):
+ *   g = exp(phi[b]);  rigid = R src[b,k] + p;  out[b,k] = w ? w[b,k]*rigid + (1-w[b,k])*prev[b,k] : rigid
+ * phi [B,6] contiguous; src/prev/out [B,N,3] with element strides (sb, sn, sc); w [B,N] contiguous or NULL
+ * (then prev is ignored: stage 0 / rigid net).  g_out [B,4,4] (optional) receives exp(phi) (rigid_matrix_list);
+ * rigid_out (optional, same strides as out) receives the un-blended rigid points (deform_rigid_points_list). */
+int rma_warp_forward(const float* phi, const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                     const float* w, const float* prev, int64_t p_sb, int64_t p_sn, int64_t p_sc,
+                     int B, int N, float* out, int64_t o_sb, int64_t o_sn, int64_t o_sc,
+                     float* g_out, float* rigid_out, void* stream);
+/* Backward of the fused warp w.r.t. phi and w (prev is detached in the reference, network.py:606; src is data):
+ *   grad_w[b,k] = sum_c go[b,k,c] (rigid_c - prev_c);  grad_rigid = w*go (or go);  then transform backward and
+ *   ExpMap.backward chained:  grad_phi [B,6] (overwritten).  grad_src (optional, strided like src) = R^T grad_rigid.
+ * scratch: B*12 floats, zeroed inside the call. */
+int rma_warp_backward(const float* phi, const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
+                      const float* w, const float* prev, int64_t p_sb, int64_t p_sn, int64_t p_sc,
+                      const float* go, int64_t g_sb, int64_t g_sn, int64_t g_sc,
+                      int B, int N, float* grad_phi, float* grad_w,
+                      float* grad_src, int64_t gs_sb, int64_t gs_sn, int64_t gs_sc,
+                      float* scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Host-buffer convenience entry (what a non-torch FFI binding would call): pageable or pinned HOST pointers,
+ * contiguous [B,N,3] / [B,M,3]; allocates device memory, copies in, runs forward (+ backward of
+ * loss_on_cd = 0.5 (sum dist1 + sum dist2) / B, loss.py:200-205, when grad pointers are non-NULL), copies out and
+ * synchronises.  loss_host receives the scalar. */
+int rma_chamfer_loss_host(const float* x_host, const float* y_host, int B, int N, int M,
+                          float* loss_host, float* dist1_host, float* dist2_host,
+                          int32_t* idx1_host, int32_t* idx2_host, float* grad_x_host, float* grad_y_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMA_B200_H_ */

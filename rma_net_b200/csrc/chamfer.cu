@@ -1,0 +1,703 @@
+// Batched chamfer nearest-neighbour search (both directions) + backward scatter for B200 (sm_100a).
+//
+// Replaces compute_sqrdis_map / chamfer_dist (reference model/loss.py:45-58, 60-70) and their implicit autograd
+// (SURVEY.md §8a rows a1-a4).  The [B,N,M] distance matrix is never materialised.  See DESIGN.md §3-§4.
+//
+// Pipeline of one forward call (3 launches on the caller's stream):
+//   1. chamfer_prep_kernel     strided AoS inputs -> register/TMA-friendly packs in the workspace, best-key init
+//   2. chamfer_search_kernel   every pair distance evaluated ONCE (packed fp32x2 difference form) and used for
+//                              both directions: running row minima stay in registers, column minima go through a
+//                              per-warp shared-memory transpose; winners are merged with 64-bit atomicMin on
+//                              (distance bits << 32 | coarse index) keys
+//   3. chamfer_finalize_kernel resolves the coarse index (a 32-column tile / a 16-row group) to the exact first
+//                              minimum by re-evaluating that tile with the identical operation order
+// Backward: memset + one scatter kernel with warp-aggregated atomics.
+#include "common.cuh"
+#include "../../include/rma_b200.h"
+
+#include <cstdio>
+
+namespace rma {
+
+constexpr int kRowsPerThread = 16;                      // R: source points held in registers per thread
+constexpr int kRowsPerWarp = 32 * kRowsPerThread;       // 512: one "row block"
+constexpr int kSearchWarps = 4;                         // warps per CTA (one per SM sub-partition)
+constexpr int kSearchThreads = 32 * kSearchWarps;
+constexpr int kRowsPerCta = kRowsPerWarp * kSearchWarps;  // 2048
+constexpr int kTile = 32;                               // columns per tile (= lanes, for the column transpose)
+constexpr int kChunk = 1024;                            // columns staged in shared memory at a time
+constexpr int kCbStride = 33;                           // padded row of the per-warp column-min transpose buffer
+constexpr float kRowSentinel = 1e18f;                   // padded source rows:  d ~ 3e36 against real targets
+constexpr float kColSentinelNeg = 3e18f;                // padded target columns (stored negated): d ~ 2.7e37
+
+struct Geometry {
+  int B, N, M;
+  int nRB;    // row blocks (512 rows) per batch element
+  int Npad;   // nRB * 512
+  int nRBC;   // CTA row blocks (2048 rows) per batch element
+  int Mp;     // padded column count: roundup(M, 32) + 32
+  __host__ __device__ size_t rowpack_floats() const { return (size_t)B * Npad * 3; }
+  __host__ __device__ size_t colpack_float4() const { return (size_t)B * Mp * 2; }
+};
+
+static Geometry make_geometry(int B, int N, int M) {
+  Geometry g;
+  g.B = B; g.N = N; g.M = M;
+  g.nRB = (N + kRowsPerWarp - 1) / kRowsPerWarp;
+  g.Npad = g.nRB * kRowsPerWarp;
+  g.nRBC = (g.nRB + kSearchWarps - 1) / kSearchWarps;
+  g.Mp = (M + kTile - 1) / kTile * kTile + kTile;
+  return g;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct Workspace {
+  float* rowpack;   // [B][nRB][12][32] float4 : per-thread 16 rows as x[16], y[16], z[16], lane-coalesced
+  float4* colpack;  // [B][Mp][2] float4       : (-x,-x,-y,-y), (-z,-z,0,0)
+  u64* rowbest;     // [B][Npad]               : (dist bits << 32) | tile start column
+  u64* colbest;     // [B][Mp]                 : (dist bits << 32) | 16-row group id
+  size_t bytes;
+};
+
+static Workspace carve(const Geometry& g, void* base) {
+  Workspace w;
+  char* p = (char*)base;
+  size_t off = 0;
+  w.rowpack = (float*)(p + off);  off += align256(g.rowpack_floats() * sizeof(float));
+  w.colpack = (float4*)(p + off); off += align256(g.colpack_float4() * sizeof(float4));
+  w.rowbest = (u64*)(p + off);    off += align256((size_t)g.B * g.Npad * sizeof(u64));
+  w.colbest = (u64*)(p + off);    off += align256((size_t)g.B * g.Mp * sizeof(u64));
+  w.bytes = off;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 1. prep
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chamfer_prep_kernel(
+    const float* __restrict__ x, long long xsb, long long xsn, long long xsc,
+    const float* __restrict__ y, long long ysb, long long ysn, long long ysc,
+    Geometry g, Workspace w) {
+  const long long nrow = (long long)g.B * g.Npad;
+  const long long ncol = (long long)g.B * g.Mp;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nrow + ncol;
+       t += (long long)gridDim.x * blockDim.x) {
+    if (t < nrow) {
+      const int b = (int)(t / g.Npad), i = (int)(t % g.Npad);
+      float px = kRowSentinel, py = kRowSentinel, pz = kRowSentinel;
+      if (i < g.N) {
+        const float* s = x + b * xsb + i * xsn;
+        px = s[0]; py = s[xsc]; pz = s[2 * xsc];
+      }
+      const int rb = i / kRowsPerWarp, lane = (i % kRowsPerWarp) / kRowsPerThread, r = i % kRowsPerThread;
+      // float4 slot q = c*4 + r/4 of this (row block, lane); element r%4
+      const size_t base = ((size_t)(b * g.nRB + rb) * 12) * 32 + lane;
+      const int q = r >> 2, e = r & 3;
+      w.rowpack[(base + (size_t)(q)*32) * 4 + e] = px;
+      w.rowpack[(base + (size_t)(4 + q) * 32) * 4 + e] = py;
+      w.rowpack[(base + (size_t)(8 + q) * 32) * 4 + e] = pz;
+      w.rowbest[t] = ~0ull;
+    } else {
+      const long long u = t - nrow;
+      const int b = (int)(u / g.Mp), j = (int)(u % g.Mp);
+      float nx = kColSentinelNeg, ny = kColSentinelNeg, nz = kColSentinelNeg;
+      if (j < g.M) {
+        const float* s = y + b * ysb + j * ysn;
+        nx = -s[0]; ny = -s[ysc]; nz = -s[2 * ysc];
+      }
+      w.colpack[2 * u] = make_float4(nx, nx, ny, ny);
+      w.colpack[2 * u + 1] = make_float4(nz, nz, 0.f, 0.f);
+      w.colbest[u] = ~0ull;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2. search
+// ---------------------------------------------------------------------------------------------------------------
+// One column against the thread's 16 rows (8 packed row pairs): 3 FADD2 + FMUL2 + 2 FFMA2 per row pair.
+// Returns the minimum over the 16 rows (7 FMNMX3 + 1 FMNMX).
+__device__ __forceinline__ float column_step(const u64 (&px)[8], const u64 (&py)[8], const u64 (&pz)[8],
+                                             u64 cx, u64 cy, u64 cz, float (&d)[16]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const u64 dx = add2(px[k], cx), dy = add2(py[k], cy), dz = add2(pz[k], cz);
+    u64 t = mul2(dx, dx);
+    t = fma2(dy, dy, t);
+    t = fma2(dz, dz, t);
+    unpack2(t, d[2 * k], d[2 * k + 1]);
+  }
+  const float t0 = min3(d[0], d[1], d[2]);
+  const float t1 = min3(d[3], d[4], d[5]);
+  const float t2 = min3(d[6], d[7], d[8]);
+  const float t3 = min3(d[9], d[10], d[11]);
+  const float t4 = min3(d[12], d[13], d[14]);
+  const float u0 = min3(t0, t1, d[15]);
+  const float u1 = min3(t2, t3, t4);
+  return fminf(u0, u1);
+}
+
+struct SearchArgs {
+  const float4* rowpack;
+  const float4* colpack;
+  u64* rowbest;
+  u64* colbest;
+  int N, M, nRB, Npad, nRBC, Mp, S;
+};
+
+__global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(SearchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* scol = reinterpret_cast<float4*>(smem_raw);                               // [kChunk][2]
+  float* cball = reinterpret_cast<float*>(smem_raw + (size_t)kChunk * 2 * sizeof(float4));  // [warps][32][33]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.x % a.S;
+  const int rbc = (blockIdx.x / a.S) % a.nRBC;
+  const int b = blockIdx.x / (a.S * a.nRBC);
+  const int rb = rbc * kSearchWarps + warp;
+  const bool has_rows = rb < a.nRB;   // warp-uniform
+  const int c0 = (int)((long long)s * a.M / a.S);
+  const int c1 = (int)((long long)(s + 1) * a.M / a.S);
+  const int ncols = (c1 - c0 + kTile - 1) / kTile * kTile;   // tiles may overrun c1 (into real or sentinel columns)
+
+  float* cb = cball + warp * (kTile * kCbStride);
+
+  // The thread's 16 source points, packed as row pairs (2k, 2k+1).
+  u64 px[8], py[8], pz[8];
+  float m[kRowsPerThread];
+  int mt[kRowsPerThread];
+  if (has_rows) {
+    const float4* rp = a.rowpack + ((size_t)(b * a.nRB + rb) * 12) * 32 + lane;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 vx = rp[(size_t)q * 32], vy = rp[(size_t)(4 + q) * 32], vz = rp[(size_t)(8 + q) * 32];
+      px[2 * q] = pack2(vx.x, vx.y); px[2 * q + 1] = pack2(vx.z, vx.w);
+      py[2 * q] = pack2(vy.x, vy.y); py[2 * q + 1] = pack2(vy.z, vy.w);
+      pz[2 * q] = pack2(vz.x, vz.y); pz[2 * q + 1] = pack2(vz.z, vz.w);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kRowsPerThread; ++r) { m[r] = __int_as_float(0x7f800000); mt[r] = 0; }
+
+  const float4* cp = a.colpack + ((size_t)b * a.Mp + c0) * 2;
+
+  for (int cs = 0; cs < ncols; cs += kChunk) {
+    const int nc = min(kChunk, ncols - cs);
+    __syncthreads();   // previous chunk fully consumed
+    for (int idx = tid; idx < nc * 2; idx += kSearchThreads) scol[idx] = cp[(size_t)cs * 2 + idx];
+    __syncthreads();
+    if (!has_rows) continue;
+
+#pragma unroll 1
+    for (int t0 = 0; t0 < nc; t0 += kTile) {
+      float tm[kRowsPerThread];
+#pragma unroll
+      for (int r = 0; r < kRowsPerThread; ++r) tm[r] = __int_as_float(0x7f800000);
+      const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(scol + (size_t)t0 * 2);
+
+#pragma unroll 2
+      for (int jj = 0; jj < kTile; jj += 2) {
+        const ulonglong2 a0 = sp[2 * jj];
+        const u64 az = *reinterpret_cast<const u64*>(&sp[2 * jj + 1]);
+        const ulonglong2 b0 = sp[2 * jj + 2];
+        const u64 bz = *reinterpret_cast<const u64*>(&sp[2 * jj + 3]);
+        float dA[16], dB[16];
+        const float cmA = column_step(px, py, pz, a0.x, a0.y, az, dA);
+        const float cmB = column_step(px, py, pz, b0.x, b0.y, bz, dB);
+#pragma unroll
+        for (int r = 0; r < kRowsPerThread; ++r) tm[r] = min3(tm[r], dA[r], dB[r]);
+        cb[jj * kCbStride + lane] = cmA;
+        cb[(jj + 1) * kCbStride + lane] = cmB;
+      }
+
+      // Row direction: strict '<' keeps the earliest tile on ties (lowest index, torch.min semantics).
+      const int tile_start = c0 + cs + t0;
+#pragma unroll
+      for (int r = 0; r < kRowsPerThread; ++r) {
+        const bool better = tm[r] < m[r];
+        m[r] = better ? tm[r] : m[r];
+        mt[r] = better ? tile_start : mt[r];
+      }
+
+      // Column direction: lane l reduces column (tile_start + l) over the 32 lanes' partial minima.
+      __syncwarp();
+      {
+        const float* col = cb + lane * kCbStride;
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = col[k];
+        float mm = v[31];
+#pragma unroll
+        for (int k = 0; k < 30; k += 2) mm = min3(mm, v[k], v[k + 1]);
+        mm = fminf(mm, v[30]);
+        int id = 31;
+#pragma unroll
+        for (int k = 30; k >= 0; --k) id = (v[k] == mm) ? k : id;   // lowest lane attaining the minimum
+        const int j = tile_start + lane;
+        if (j < c1) {
+          const u64 key = ((u64)__float_as_uint(mm) << 32) | (unsigned)(rb * 32 + id);
+          atomicMin(a.colbest + (size_t)b * a.Mp + j, key);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  if (has_rows) {
+    const int i0 = rb * kRowsPerWarp + lane * kRowsPerThread;
+    u64* rbest = a.rowbest + (size_t)b * a.Npad + i0;
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; ++r) {
+      if (i0 + r < a.N) atomicMin(rbest + r, ((u64)__float_as_uint(m[r]) << 32) | (unsigned)mt[r]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3. finalize: coarse winner -> exact (distance, first index)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) chamfer_finalize_kernel(
+    Geometry g, Workspace w, float* __restrict__ dist1, float* __restrict__ dist2,
+    int* __restrict__ idx1, int* __restrict__ idx2) {
+  const long long nrow = (long long)g.B * g.N;
+  const long long ncol = (long long)g.B * g.M;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nrow) {
+    const int b = (int)(t / g.N), i = (int)(t % g.N);
+    const u64 key = w.rowbest[(size_t)b * g.Npad + i];
+    const int jt = (int)(unsigned)(key & 0xffffffffu);
+    const int rb = i / kRowsPerWarp, lane = (i % kRowsPerWarp) / kRowsPerThread, r = i % kRowsPerThread;
+    const size_t base = ((size_t)(b * g.nRB + rb) * 12) * 32 + lane;
+    const int q = r >> 2, e = r & 3;
+    const float x = w.rowpack[(base + (size_t)q * 32) * 4 + e];
+    const float y = w.rowpack[(base + (size_t)(4 + q) * 32) * 4 + e];
+    const float z = w.rowpack[(base + (size_t)(8 + q) * 32) * 4 + e];
+    const float4* cp = w.colpack + ((size_t)b * g.Mp + jt) * 2;
+    float best = __int_as_float(0x7f800000);
+    int bj = jt;
+#pragma unroll 4
+    for (int k = 0; k < kTile; ++k) {
+      const float4 c0 = cp[2 * k], c1 = cp[2 * k + 1];
+      const float d = sqdist_neg(x, y, z, c0.x, c0.z, c1.x);
+      if (d < best) { best = d; bj = jt + k; }
+    }
+    dist1[t] = best;
+    if (idx1) idx1[t] = bj;
+  } else if (t < nrow + ncol) {
+    const long long u = t - nrow;
+    const int b = (int)(u / g.M), j = (int)(u % g.M);
+    const u64 key = w.colbest[(size_t)b * g.Mp + j];
+    const int grp = (int)(unsigned)(key & 0xffffffffu);
+    const int rb = grp >> 5, lane = grp & 31;
+    const float4 c0 = w.colpack[((size_t)b * g.Mp + j) * 2], c1 = w.colpack[((size_t)b * g.Mp + j) * 2 + 1];
+    const float4* rp = reinterpret_cast<const float4*>(w.rowpack) + ((size_t)(b * g.nRB + rb) * 12) * 32 + lane;
+    float best = __int_as_float(0x7f800000);
+    int bi = grp * kRowsPerThread;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 vx = rp[(size_t)q * 32], vy = rp[(size_t)(4 + q) * 32], vz = rp[(size_t)(8 + q) * 32];
+      const float xs[4] = {vx.x, vx.y, vx.z, vx.w}, ys[4] = {vy.x, vy.y, vy.z, vy.w},
+                  zs[4] = {vz.x, vz.y, vz.z, vz.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d = sqdist_neg(xs[e], ys[e], zs[e], c0.x, c0.z, c1.x);
+        if (d < best) { best = d; bi = grp * kRowsPerThread + q * 4 + e; }
+      }
+    }
+    dist2[u] = best;
+    if (idx2) idx2[u] = bi;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward: gradient scatter with warp-aggregated atomics
+// ---------------------------------------------------------------------------------------------------------------
+// Sum (vx,vy,vz) over the lanes that share a key; the result is valid on the lowest lane of each peer group.
+__device__ __forceinline__ void reduce_peers(unsigned peers, float& vx, float& vy, float& vz) {
+  const unsigned lane = lane_id();
+  unsigned rel = __popc(peers & ((1u << lane) - 1u));
+  unsigned higher = peers & ~((2u << lane) - 1u);
+  while (__any_sync(0xffffffffu, higher != 0)) {
+    const int next = __ffs(higher);
+    const int src = next ? next - 1 : (int)lane;
+    const float tx = __shfl_sync(0xffffffffu, vx, src);
+    const float ty = __shfl_sync(0xffffffffu, vy, src);
+    const float tz = __shfl_sync(0xffffffffu, vz, src);
+    if (next) { vx += tx; vy += ty; vz += tz; }
+    const unsigned done = __ballot_sync(0xffffffffu, rel & 1u);
+    higher &= ~done;
+    rel >>= 1;
+  }
+}
+
+__global__ void __launch_bounds__(256) chamfer_backward_kernel(
+    const float* __restrict__ x, long long xsb, long long xsn, long long xsc,
+    const float* __restrict__ y, long long ysb, long long ysn, long long ysc,
+    int B, int N, int M, const float* __restrict__ g1, const float* __restrict__ g2,
+    const int* __restrict__ idx1, const int* __restrict__ idx2, float* __restrict__ grad_x,
+    float* __restrict__ grad_y) {
+  const long long nrow = (long long)B * N, ncol = (long long)B * M;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // grid covers whole warps
+  // Every lane of the warp takes part in the match/shuffle; out-of-range or zero-gradient lanes carry a unique
+  // negative key and contribute nothing.
+  float vx = 0.f, vy = 0.f, vz = 0.f;
+  long long key = -1 - (long long)lane_id();
+  float* own = nullptr;
+  float* other = nullptr;
+  bool live = false;
+  if (t < nrow) {
+    if (g1) {
+      const int b = (int)(t / N), i = (int)(t % N);
+      const int j = idx1[t];
+      const float gg = 2.f * g1[t];
+      const float* p = x + b * xsb + i * xsn;
+      const float* q = y + b * ysb + j * ysn;
+      vx = gg * (p[0] - q[0]); vy = gg * (p[xsc] - q[ysc]); vz = gg * (p[2 * xsc] - q[2 * ysc]);
+      own = grad_x ? grad_x + t * 3 : nullptr;
+      other = grad_y ? grad_y + ((long long)b * M + j) * 3 : nullptr;
+      key = (long long)b * M + j;
+      live = true;
+    }
+  } else if (t < nrow + ncol) {
+    if (g2) {
+      const long long u = t - nrow;
+      const int b = (int)(u / M), j = (int)(u % M);
+      const int i = idx2[u];
+      const float gg = 2.f * g2[u];
+      const float* p = y + b * ysb + j * ysn;
+      const float* q = x + b * xsb + i * xsn;
+      vx = gg * (p[0] - q[0]); vy = gg * (p[ysc] - q[xsc]); vz = gg * (p[2 * ysc] - q[2 * xsc]);
+      own = grad_y ? grad_y + u * 3 : nullptr;
+      other = grad_x ? grad_x + ((long long)b * N + i) * 3 : nullptr;
+      key = nrow + (long long)b * N + i;   // disjoint key space from the x->y half (a warp can straddle both)
+      live = true;
+    }
+  }
+  if (live && own) {   // own-point term: one writer per address from this half, the other half scatters into it
+    atomicAdd(own + 0, vx); atomicAdd(own + 1, vy); atomicAdd(own + 2, vz);
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  float sx = -vx, sy = -vy, sz = -vz;
+  if (__any_sync(0xffffffffu, peers != (1u << lane_id()))) reduce_peers(peers, sx, sy, sz);   // warp-uniform
+  const bool leader = (unsigned)(__ffs(peers) - 1) == lane_id();
+  if (live && other && leader) {
+    atomicAdd(other + 0, sx); atomicAdd(other + 1, sy); atomicAdd(other + 2, sz);
+  }
+}
+
+__global__ void __launch_bounds__(256) sqrdis_map_kernel(
+    const float* __restrict__ x, long long xsb, long long xsn, long long xsc,
+    const float* __restrict__ y, long long ysb, long long ysn, long long ysc,
+    int B, int N, int M, float* __restrict__ out) {
+  const long long total = (long long)B * N * M;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(t % M);
+    const long long bi = t / M;
+    const int i = (int)(bi % N), b = (int)(bi / N);
+    const float* p = x + b * xsb + i * xsn;
+    const float* q = y + b * ysb + j * ysn;
+    out[t] = sqdist_neg(p[0], p[xsc], p[2 * xsc], -q[0], -q[ysc], -q[2 * ysc]);
+  }
+}
+
+__global__ void pack_keys_kernel(const float* __restrict__ dist, const int* __restrict__ idx, long long n,
+                                 int off, u64* __restrict__ keys) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) keys[t] = ((u64)__float_as_uint(dist[t]) << 32) | (unsigned)(idx[t] + off);
+}
+__global__ void unpack_keys_kernel(const u64* __restrict__ keys, long long n, float* __restrict__ dist,
+                                   int* __restrict__ idx) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    const u64 k = keys[t];
+    dist[t] = __uint_as_float((unsigned)(k >> 32));
+    idx[t] = (int)(unsigned)(k & 0xffffffffu);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+constexpr size_t kSearchSmem = (size_t)kChunk * 2 * sizeof(float4) + (size_t)kSearchWarps * kTile * kCbStride * sizeof(float);
+
+struct DeviceCaps { int sms; int search_occ; };
+
+static int get_caps(DeviceCaps* out) {
+  // Re-queried per call (a few microseconds of host time, no device work): keeps the library free of global
+  // state so that it is safe across devices and threads.
+  int dev = 0;
+  RMA_CUDA_TRY(cudaGetDevice(&dev));
+  RMA_CUDA_TRY(cudaDeviceGetAttribute(&out->sms, cudaDevAttrMultiProcessorCount, dev));
+  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kSearchSmem));
+  RMA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out->search_occ, chamfer_search_kernel,
+                                                             kSearchThreads, kSearchSmem));
+  if (out->search_occ < 1) out->search_occ = 1;
+  return 0;
+}
+
+// Number of column splits S: CTAs = B * nRBC * S, each sweeping ~M/S columns for its 2048 rows.  Co-resident CTAs
+// share the SM's FP32 pipe, so time ~ ceil(CTAs / SMs) * (columns per CTA + fixed per-CTA overhead).
+static int choose_splits(const Geometry& g, const DeviceCaps& caps) {
+  const long long base = (long long)g.B * g.nRBC;
+  const int smax = g.M / 64 > 1 ? (g.M / 64 < 4096 ? g.M / 64 : 4096) : 1;
+  const double overhead_cols = 40.0;
+  double best_cost = 1e300;
+  int best = 1;
+  for (int s = 1; s <= smax; ++s) {
+    const long long ctas = base * s;
+    const long long per_sm = (ctas + caps.sms - 1) / caps.sms;
+    double cost = (double)per_sm * ((double)((g.M + s - 1) / s) + overhead_cols);
+    if (per_sm == 1) cost *= 1.05;   // a single warp per sub-partition hides less latency
+    if (cost < best_cost * 0.999) { best_cost = cost; best = s; }
+    if (ctas > 64LL * caps.sms) break;
+  }
+  return best;
+}
+
+static int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > 0x7fffffffLL) g = 0x7fffffffLL;
+  return (int)g;
+}
+
+}  // namespace rma
+
+using namespace rma;
+
+extern "C" {
+
+int rma_b200_abi_version(void) { return RMA_B200_ABI_VERSION; }
+
+const char* rma_b200_error_string(int code) {
+  if (code == RMA_OK) return "ok";
+  if (code == RMA_E_BADARG) return "rma_b200: bad argument (null pointer, non-positive size or size overflow)";
+  if (code == RMA_E_WORKSPACE) return "rma_b200: workspace too small or not 256-byte aligned";
+  if (code == RMA_E_ARCH) return "rma_b200: device is not sm_100 (B200)";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "rma_b200: unknown error";
+}
+
+int rma_b200_device_info(int* sm_count, int* clock_khz, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  RMA_CUDA_TRY(cudaGetDevice(&dev));
+  if (sm_count) RMA_CUDA_TRY(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (clock_khz) RMA_CUDA_TRY(cudaDeviceGetAttribute(clock_khz, cudaDevAttrClockRate, dev));
+  if (cc_major) RMA_CUDA_TRY(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_minor) RMA_CUDA_TRY(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return RMA_OK;
+}
+
+static bool sizes_ok(int B, int N, int M) {
+  if (B <= 0 || N <= 0 || M <= 0) return false;
+  // int32 point indices inside the kernels: padded per-batch sizes must fit, total slots use 64-bit.
+  if ((long long)N > (1LL << 30) || (long long)M > (1LL << 30)) return false;
+  if ((long long)B * ((long long)N + kRowsPerWarp) >= (1LL << 31) / 12) return false;
+  if ((long long)B * ((long long)M + 2 * kTile) >= (1LL << 31) / 2) return false;
+  return true;
+}
+
+size_t rma_chamfer_workspace_bytes(int B, int N, int M) {
+  if (!sizes_ok(B, N, M)) return 0;
+  const Geometry g = make_geometry(B, N, M);
+  return carve(g, nullptr).bytes;
+}
+
+static int forward_setup(const float* x, const float* y, int B, int N, int M, void* workspace,
+                         size_t workspace_bytes, Geometry* g, Workspace* w) {
+  if (!x || !y || !workspace || !sizes_ok(B, N, M)) return RMA_E_BADARG;
+  *g = make_geometry(B, N, M);
+  if (((uintptr_t)workspace & 255u) != 0) return RMA_E_WORKSPACE;
+  *w = carve(*g, workspace);
+  if (workspace_bytes < w->bytes) return RMA_E_WORKSPACE;
+  return RMA_OK;
+}
+
+int rma_chamfer_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                     const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
+                     int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream_) {
+  Geometry g; Workspace w;
+  if (int e = forward_setup(x, y, B, N, M, workspace, workspace_bytes, &g, &w)) return e;
+  const long long slots = (long long)B * (g.Npad + g.Mp);
+  chamfer_prep_kernel<<<grid_for(slots, 256), 256, 0, (cudaStream_t)stream_>>>(x, xsb, xsn, xsc, y, ysb, ysn, ysc,
+                                                                               g, w);
+  RMA_LAUNCH_CHECK();
+  return RMA_OK;
+}
+
+int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream_) {
+  Geometry g; Workspace w;
+  if (int e = forward_setup((const float*)workspace, (const float*)workspace, B, N, M, workspace, workspace_bytes,
+                            &g, &w)) return e;
+  DeviceCaps caps;
+  if (int e = get_caps(&caps)) return e;
+  SearchArgs a;
+  a.rowpack = reinterpret_cast<const float4*>(w.rowpack);
+  a.colpack = w.colpack;
+  a.rowbest = w.rowbest;
+  a.colbest = w.colbest;
+  a.N = N; a.M = M; a.nRB = g.nRB; a.Npad = g.Npad; a.nRBC = g.nRBC; a.Mp = g.Mp;
+  a.S = choose_splits(g, caps);
+  const long long ctas = (long long)B * g.nRBC * a.S;
+  if (ctas > 0x7fffffffLL) return RMA_E_BADARG;
+  chamfer_search_kernel<<<(int)ctas, kSearchThreads, kSearchSmem, (cudaStream_t)stream_>>>(a);
+  RMA_LAUNCH_CHECK();
+  return RMA_OK;
+}
+
+int rma_chamfer_finalize(int B, int N, int M, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
+                         void* workspace, size_t workspace_bytes, void* stream_) {
+  Geometry g; Workspace w;
+  if (!dist1 || !dist2) return RMA_E_BADARG;
+  if (int e = forward_setup((const float*)workspace, (const float*)workspace, B, N, M, workspace, workspace_bytes,
+                            &g, &w)) return e;
+  chamfer_finalize_kernel<<<grid_for((long long)B * ((long long)N + M), 128), 128, 0, (cudaStream_t)stream_>>>(
+      g, w, dist1, dist2, idx1, idx2);
+  RMA_LAUNCH_CHECK();
+  return RMA_OK;
+}
+
+int rma_chamfer_search_config(int B, int N, int M, int* ctas, int* threads, int* splits, int* ctas_per_sm) {
+  if (!sizes_ok(B, N, M)) return RMA_E_BADARG;
+  const Geometry g = make_geometry(B, N, M);
+  DeviceCaps caps;
+  if (int e = get_caps(&caps)) return e;
+  const int S = choose_splits(g, caps);
+  if (ctas) *ctas = B * g.nRBC * S;
+  if (threads) *threads = kSearchThreads;
+  if (splits) *splits = S;
+  if (ctas_per_sm) *ctas_per_sm = caps.search_occ;
+  return RMA_OK;
+}
+
+int rma_chamfer_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                        const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
+                        int B, int N, int M, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dist1 || !dist2) return RMA_E_BADARG;
+  if (int e = rma_chamfer_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, workspace, workspace_bytes, stream))
+    return e;
+  if (int e = rma_chamfer_search(B, N, M, workspace, workspace_bytes, stream)) return e;
+  return rma_chamfer_finalize(B, N, M, dist1, dist2, idx1, idx2, workspace, workspace_bytes, stream);
+}
+
+int rma_chamfer_backward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                         const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
+                         int B, int N, int M, const float* g1, const float* g2, const int32_t* idx1,
+                         const int32_t* idx2, float* grad_x, float* grad_y, void* stream_) {
+  if (!x || !y || !sizes_ok(B, N, M)) return RMA_E_BADARG;
+  if ((g1 && !idx1) || (g2 && !idx2)) return RMA_E_BADARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (grad_x) RMA_CUDA_TRY(cudaMemsetAsync(grad_x, 0, (size_t)B * N * 3 * sizeof(float), stream));
+  if (grad_y) RMA_CUDA_TRY(cudaMemsetAsync(grad_y, 0, (size_t)B * M * 3 * sizeof(float), stream));
+  if ((!grad_x && !grad_y) || (!g1 && !g2)) return RMA_OK;
+  const long long n = (long long)B * ((long long)N + M);
+  chamfer_backward_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, g1,
+                                                                g2, idx1, idx2, grad_x, grad_y);
+  RMA_LAUNCH_CHECK();
+  return RMA_OK;
+}
+
+int rma_sqrdis_map(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                   const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
+                   int B, int N, int M, float* out, void* stream_) {
+  if (!x || !y || !out || B <= 0 || N <= 0 || M <= 0) return RMA_E_BADARG;
+  const long long total = (long long)B * N * M;
+  long long grid = (total + 255) / 256;
+  if (grid > 148LL * 64) grid = 148LL * 64;
+  sqrdis_map_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream_>>>(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M,
+                                                                  out);
+  RMA_LAUNCH_CHECK();
+  return RMA_OK;
+}
+
+int rma_pack_min_keys(const float* dist, const int32_t* idx, int64_t n, int32_t idx_offset, uint64_t* keys,
+                      void* stream_) {
+  if (!dist || !idx || !keys || n <= 0) return RMA_E_BADARG;
+  pack_keys_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream_>>>(dist, idx, n, idx_offset, (u64*)keys);
+  RMA_LAUNCH_CHECK();
+  return RMA_OK;
+}
+
+int rma_unpack_min_keys(const uint64_t* keys, int64_t n, float* dist, int32_t* idx, void* stream_) {
+  if (!dist || !idx || !keys || n <= 0) return RMA_E_BADARG;
+  unpack_keys_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream_>>>((const u64*)keys, n, dist, idx);
+  RMA_LAUNCH_CHECK();
+  return RMA_OK;
+}
+
+// loss_on_cd reduction for the host-buffer entry: 0.5 * (sum d1 + sum d2) / B in double.
+__global__ void __launch_bounds__(256) loss_sum_kernel(const float* __restrict__ d1, long long n1,
+                                                       const float* __restrict__ d2, long long n2,
+                                                       double* __restrict__ acc) {
+  double s = 0.0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n1 + n2;
+       t += (long long)gridDim.x * blockDim.x)
+    s += (double)(t < n1 ? d1[t] : d2[t - n1]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane_id() == 0) atomicAdd(acc, s);
+}
+
+__global__ void fill_kernel(float* p, long long n, float v) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) p[t] = v;
+}
+
+int rma_chamfer_loss_host(const float* x_host, const float* y_host, int B, int N, int M, float* loss_host,
+                          float* dist1_host, float* dist2_host, int32_t* idx1_host, int32_t* idx2_host,
+                          float* grad_x_host, float* grad_y_host) {
+  if (!x_host || !y_host || !sizes_ok(B, N, M)) return RMA_E_BADARG;
+  const size_t nx = (size_t)B * N, ny = (size_t)B * M;
+  const size_t wsb = rma_chamfer_workspace_bytes(B, N, M);
+  const bool want_grad = grad_x_host || grad_y_host;
+  // one device allocation, carved
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+  const size_t o_x = take(nx * 12), o_y = take(ny * 12), o_d1 = take(nx * 4), o_d2 = take(ny * 4),
+               o_i1 = take(nx * 4), o_i2 = take(ny * 4), o_ws = take(wsb), o_acc = take(8),
+               o_g1 = take(want_grad ? nx * 4 : 0), o_g2 = take(want_grad ? ny * 4 : 0),
+               o_gx = take(want_grad ? nx * 12 : 0), o_gy = take(want_grad ? ny * 12 : 0);
+  char* d = nullptr;
+  RMA_CUDA_TRY(cudaMalloc((void**)&d, off));
+  cudaStream_t st = 0;
+  int rc = RMA_OK;
+  auto fail = [&](int e) { cudaFree(d); return e; };
+#define TRY_(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return fail((int)e__); } while (0)
+  TRY_(cudaMemcpyAsync(d + o_x, x_host, nx * 12, cudaMemcpyHostToDevice, st));
+  TRY_(cudaMemcpyAsync(d + o_y, y_host, ny * 12, cudaMemcpyHostToDevice, st));
+  rc = rma_chamfer_forward((float*)(d + o_x), (int64_t)N * 3, 3, 1, (float*)(d + o_y), (int64_t)M * 3, 3, 1, B, N, M,
+                           (float*)(d + o_d1), (float*)(d + o_d2), (int32_t*)(d + o_i1), (int32_t*)(d + o_i2),
+                           d + o_ws, wsb, st);
+  if (rc) return fail(rc);
+  TRY_(cudaMemsetAsync(d + o_acc, 0, 8, st));
+  loss_sum_kernel<<<148, 256, 0, st>>>((float*)(d + o_d1), (long long)nx, (float*)(d + o_d2), (long long)ny,
+                                       (double*)(d + o_acc));
+  if (want_grad) {
+    const float gval = 0.5f / (float)B;
+    fill_kernel<<<grid_for((long long)nx, 256), 256, 0, st>>>((float*)(d + o_g1), (long long)nx, gval);
+    fill_kernel<<<grid_for((long long)ny, 256), 256, 0, st>>>((float*)(d + o_g2), (long long)ny, gval);
+    rc = rma_chamfer_backward((float*)(d + o_x), (int64_t)N * 3, 3, 1, (float*)(d + o_y), (int64_t)M * 3, 3, 1, B, N,
+                              M, (float*)(d + o_g1), (float*)(d + o_g2), (int32_t*)(d + o_i1),
+                              (int32_t*)(d + o_i2), (float*)(d + o_gx), (float*)(d + o_gy), st);
+    if (rc) return fail(rc);
+  }
+  double acc = 0.0;
+  TRY_(cudaMemcpyAsync(&acc, d + o_acc, 8, cudaMemcpyDeviceToHost, st));
+  if (dist1_host) TRY_(cudaMemcpyAsync(dist1_host, d + o_d1, nx * 4, cudaMemcpyDeviceToHost, st));
+  if (dist2_host) TRY_(cudaMemcpyAsync(dist2_host, d + o_d2, ny * 4, cudaMemcpyDeviceToHost, st));
+  if (idx1_host) TRY_(cudaMemcpyAsync(idx1_host, d + o_i1, nx * 4, cudaMemcpyDeviceToHost, st));
+  if (idx2_host) TRY_(cudaMemcpyAsync(idx2_host, d + o_i2, ny * 4, cudaMemcpyDeviceToHost, st));
+  if (grad_x_host) TRY_(cudaMemcpyAsync(grad_x_host, d + o_gx, nx * 12, cudaMemcpyDeviceToHost, st));
+  if (grad_y_host) TRY_(cudaMemcpyAsync(grad_y_host, d + o_gy, ny * 12, cudaMemcpyDeviceToHost, st));
+  TRY_(cudaStreamSynchronize(st));
+#undef TRY_
+  if (loss_host) *loss_host = (float)(0.5 * acc / (double)B);
+  cudaFree(d);
+  return RMA_OK;
+}
+
+}  // extern "C"

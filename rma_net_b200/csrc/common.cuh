@@ -1,0 +1,70 @@
+// Shared device helpers for the B200 (sm_100a) chamfer / se(3) kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+typedef unsigned long long u64;
+
+#define RMA_CUDA_TRY(expr)                         \
+  do {                                             \
+    cudaError_t e__ = (expr);                      \
+    if (e__ != cudaSuccess) return (int)e__;       \
+  } while (0)
+
+// Launch-error check that does not synchronise (keeps calls asynchronous and graph-capturable).
+#define RMA_LAUNCH_CHECK()                         \
+  do {                                             \
+    cudaError_t e__ = cudaPeekAtLastError();       \
+    if (e__ != cudaSuccess) return (int)e__;       \
+  } while (0)
+
+namespace rma {
+
+// ---- packed fp32x2 arithmetic (sm_100+: FADD2 / FMUL2 / FFMA2). ------------------------------------------------
+// One instruction performs two IEEE-754 round-to-nearest fp32 operations (no ftz), bit-identical to the scalar
+// __fadd_rn / __fmul_rn / __fmaf_rn on each half; measured on B200 at the same FLOP rate as scalar FFMA with half
+// the issue slots (profiles/r01_fp32_microbench.jsonl), which is what leaves room for the min bookkeeping.
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// 3-input minimum (sm_100+: FMNMX3).
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// Scalar squared distance with the SAME operation order as the packed search loop, so that re-evaluating a
+// candidate reproduces the search kernel's value bit for bit:  dx*dx -> fma(dy,dy,.) -> fma(dz,dz,.).
+// `nyx` etc. are the NEGATED target coordinates (x + (-y) == x - y exactly in IEEE arithmetic).
+__device__ __forceinline__ float sqdist_neg(float x, float y, float z, float nyx, float nyy, float nyz) {
+  float dx = __fadd_rn(x, nyx), dy = __fadd_rn(y, nyy), dz = __fadd_rn(z, nyz);
+  float d = __fmul_rn(dx, dx);
+  d = __fmaf_rn(dy, dy, d);
+  d = __fmaf_rn(dz, dz, d);
+  return d;
+}
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+}  // namespace rma

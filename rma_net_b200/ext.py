@@ -1,0 +1,352 @@
+"""Tensor-level `forward` / `backward` entry points over the C ABI (include/rma_b200.h).
+
+This plays the role of the pybind11 modules of the reference's extension (`point_render.forward/backward`,
+model/exfunc/expackages/point_render/point_render.cpp:40-139): validate tensors the way CHECK_CUDA /
+CHECK_CONTIGUOUS do (point_render.cpp:21-27) — but raising instead of exiting, and accepting strided views —
+allocate outputs and scratch with torch, and hand raw device pointers + the current stream to the kernels.
+PyTorch is used for memory and streams only; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _check_points(name: str, t: torch.Tensor) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (rma_net_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    if t.dim() != 3 or t.shape[-1] != 3:
+        raise RuntimeError(f"{name} must have shape [B, N, 3], got {tuple(t.shape)}")
+
+
+def _same_device(*ts: torch.Tensor) -> None:
+    dev = ts[0].device
+    for t in ts[1:]:
+        if t is not None and t.device != dev:
+            raise RuntimeError("all tensors must be on the same CUDA device")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# chamfer
+# ------------------------------------------------------------------------------------------------------------
+def chamfer_workspace_bytes(B: int, N: int, M: int) -> int:
+    return int(_lib.load().rma_chamfer_workspace_bytes(B, N, M))
+
+
+def chamfer_forward(points_x: torch.Tensor, points_y: torch.Tensor, want_idx: bool = True):
+    """[B,N,3], [B,M,3] (any strides) -> dist1 [B,N], dist2 [B,M], idx1 [B,N] int32, idx2 [B,M] int32."""
+    _check_points("points_x", points_x)
+    _check_points("points_y", points_y)
+    _same_device(points_x, points_y)
+    B, N, M = points_x.shape[0], points_x.shape[1], points_y.shape[1]
+    if points_y.shape[0] != B:
+        raise RuntimeError(f"batch sizes differ: {B} vs {points_y.shape[0]}")
+    if B == 0 or N == 0 or M == 0:
+        raise RuntimeError("chamfer_dist needs non-empty point sets (min over an empty dimension)")
+    lib = _lib.load()
+    with torch.cuda.device(points_x.device):
+        wsb = lib.rma_chamfer_workspace_bytes(B, N, M)
+        if wsb == 0:
+            raise RuntimeError(f"problem size not supported: B={B}, N={N}, M={M}")
+        dev = points_x.device
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        dist1 = torch.empty((B, N), dtype=torch.float32, device=dev)
+        dist2 = torch.empty((B, M), dtype=torch.float32, device=dev)
+        idx1 = torch.empty((B, N), dtype=torch.int32, device=dev) if want_idx else None
+        idx2 = torch.empty((B, M), dtype=torch.int32, device=dev) if want_idx else None
+        xs, ys = points_x.stride(), points_y.stride()
+        rc = lib.rma_chamfer_forward(_ptr(points_x), xs[0], xs[1], xs[2], _ptr(points_y), ys[0], ys[1], ys[2],
+                                     B, N, M, _ptr(dist1), _ptr(dist2), _ptr(idx1), _ptr(idx2),
+                                     _ptr(ws), wsb, _stream())
+        _lib.check(rc, "rma_chamfer_forward")
+    return dist1, dist2, idx1, idx2
+
+
+def chamfer_backward(points_x, points_y, idx1, idx2, g1, g2, need_x: bool = True, need_y: bool = True):
+    """Returns (grad_x [B,N,3] or None, grad_y [B,M,3] or None)."""
+    _check_points("points_x", points_x)
+    _check_points("points_y", points_y)
+    B, N, M = points_x.shape[0], points_x.shape[1], points_y.shape[1]
+    dev = points_x.device
+    if g1 is not None:
+        g1 = g1.to(torch.float32).contiguous()
+    if g2 is not None:
+        g2 = g2.to(torch.float32).contiguous()
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        gx = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if need_x else None
+        gy = torch.empty((B, M, 3), dtype=torch.float32, device=dev) if need_y else None
+        xs, ys = points_x.stride(), points_y.stride()
+        rc = lib.rma_chamfer_backward(_ptr(points_x), xs[0], xs[1], xs[2], _ptr(points_y), ys[0], ys[1], ys[2],
+                                      B, N, M, _ptr(g1), _ptr(g2), _ptr(idx1), _ptr(idx2), _ptr(gx), _ptr(gy),
+                                      _stream())
+        _lib.check(rc, "rma_chamfer_backward")
+    return gx, gy
+
+
+def sqrdis_map(points_x: torch.Tensor, points_y: torch.Tensor) -> torch.Tensor:
+    _check_points("points_x", points_x)
+    _check_points("points_y", points_y)
+    B, N, M = points_x.shape[0], points_x.shape[1], points_y.shape[1]
+    if points_y.shape[0] != B:
+        raise RuntimeError(f"batch sizes differ: {B} vs {points_y.shape[0]}")
+    out = torch.empty((B, N, M), dtype=torch.float32, device=points_x.device)
+    if out.numel() == 0:
+        return out
+    xs, ys = points_x.stride(), points_y.stride()
+    with torch.cuda.device(points_x.device):
+        rc = _lib.load().rma_sqrdis_map(_ptr(points_x), xs[0], xs[1], xs[2], _ptr(points_y), ys[0], ys[1], ys[2],
+                                        B, N, M, _ptr(out), _stream())
+        _lib.check(rc, "rma_sqrdis_map")
+    return out
+
+
+def pack_min_keys(dist: torch.Tensor, idx: torch.Tensor, idx_offset: int = 0) -> torch.Tensor:
+    """(float32 d >= 0, int32 idx) -> int64 keys whose signed order is (d, idx) order."""
+    dist = dist.contiguous()
+    idx = idx.contiguous()
+    keys = torch.empty(dist.shape, dtype=torch.int64, device=dist.device)
+    with torch.cuda.device(dist.device):
+        rc = _lib.load().rma_pack_min_keys(_ptr(dist), _ptr(idx), dist.numel(), idx_offset, _ptr(keys), _stream())
+        _lib.check(rc, "rma_pack_min_keys")
+    return keys
+
+
+def unpack_min_keys(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    keys = keys.contiguous()
+    dist = torch.empty(keys.shape, dtype=torch.float32, device=keys.device)
+    idx = torch.empty(keys.shape, dtype=torch.int32, device=keys.device)
+    with torch.cuda.device(keys.device):
+        rc = _lib.load().rma_unpack_min_keys(_ptr(keys), keys.numel(), _ptr(dist), _ptr(idx), _stream())
+        _lib.check(rc, "rma_unpack_min_keys")
+    return dist, idx
+
+
+# ------------------------------------------------------------------------------------------------------------
+# se(3)
+# ------------------------------------------------------------------------------------------------------------
+def _check_f32_cuda(name: str, t: torch.Tensor, last: int) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (rma_net_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    if t.dim() < 1 or t.shape[-1] != last:
+        raise RuntimeError(f"{name} must have last dimension {last}, got {tuple(t.shape)}")
+
+
+def se3_exp_forward(x: torch.Tensor) -> torch.Tensor:
+    """[*,6] -> [*,4,4]"""
+    _check_f32_cuda("x", x, 6)
+    xc = x.contiguous().view(-1, 6)
+    n = xc.shape[0]
+    g = torch.empty((n, 4, 4), dtype=torch.float32, device=x.device)
+    if n:
+        with torch.cuda.device(x.device):
+            rc = _lib.load().rma_se3_exp_forward(_ptr(xc), n, _ptr(g), _stream())
+            _lib.check(rc, "rma_se3_exp_forward")
+    return g.view(*x.shape[:-1], 4, 4)
+
+
+def se3_exp_backward(x: torch.Tensor, grad_g: torch.Tensor) -> torch.Tensor:
+    _check_f32_cuda("x", x, 6)
+    xc = x.contiguous().view(-1, 6)
+    n = xc.shape[0]
+    go = grad_g.to(torch.float32).contiguous().view(-1, 4, 4)
+    if go.shape[0] != n:
+        raise RuntimeError("grad_output does not match x")
+    gx = torch.empty((n, 6), dtype=torch.float32, device=x.device)
+    if n:
+        with torch.cuda.device(x.device):
+            rc = _lib.load().rma_se3_exp_backward(_ptr(xc), _ptr(go), n, _ptr(gx), _stream())
+            _lib.check(rc, "rma_se3_exp_backward")
+    return gx.view(x.shape)
+
+
+def _collapse(shape, strides):
+    """Stride of the flattened index over dims (shape, strides), or None if they do not collapse to one stride."""
+    dims = [(d, s) for d, s in zip(shape, strides) if d != 1]
+    if not dims:
+        return 0
+    for (d0, s0), (d1, s1) in zip(dims[:-1], dims[1:]):
+        if s0 != s1 * d1:
+            return None
+    return dims[-1][1]
+
+
+class TransformPlan:
+    """How a `transform(g, a)` call maps onto G transforms x P points (see rma_se3_transform_forward)."""
+
+    def __init__(self, g: torch.Tensor, a: torch.Tensor):
+        _check_f32_cuda("g", g, 4)
+        if g.dim() < 2 or g.shape[-2] != 4:
+            raise RuntimeError(f"g must have shape [*,4,4], got {tuple(g.shape)}")
+        if not a.is_cuda or a.dtype != torch.float32:
+            raise RuntimeError("a must be a float32 CUDA tensor (rma_net_b200 has no CPU path)")
+        self.same_rank = g.dim() == a.dim()
+        if self.same_rank:                       # a: [*,3,N]   (se3.py:108-109)
+            if a.dim() < 2 or a.shape[-2] != 3:
+                raise RuntimeError(f"a must have shape [*,3,N], got {tuple(a.shape)}")
+            lead = torch.broadcast_shapes(g.shape[:-2], a.shape[:-2])
+            npts = a.shape[-1]
+            self.out_shape = tuple(lead) + (3, npts)
+            ge = g.expand(*lead, 4, 4)
+            ae = a.expand(*lead, 3, npts)
+            self.G = 1
+            for d in lead:
+                self.G *= d
+            self.P = npts
+            st = _collapse(lead, ae.stride()[:-2])
+            if st is None:
+                ae = ae.contiguous()
+                st = 3 * npts
+            self.a = ae
+            self.a_strides = (st, ae.stride(-1), ae.stride(-2))      # (s_t, s_k, s_c)
+            self.g_flat = ge.reshape(-1, 4, 4).contiguous()
+            self.o_strides = (3 * npts, 1, npts)
+            self.lead = tuple(lead)
+            self.split = len(lead)
+        else:                                    # a: [*,3]     (se3.py:110-111)
+            if a.shape[-1] != 3:
+                raise RuntimeError(f"a must have shape [*,3], got {tuple(a.shape)}")
+            lead = torch.broadcast_shapes(g.shape[:-2], a.shape[:-1])
+            self.out_shape = tuple(lead) + (3,)
+            ge = g.expand(*lead, 4, 4)
+            ae = a.expand(*lead, 3)
+            # trailing leading-dims over which g is constant -> points per transform
+            gs = ge.stride()[:-2]
+            split = len(lead)
+            while split > 0 and (gs[split - 1] == 0 or lead[split - 1] == 1):
+                split -= 1
+            self.G = 1
+            for d in lead[:split]:
+                self.G *= d
+            self.P = 1
+            for d in lead[split:]:
+                self.P *= d
+            st = _collapse(lead[:split], ae.stride()[:split])
+            sk = _collapse(lead[split:], ae.stride()[split:-1])
+            if st is None or sk is None:
+                ae = ae.contiguous()
+                st, sk = 3 * self.P, 3
+            self.a = ae
+            self.a_strides = (st, sk, ae.stride(-1))
+            idx = (slice(None),) * split + (0,) * (len(lead) - split)
+            self.g_flat = ge[idx].reshape(-1, 4, 4).contiguous()
+            self.o_strides = (3 * self.P, 3, 1)
+            self.lead = tuple(lead)
+            self.split = split
+
+
+def se3_transform_forward(g: torch.Tensor, a: torch.Tensor):
+    plan = TransformPlan(g, a)
+    out = torch.empty(plan.out_shape, dtype=torch.float32, device=a.device)
+    if out.numel():
+        with torch.cuda.device(a.device):
+            rc = _lib.load().rma_se3_transform_forward(
+                _ptr(plan.g_flat), _ptr(plan.a), *plan.a_strides, plan.G, plan.P,
+                _ptr(out), *plan.o_strides, _stream())
+            _lib.check(rc, "rma_se3_transform_forward")
+    return out, plan
+
+
+def se3_transform_backward(plan: TransformPlan, grad_out: torch.Tensor, g_shape, a_shape,
+                           need_g: bool, need_a: bool):
+    go = grad_out.to(torch.float32).contiguous()
+    dev = go.device
+    grad_g = torch.empty((plan.G, 4, 4), dtype=torch.float32, device=dev) if need_g else None
+    grad_a = torch.empty(plan.out_shape, dtype=torch.float32, device=dev) if need_a else None
+    if go.numel():
+        with torch.cuda.device(dev):
+            rc = _lib.load().rma_se3_transform_backward(
+                _ptr(plan.g_flat), _ptr(plan.a), *plan.a_strides, _ptr(go), *plan.o_strides, plan.G, plan.P,
+                _ptr(grad_g), _ptr(grad_a), *plan.o_strides, _stream())
+            _lib.check(rc, "rma_se3_transform_backward")
+    if grad_g is not None:
+        lead_g = plan.lead[:plan.split] + (1,) * (len(plan.lead) - plan.split)
+        grad_g = grad_g.view(*lead_g, 4, 4).sum_to_size(g_shape) if tuple(lead_g) + (4, 4) != tuple(g_shape) \
+            else grad_g.view(g_shape)
+    if grad_a is not None and tuple(grad_a.shape) != tuple(a_shape):
+        grad_a = grad_a.sum_to_size(a_shape)
+    return grad_g, grad_a
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fused recurrent-loop warp
+# ------------------------------------------------------------------------------------------------------------
+def warp_forward(phi, src, w=None, prev=None, want_rigid: bool = True, want_g: bool = True):
+    """phi [B,6]; src [B,N,3] (any strides); w [B,N] or [B,1,N] or None; prev [B,N,3] or None.
+    Returns (out [B,N,3], rigid [B,N,3] or None, g [B,4,4] or None)."""
+    _check_f32_cuda("phi", phi, 6)
+    _check_points("src", src)
+    B, N = src.shape[0], src.shape[1]
+    phic = phi.contiguous().view(-1, 6)
+    if phic.shape[0] != B:
+        raise RuntimeError(f"phi must be [B,6] with B={B}, got {tuple(phi.shape)}")
+    wc = None
+    if w is not None:
+        if prev is None:
+            raise RuntimeError("prev is required when w is given")
+        _check_points("prev", prev)
+        wc = w.to(torch.float32).contiguous().view(B, N)
+    dev = src.device
+    out = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+    blend = wc is not None
+    rigid = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if (want_rigid and blend) else None
+    g = torch.empty((B, 4, 4), dtype=torch.float32, device=dev) if want_g else None
+    ss = src.stride()
+    ps = prev.stride() if blend else (0, 0, 0)
+    if B and N:
+        with torch.cuda.device(dev):
+            rc = _lib.load().rma_warp_forward(_ptr(phic), _ptr(src), ss[0], ss[1], ss[2], _ptr(wc),
+                                              _ptr(prev if blend else None), ps[0], ps[1], ps[2], B, N,
+                                              _ptr(out), 3 * N, 3, 1, _ptr(g), _ptr(rigid), _stream())
+            _lib.check(rc, "rma_warp_forward")
+    if want_rigid and not blend:
+        rigid = out
+    return out, rigid, g
+
+
+def warp_backward(phi, src, w, prev, grad_out, need_w: bool, need_src: bool):
+    """Returns (grad_phi [B,6], grad_w [B,N] or None, grad_src [B,N,3] or None)."""
+    B, N = src.shape[0], src.shape[1]
+    dev = src.device
+    phic = phi.contiguous().view(-1, 6)
+    blend = w is not None
+    wc = w.to(torch.float32).contiguous().view(B, N) if blend else None
+    go = grad_out.to(torch.float32).contiguous()
+    grad_phi = torch.empty((B, 6), dtype=torch.float32, device=dev)
+    grad_w = torch.empty((B, N), dtype=torch.float32, device=dev) if (need_w and blend) else None
+    grad_src = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if need_src else None
+    scratch = torch.empty((B, 12), dtype=torch.float32, device=dev)
+    ss = src.stride()
+    ps = prev.stride() if blend else (0, 0, 0)
+    with torch.cuda.device(dev):
+        rc = _lib.load().rma_warp_backward(_ptr(phic), _ptr(src), ss[0], ss[1], ss[2], _ptr(wc),
+                                           _ptr(prev if blend else None), ps[0], ps[1], ps[2],
+                                           _ptr(go), 3 * N, 3, 1, B, N, _ptr(grad_phi), _ptr(grad_w),
+                                           _ptr(grad_src), 3 * N, 3, 1, _ptr(scratch), _stream())
+        _lib.check(rc, "rma_warp_backward")
+    return grad_phi.view(phi.shape), grad_w, grad_src
+
+
+def device_info():
+    sm, khz, maj, mnr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = _lib.load().rma_b200_device_info(ctypes.byref(sm), ctypes.byref(khz), ctypes.byref(maj), ctypes.byref(mnr))
+    _lib.check(rc, "rma_b200_device_info")
+    return dict(sm_count=sm.value, clock_khz=khz.value, cc=(maj.value, mnr.value))

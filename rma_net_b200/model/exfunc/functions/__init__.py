@@ -1,0 +1,2 @@
+from .chamfer_func import Chamfer, ChamferFunction  # noqa: F401
+from .warp_func import Warp, WarpFunction  # noqa: F401

@@ -1,0 +1,33 @@
+"""Chamfer nearest-neighbour op packaged the way the reference packages its native ops
+(model/exfunc/functions/point_render_func.py:19-45): an autograd.Function whose forward calls `ext.forward`,
+saves what backward needs, returns extra non-differentiable outputs whose grads are ignored, plus a thin nn.Module.
+"""
+import torch
+
+from .... import ext
+
+
+class ChamferFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points_x, points_y):
+        dist1, dist2, idx1, idx2 = ext.chamfer_forward(points_x, points_y, want_idx=True)
+        ctx.save_for_backward(points_x, points_y, idx1, idx2)
+        ctx.mark_non_differentiable(idx1, idx2)
+        return dist1, dist2, idx1, idx2
+
+    @staticmethod
+    def backward(ctx, grad_dist1, grad_dist2, _i1, _i2):
+        points_x, points_y, idx1, idx2 = ctx.saved_tensors
+        need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_x or need_y):
+            return None, None
+        grad_x, grad_y = ext.chamfer_backward(points_x, points_y, idx1, idx2, grad_dist1, grad_dist2,
+                                              need_x=need_x, need_y=need_y)
+        return grad_x, grad_y
+
+
+class Chamfer(torch.nn.Module):
+    """forward(points_x [B,M,3], points_y [B,N,3]) -> (dist1 [B,M], dist2 [B,N], idx1, idx2)."""
+
+    def forward(self, points_x, points_y):
+        return ChamferFunction.apply(points_x, points_y)

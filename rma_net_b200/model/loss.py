@@ -1,0 +1,50 @@
+"""Chamfer part of the reference's model/loss.py, same names and argument meaning, CUDA-only.
+
+    compute_sqrdis_map   loss.py:45-58     (kept callable; materialises [B,M,N]; NOT used by the hot path)
+    chamfer_dist         loss.py:60-70     -> (dist1 [B,M], dist2 [B,N])
+    loss_on_cd           loss.py:200-205   (a method of Loss in the reference; a function here)
+    loss_cd_stages       loss.py:260-267   (the gamma-weighted stage loop of Loss.forward)
+
+Differences from the reference that a caller can observe: distances are evaluated in fp32
+difference form (accurate to ~2e-7 relative) instead of the expanded |x|^2+|y|^2-2x.y form (1e-2..1e-5), so they
+are never negative; CPU tensors raise instead of running.
+"""
+import torch
+
+from .. import ext
+from .exfunc.functions.chamfer_func import ChamferFunction
+
+
+def compute_sqrdis_map(points_x, points_y):
+    """points_x [B,M,3], points_y [B,N,3] -> [B,M,N] squared distances (forward only)."""
+    if points_x.requires_grad or points_y.requires_grad:
+        if torch.is_grad_enabled():
+            raise RuntimeError("compute_sqrdis_map is forward-only here; use chamfer_dist for the differentiable path")
+    return ext.sqrdis_map(points_x, points_y)
+
+
+def chamfer_dist(points_x, points_y):
+    """points_x [B,M,3], points_y [B,N,3] -> (dist1 [B,M], dist2 [B,N]); differentiable w.r.t. both."""
+    dist1, dist2, _, _ = ChamferFunction.apply(points_x, points_y)
+    return dist1, dist2
+
+
+def chamfer_dist_with_idx(points_x, points_y):
+    """As chamfer_dist, plus the int32 argmin indices (first minimum, torch.min tie-break)."""
+    return ChamferFunction.apply(points_x, points_y)
+
+
+def loss_on_cd(deformation_p, p1):
+    thisbatchsize = deformation_p.size()[0]
+    dist1, dist2 = chamfer_dist(deformation_p, p1)
+    return (torch.sum(dist1) + torch.sum(dist2)) * 0.5 / thisbatchsize
+
+
+def loss_cd_stages(deformation_points_list, target_points, gamma=0.8, weight_cd=1.0):
+    """sum_i gamma^(T-i-1) * loss_on_cd(deformation_i^T, target) * weight_cd; deformation_i is [B,3,N]."""
+    iter_time = len(deformation_points_list)
+    loss_cd = 0
+    for i in range(iter_time):
+        loss_cd = loss_cd + gamma ** (iter_time - i - 1) * loss_on_cd(
+            deformation_points_list[i].transpose(1, 2), target_points)
+    return loss_cd * weight_cd

@@ -1,0 +1,281 @@
+"""GPU parity tests: CUDA chamfer path (through the C ABI) vs the oracle, on golden fixtures, seeded synthetic
+inputs, edge cases, and — at BASELINE.json's full sizes — the bit-exact fp32 C oracle and size-independent properties.
+
+Bars: argmin indices equal to the fp64 difference-form oracle except documented near-ties
+(two candidates whose fp64 distances differ by <= 2^-20 relative — fp32 difference-form resolution is ~3*2^-24);
+distances within 1e-5 relative; gradients within 1e-5 of |grad|_inf per tensor.  Against the fp32 C oracle that
+uses the kernels' operation order the bar is BIT-exact distances and indices.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, chamfer_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+CASES = sorted(os.path.basename(p)[8:-4] for p in glob.glob(
+    os.path.join(os.path.dirname(__file__), "golden", "chamfer_*.npz")))
+
+
+def _run(x_np, y_np, dev, grads=True):
+    from rma_net_b200.model.loss import chamfer_dist_with_idx
+    x = torch.from_numpy(np.ascontiguousarray(x_np)).to(dev).requires_grad_(grads)
+    y = torch.from_numpy(np.ascontiguousarray(y_np)).to(dev).requires_grad_(grads)
+    d1, d2, i1, i2 = chamfer_dist_with_idx(x, y)
+    out = dict(dist1=d1.detach().cpu().numpy(), dist2=d2.detach().cpu().numpy(),
+               idx1=i1.cpu().numpy(), idx2=i2.cpu().numpy())
+    if grads:
+        B = x.shape[0]
+        loss = (d1.sum() + d2.sum()) * 0.5 / B
+        loss.backward()
+        out.update(loss=loss.item(), grad_x=x.grad.cpu().numpy(), grad_y=y.grad.cpu().numpy())
+    return out
+
+
+def _check_vs_exact(x, y, got, exact=None):
+    exact = exact or c_oracle.chamfer_fwd(x, y, "f64")
+    np.testing.assert_allclose(got["dist1"], exact["dist1"], rtol=REL, atol=1e-37)
+    np.testing.assert_allclose(got["dist2"], exact["dist2"], rtol=REL, atol=1e-37)
+    n1, near1, bad1 = co.classify_index_mismatches(x, y, got["idx1"], exact["idx1"])
+    n2, near2, bad2 = co.classify_index_mismatches(y, x, got["idx2"], exact["idx2"])
+    assert bad1 == 0 and bad2 == 0, f"index mismatches that are not near-ties: {bad1}, {bad2}"
+    assert n1 + n2 <= max(2, (got["idx1"].size + got["idx2"].size) // 20000), "too many near-ties to be chance"
+    return exact
+
+
+def _check_bit_exact_f32(x, y, got):
+    ref = c_oracle.chamfer_fwd(x, y, "f32")
+    assert np.array_equal(got["idx1"], ref["idx1"]) and np.array_equal(got["idx2"], ref["idx2"])
+    assert np.array_equal(got["dist1"].view(np.uint32), ref["dist1"].view(np.uint32))
+    assert np.array_equal(got["dist2"].view(np.uint32), ref["dist2"].view(np.uint32))
+
+
+def _check_grads(x, y, got):
+    B = x.shape[0]
+    # gradients evaluated at the GPU's own indices (identical to the oracle's except at documented near-ties)
+    gx, gy = c_oracle.chamfer_bwd(x, y, got["idx1"], got["idx2"], 0.5 / B, 0.5 / B)
+    np.testing.assert_allclose(got["grad_x"], gx, rtol=0, atol=REL * np.abs(gx).max() + 1e-30)
+    np.testing.assert_allclose(got["grad_y"], gy, rtol=0, atol=REL * np.abs(gy).max() + 1e-30)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_golden_fixtures(cuda, golden_dir, case):
+    g = dict(np.load(os.path.join(golden_dir, f"chamfer_{case}.npz")))
+    x, y = g["x"], g["y"]
+    got = _run(x, y, cuda)
+    _check_vs_exact(x, y, got)
+    _check_bit_exact_f32(x, y, got)
+    _check_grads(x, y, got)
+    # against the reference's own fp32 outputs, at the reference's error bound
+    scale = float((x.astype(np.float64) ** 2).sum(-1).max() + (y.astype(np.float64) ** 2).sum(-1).max())
+    atol = 8 * 2.0 ** -24 * scale
+    np.testing.assert_allclose(got["dist1"], g["ref_dist1"], rtol=0, atol=atol)
+    np.testing.assert_allclose(got["dist2"], g["ref_dist2"], rtol=0, atol=atol)
+    assert abs(got["loss"] - float(g["ref_loss"])) <= 1e-5 * abs(got["loss"]) + atol
+    if np.array_equal(got["idx1"], g["ref_idx1"]) and np.array_equal(got["idx2"], g["ref_idx2"]):
+        np.testing.assert_allclose(got["grad_x"], g["ref_grad_x"], rtol=0, atol=3e-6 * np.abs(g["ref_grad_x"]).max())
+        np.testing.assert_allclose(got["grad_y"], g["ref_grad_y"], rtol=0, atol=3e-6 * np.abs(g["ref_grad_y"]).max())
+
+
+def test_survey_known_answers_on_gpu(cuda, golden_dir):
+    g = dict(np.load(os.path.join(golden_dir, "chamfer_samples1.npz")))
+    got = _run(g["x"], g["y"], cuda)
+    assert int(got["idx1"].sum()) == 2122746 and int(got["idx2"].sum()) == 2157379
+    assert abs(got["dist1"].astype(np.float64).sum() - 8.03275674327) < 1e-5
+    assert abs(got["dist2"].astype(np.float64).sum() - 9.98332504104) < 1e-5
+    assert abs(np.linalg.norm(got["grad_x"].astype(np.float64)) - 13.2095995) < 2e-4
+
+
+SHAPES = [(1, 1, 1), (1, 1, 7), (2, 5, 1), (1, 15, 17), (3, 16, 32), (2, 31, 33), (1, 511, 64), (1, 512, 65),
+          (2, 513, 100), (1, 2047, 2049), (2, 2048, 640), (1, 2049, 31), (5, 100, 3000), (1, 4096, 4096),
+          (3, 1000, 1300), (1, 6000, 200)]
+
+
+@pytest.mark.parametrize("B,N,M", SHAPES)
+@pytest.mark.parametrize("dist", ["uniform", "normal"])
+def test_ragged_shapes(cuda, B, N, M, dist):
+    g = torch.Generator().manual_seed(1000 + B * 7 + N * 3 + M)
+    if dist == "uniform":
+        x = (torch.rand(B, N, 3, generator=g) * 2 - 1).numpy()
+        y = (torch.rand(B, M, 3, generator=g) * 2 - 1).numpy()
+    else:
+        x = (torch.randn(B, N, 3, generator=g) * 0.3).numpy()
+        y = (torch.randn(B, M, 3, generator=g) * 0.3 + 0.1).numpy()
+    got = _run(x, y, cuda)
+    _check_vs_exact(x, y, got)
+    _check_bit_exact_f32(x, y, got)
+    _check_grads(x, y, got)
+
+
+def test_exact_ties_lowest_index(cuda):
+    """torch.min(dim) tie-break: first index wins and gets all the gradient (SURVEY.md §8c tie test)."""
+    x = np.zeros((1, 1, 3), np.float32)
+    y = np.array([[[1, 0, 0], [0, 1, 0], [-1, 0, 0], [0, 1, 0]]], np.float32)
+    got = _run(x, y, cuda)
+    assert got["idx1"][0, 0] == 0 and list(got["idx2"][0]) == [0, 0, 0, 0]
+    # duplicated points across tile / row-group / split boundaries
+    rng = np.random.default_rng(5)
+    base = rng.uniform(-1, 1, (1, 700, 3)).astype(np.float32)
+    xs = np.concatenate([base, base, base[:, :300]], 1)            # N = 1700, every point duplicated
+    ys = np.concatenate([base[:, ::-1], base, base], 1)            # M = 2100
+    got = _run(xs, ys, cuda)
+    ref = c_oracle.chamfer_fwd(xs, ys, "f64")
+    assert np.array_equal(got["idx1"], ref["idx1"]) and np.array_equal(got["idx2"], ref["idx2"])
+    assert np.all(got["dist1"] == 0) and np.all(got["dist2"] == 0)
+    _check_grads(xs, ys, got)
+
+
+def test_strided_views_as_the_callers_pass_them(cuda):
+    """train_view.py:369-370 slices [B,2N,3] into source/target (batch stride 6N); loss.py:264 passes
+    deformation.transpose(1,2) of a [B,3,N] tensor."""
+    from rma_net_b200.model.loss import chamfer_dist_with_idx
+    g = torch.Generator().manual_seed(7)
+    B, N = 3, 777
+    pair = (torch.rand(B, 2 * N, 3, generator=g) * 2 - 1).to(cuda)
+    src, tgt = pair[:, :N], pair[:, N:]
+    assert not src.is_contiguous()
+    d1, d2, i1, i2 = chamfer_dist_with_idx(src, tgt)
+    e = c_oracle.chamfer_fwd(src.cpu().numpy(), tgt.cpu().numpy(), "f32")
+    assert np.array_equal(i1.cpu().numpy(), e["idx1"]) and np.array_equal(i2.cpu().numpy(), e["idx2"])
+    assert np.array_equal(d1.cpu().numpy(), e["dist1"])
+    d3n = src.transpose(1, 2).contiguous()                         # [B,3,N] as the network holds it
+    d1b, d2b, i1b, i2b = chamfer_dist_with_idx(d3n.transpose(1, 2), tgt)
+    assert torch.equal(d1b, d1) and torch.equal(i2b, i2)
+    # gradient flows back into the strided leaf layout
+    d3n.requires_grad_(True)
+    a, b_, _, _ = chamfer_dist_with_idx(d3n.transpose(1, 2), tgt)
+    (a.sum() + b_.sum()).backward()
+    assert d3n.grad.shape == d3n.shape and torch.isfinite(d3n.grad).all()
+
+
+def test_metric_call_no_grad_and_argument_errors(cuda):
+    """train_view.py:285-286, 379-380: no_grad forward-only calls; bad arguments raise RuntimeError."""
+    from rma_net_b200.model.loss import chamfer_dist, loss_on_cd
+    x = torch.rand(2, 100, 3, device=cuda)
+    y = torch.rand(2, 90, 3, device=cuda)
+    with torch.no_grad():
+        d1, d2 = chamfer_dist(y, x)
+        assert d1.shape == (2, 90) and d2.shape == (2, 100)
+        err = (torch.mean(d1 + d2[:, :90]) * 0.5).item()
+        assert np.isfinite(err)
+    assert loss_on_cd(x, y).dim() == 0
+    with pytest.raises(RuntimeError):
+        chamfer_dist(x, y[:1])
+    with pytest.raises(RuntimeError):
+        chamfer_dist(x.double(), y.double())
+    with pytest.raises(RuntimeError):
+        chamfer_dist(x[:, :, :2], y)
+    with pytest.raises(RuntimeError):
+        chamfer_dist(x[:, :0], y)
+    with pytest.raises(RuntimeError):
+        chamfer_dist(x.cpu(), y.cpu())
+
+
+def test_upstream_gradients_and_partial_requires_grad(cuda):
+    from rma_net_b200.model.loss import chamfer_dist_with_idx
+    rng = np.random.default_rng(11)
+    x = rng.normal(size=(2, 300, 3)).astype(np.float32)
+    y = rng.normal(size=(2, 350, 3)).astype(np.float32)
+    g1 = rng.normal(size=(2, 300)).astype(np.float32)
+    g2 = rng.normal(size=(2, 350)).astype(np.float32)
+    xt = torch.from_numpy(x).to(cuda).requires_grad_(True)
+    yt = torch.from_numpy(y).to(cuda).requires_grad_(True)
+    d1, d2, i1, i2 = chamfer_dist_with_idx(xt, yt)
+    (d1 * torch.from_numpy(g1).to(cuda)).sum().backward(retain_graph=True)        # only g1 flows
+    gx, gy = c_oracle.chamfer_bwd(x, y, i1.cpu().numpy(), i2.cpu().numpy(), g1, np.zeros_like(g2))
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), gx, atol=REL * np.abs(gx).max())
+    np.testing.assert_allclose(yt.grad.cpu().numpy(), gy, atol=REL * np.abs(gy).max())
+    xt.grad = None; yt.grad = None
+    ((d1 * torch.from_numpy(g1).to(cuda)).sum() + (d2 * torch.from_numpy(g2).to(cuda)).sum()).backward()
+    gx, gy = c_oracle.chamfer_bwd(x, y, i1.cpu().numpy(), i2.cpu().numpy(), g1, g2)
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), gx, atol=REL * np.abs(gx).max())
+    np.testing.assert_allclose(yt.grad.cpu().numpy(), gy, atol=REL * np.abs(gy).max())
+    # only x requires grad
+    xt2 = torch.from_numpy(x).to(cuda).requires_grad_(True)
+    d1, d2, _, _ = chamfer_dist_with_idx(xt2, torch.from_numpy(y).to(cuda))
+    (d1.sum() + d2.sum()).backward()
+    gx, _ = c_oracle.chamfer_bwd(x, y, i1.cpu().numpy(), i2.cpu().numpy(), 1.0, 1.0)
+    np.testing.assert_allclose(xt2.grad.cpu().numpy(), gx, atol=REL * np.abs(gx).max())
+
+
+def test_heavy_scatter_contention(cuda, golden_dir):
+    """samples/4: 35 distinct targets are nearest to 1024 sources -> same-address atomics; also a degenerate cloud."""
+    x = np.random.default_rng(3).normal(size=(2, 4096, 3)).astype(np.float32)
+    y = np.zeros((2, 64, 3), np.float32)
+    y[:, :, 0] = 100.0 + np.arange(64)[None] * 1e-3                # everything maps to target 0
+    got = _run(x, y, cuda)
+    assert np.all(got["idx1"] == 0)
+    _check_grads(x, y, got)
+
+
+def test_sqrdis_map_and_host_entry(cuda):
+    import ctypes
+    from rma_net_b200 import _lib
+    from rma_net_b200.model.loss import compute_sqrdis_map
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-1, 1, (2, 130, 3)).astype(np.float32)
+    y = rng.uniform(-1, 1, (2, 70, 3)).astype(np.float32)
+    sq = compute_sqrdis_map(torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda)).cpu().numpy()
+    ref = ((x[:, :, None].astype(np.float64) - y[:, None].astype(np.float64)) ** 2).sum(-1)
+    np.testing.assert_allclose(sq, ref, rtol=1e-6, atol=1e-12)
+    # C-ABI host-buffer entry (what a non-torch binding calls)
+    lib = _lib.load()
+    loss = ctypes.c_float()
+    d1 = np.empty((2, 130), np.float32); d2 = np.empty((2, 70), np.float32)
+    i1 = np.empty((2, 130), np.int32); i2 = np.empty((2, 70), np.int32)
+    gx = np.empty_like(x); gy = np.empty_like(y)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.rma_chamfer_loss_host(p(x), p(y), 2, 130, 70, ctypes.byref(loss), p(d1), p(d2), p(i1), p(i2), p(gx), p(gy))
+    assert rc == 0
+    e = c_oracle.chamfer_fwd(x, y, "f32")
+    assert np.array_equal(i1, e["idx1"]) and np.array_equal(d2, e["dist2"])
+    l64, gx64, gy64, _ = co.loss_on_cd_exact(x, y)
+    assert abs(loss.value - l64) < 1e-5 * l64
+    np.testing.assert_allclose(gx, gx64, atol=REL * np.abs(gx64).max())
+
+
+@pytest.mark.parametrize("cfg", ["C2_uniform", "C2_normal", "C3_shape", "C4_slice"])
+def test_baseline_sizes_bit_exact_and_properties(cuda, cfg):
+    """BASELINE.json sizes (SURVEY.md §8d seeds): bit-exact vs the fp32 C oracle, fp64 oracle bars, and
+    size-independent properties: swap symmetry, self-distance, translation of the index set."""
+    from rma_net_b200.model.loss import chamfer_dist_with_idx
+    if cfg == "C2_uniform":
+        g = torch.Generator().manual_seed(0)
+        x = torch.rand(16, 4096, 3, generator=g) * 2 - 1
+        y = torch.rand(16, 4096, 3, generator=g) * 2 - 1
+    elif cfg == "C2_normal":
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(16, 4096, 3, generator=g) * 0.3
+        y = torch.randn(16, 4096, 3, generator=g) * 0.3
+    elif cfg == "C3_shape":
+        g = torch.Generator().manual_seed(2)
+        x = torch.rand(4, 8192, 3, generator=g) * 2 - 1
+        y = torch.rand(4, 8192, 3, generator=g) * 2 - 1
+    else:
+        g = torch.Generator().manual_seed(3)
+        x = torch.rand(64, 2048, 3, generator=g) * 2 - 1
+        y = torch.rand(64, 2048, 3, generator=g) * 2 - 1
+    xn, yn = x.numpy(), y.numpy()
+    got = _run(xn, yn, cuda)
+    _check_bit_exact_f32(xn, yn, got)
+    _check_vs_exact(xn, yn, got)
+    _check_grads(xn, yn, got)
+    xd, yd = x.to(cuda), y.to(cuda)
+    # swap symmetry: chamfer(y, x) is chamfer(x, y) with the outputs exchanged, bit for bit
+    d1s, d2s, i1s, i2s = chamfer_dist_with_idx(yd, xd)
+    assert np.array_equal(d1s.cpu().numpy(), got["dist2"]) and np.array_equal(d2s.cpu().numpy(), got["dist1"])
+    assert np.array_equal(i1s.cpu().numpy(), got["idx2"]) and np.array_equal(i2s.cpu().numpy(), got["idx1"])
+    # self distance: zero, identity indices (no duplicate points in these clouds)
+    d1, d2, i1, i2 = chamfer_dist_with_idx(xd, xd)
+    ar = torch.arange(x.shape[1], device=cuda, dtype=torch.int32)[None].expand(x.shape[0], -1)
+    assert torch.all(d1 == 0) and torch.all(d2 == 0) and torch.equal(i1, ar) and torch.equal(i2, ar)
+    # permuting the targets permutes the indices (ties aside: none at distance level here)
+    perm = torch.randperm(y.shape[1], generator=g).to(cuda)
+    d1p, d2p, i1p, i2p = chamfer_dist_with_idx(xd, yd[:, perm])
+    assert torch.equal(d1p.cpu(), torch.from_numpy(got["dist1"]))
+    assert torch.equal(perm[i1p.long()].cpu().int(), torch.from_numpy(got["idx1"]))
