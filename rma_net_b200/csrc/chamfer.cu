@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(256) chamfer_backward_kernel(
       vx = gg * (p[0] - q[0]); vy = gg * (p[ysc] - q[xsc]); vz = gg * (p[2 * ysc] - q[2 * xsc]);
       own = grad_y ? grad_y + u * 3 : nullptr;
       other = grad_x ? grad_x + ((long long)b * N + i) * 3 : nullptr;
-      key = nrow + (long long)b * N + i;   // disjoint key space from the x->y half (a warp can straddle both)
+      key = ncol + (long long)b * N + i;   // x->y keys live in [0, ncol): disjoint (a warp can straddle both halves)
       live = true;
     }
   }

@@ -318,7 +318,7 @@ def warp_forward(phi, src, w=None, prev=None, want_rigid: bool = True, want_g: b
                                               _ptr(out), 3 * N, 3, 1, _ptr(g), _ptr(rigid), _stream())
             _lib.check(rc, "rma_warp_forward")
     if want_rigid and not blend:
-        rigid = out
+        rigid = out.detach()          # stage 0 / rigid net: the rigid points ARE the deformation (network.py:570)
     return out, rigid, g
 
 
