@@ -318,7 +318,7 @@ def run_ours(args):
                                     f"reaches 97% of it (profiles/r01_fp32_microbench.jsonl)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4), "d2h_bytes_per_step": 4},
-        "gpu_launches": 4 * args.steps,      # prep + search + finalize + backward-scatter per step (memsets excluded)
+        "gpu_launches": 4 * args.steps,      # prep + search + finalize(+loss,+grads) + scale_pair per step
         "clocks": clocks,
         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
         "step_ms_min_max": [min(step_ms), max(step_ms)],

@@ -71,6 +71,21 @@ int rma_chamfer_finalize(int B, int N, int M, float* dist1, float* dist2, int32_
 /* Launch shape the search kernel will use for (B,N,M) on the current device (reporting only). */
 int rma_chamfer_search_config(int B, int N, int M, int* ctas, int* threads, int* splits, int* ctas_per_sm);
 
+/* Fused loss_on_cd (model/loss.py:200-205 on top of chamfer_dist): in the same three launches,
+ *   *loss   = 0.5 * (sum dist1 + sum dist2) / B                 (device scalar, overwritten)
+ *   grad_x  = d loss / d x  [B,N,3],  grad_y = d loss / d y  [B,M,3]   (contiguous, overwritten; either may be NULL)
+ * so that the caller's backward is a scale by the upstream scalar (rma_scale_pair) instead of a second scatter pass
+ * plus ~10 small torch kernels.  dist1/dist2/idx1/idx2 are optional outputs (NULL to skip). */
+int rma_chamfer_cd_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                           const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
+                           int B, int N, int M, float* loss, float* dist1, float* dist2, int32_t* idx1,
+                           int32_t* idx2, float* grad_x, float* grad_y, void* workspace, size_t workspace_bytes,
+                           void* stream);
+/* out_a[i] = *scalar_dev * a[i] (i < na), out_b[i] = *scalar_dev * b[i] (i < nb) in one launch; the scalar is read
+ * on the device (no host sync).  Either half may be empty (n = 0). */
+int rma_scale_pair(const float* a, int64_t na, const float* b, int64_t nb, const float* scalar_dev, float* out_a,
+                   float* out_b, void* stream);
+
 /* Backward of the above.  Replaces the implicit torch autograd of loss.py:45-70 (MinBackward x2, BmmBackward,
  * MulBackward — SURVEY.md §8a row a4).  g1 [B,N], g2 [B,M] contiguous upstream gradients (either may be NULL = 0).
  *   grad_x[b,i] = 2 g1[b,i] (x_i - y_idx1[b,i]) + sum_{j: idx2[b,j]=i} 2 g2[b,j] (x_i - y_j)

@@ -78,9 +78,11 @@ static Workspace carve(const Geometry& g, void* base) {
 __global__ void __launch_bounds__(256) chamfer_prep_kernel(
     const float* __restrict__ x, long long xsb, long long xsn, long long xsc,
     const float* __restrict__ y, long long ysb, long long ysn, long long ysc,
-    Geometry g, Workspace w) {
+    Geometry g, Workspace w, float* __restrict__ zero_loss, float* __restrict__ zero_gx,
+    float* __restrict__ zero_gy) {
   const long long nrow = (long long)g.B * g.Npad;
   const long long ncol = (long long)g.B * g.Mp;
+  if (zero_loss && blockIdx.x == 0 && threadIdx.x == 0) *zero_loss = 0.f;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nrow + ncol;
        t += (long long)gridDim.x * blockDim.x) {
     if (t < nrow) {
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(256) chamfer_prep_kernel(
       if (i < g.N) {
         const float* s = x + b * xsb + i * xsn;
         px = s[0]; py = s[xsc]; pz = s[2 * xsc];
+        if (zero_gx) { float* o = zero_gx + ((long long)b * g.N + i) * 3; o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; }
       }
       const int rb = i / kRowsPerWarp, lane = (i % kRowsPerWarp) / kRowsPerThread, r = i % kRowsPerThread;
       // float4 slot q = c*4 + r/4 of this (row block, lane); element r%4
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(256) chamfer_prep_kernel(
       if (j < g.M) {
         const float* s = y + b * ysb + j * ysn;
         nx = -s[0]; ny = -s[ysc]; nz = -s[2 * ysc];
+        if (zero_gy) { float* o = zero_gy + ((long long)b * g.M + j) * 3; o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; }
       }
       w.colpack[2 * u] = make_float4(nx, nx, ny, ny);
       w.colpack[2 * u + 1] = make_float4(nz, nz, 0.f, 0.f);
@@ -148,8 +152,8 @@ struct SearchArgs {
 
 __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(SearchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* scol = reinterpret_cast<float4*>(smem_raw);                               // [kChunk][2]
-  float* cball = reinterpret_cast<float*>(smem_raw + (size_t)kChunk * 2 * sizeof(float4));  // [warps][32][33]
+  float4* scol = reinterpret_cast<float4*>(smem_raw);                                    // [kChunk + 2][2]
+  float* cball = reinterpret_cast<float*>(smem_raw + (size_t)(kChunk + 2) * 2 * sizeof(float4));  // [warps][2][32][33]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s = blockIdx.x % a.S;
@@ -161,7 +165,8 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
   const int c1 = (int)((long long)(s + 1) * a.M / a.S);
   const int ncols = (c1 - c0 + kTile - 1) / kTile * kTile;   // tiles may overrun c1 (into real or sentinel columns)
 
-  float* cb = cball + warp * (kTile * kCbStride);
+  float* cb = cball + warp * (2 * kTile * kCbStride);
+  u64* colbest = a.colbest + (size_t)b * a.Mp;
 
   // The thread's 16 source points, packed as row pairs (2k, 2k+1).
   u64 px[8], py[8], pz[8];
@@ -182,6 +187,12 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
 
   const float4* cp = a.colpack + ((size_t)b * a.Mp + c0) * 2;
 
+  // Column direction, software-pipelined: while tile t is being computed, lane l reduces column l of tile t-1
+  // (32 per-lane partial minima in the other half of the double buffer), two values per inner step, so the
+  // dependent compare/select chain hides behind the FP32 work instead of stalling at every tile boundary.
+  int pend_start = -1;   // first column of the tile whose column reduce is pending (warp-uniform)
+  int parity = 0;
+
   for (int cs = 0; cs < ncols; cs += kChunk) {
     const int nc = min(kChunk, ncols - cs);
     __syncthreads();   // previous chunk fully consumed
@@ -195,20 +206,41 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
 #pragma unroll
       for (int r = 0; r < kRowsPerThread; ++r) tm[r] = __int_as_float(0x7f800000);
       const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(scol + (size_t)t0 * 2);
+      float* cbw = cb + parity * (kTile * kCbStride) + lane;                       // this tile: [col][lane]
+      const float* cbr = cb + (parity ^ 1) * (kTile * kCbStride) + lane * kCbStride;  // previous tile: my column
+      float pm = __int_as_float(0x7f800000);
+      int pid = 0;
+
+      // operands of the first step; every step prefetches the next one (the last prefetch of a chunk reads the
+      // 2-column pad behind the staged data and is never used)
+      ulonglong2 n0 = sp[0];
+      u64 n0z = *reinterpret_cast<const u64*>(&sp[1]);
+      ulonglong2 n1 = sp[2];
+      u64 n1z = *reinterpret_cast<const u64*>(&sp[3]);
 
 #pragma unroll 2
       for (int jj = 0; jj < kTile; jj += 2) {
-        const ulonglong2 a0 = sp[2 * jj];
-        const u64 az = *reinterpret_cast<const u64*>(&sp[2 * jj + 1]);
-        const ulonglong2 b0 = sp[2 * jj + 2];
-        const u64 bz = *reinterpret_cast<const u64*>(&sp[2 * jj + 3]);
+        const ulonglong2 a0 = n0, b0 = n1;
+        const u64 az = n0z, bz = n1z;
+        n0 = sp[2 * jj + 4];
+        n0z = *reinterpret_cast<const u64*>(&sp[2 * jj + 5]);
+        n1 = sp[2 * jj + 6];
+        n1z = *reinterpret_cast<const u64*>(&sp[2 * jj + 7]);
+        const float v0 = cbr[jj], v1 = cbr[jj + 1];
         float dA[16], dB[16];
         const float cmA = column_step(px, py, pz, a0.x, a0.y, az, dA);
         const float cmB = column_step(px, py, pz, b0.x, b0.y, bz, dB);
 #pragma unroll
         for (int r = 0; r < kRowsPerThread; ++r) tm[r] = min3(tm[r], dA[r], dB[r]);
-        cb[jj * kCbStride + lane] = cmA;
-        cb[(jj + 1) * kCbStride + lane] = cmB;
+        cbw[jj * kCbStride] = cmA;
+        cbw[(jj + 1) * kCbStride] = cmB;
+        // pending column reduce: ascending lane order + strict '<' = lowest lane (lowest rows) wins ties
+        const bool l0 = v0 < pm;
+        pm = l0 ? v0 : pm;
+        pid = l0 ? jj : pid;
+        const bool l1 = v1 < pm;
+        pm = l1 ? v1 : pm;
+        pid = l1 ? jj + 1 : pid;
       }
 
       // Row direction: strict '<' keeps the earliest tile on ties (lowest index, torch.min semantics).
@@ -220,31 +252,33 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
         mt[r] = better ? tile_start : mt[r];
       }
 
-      // Column direction: lane l reduces column (tile_start + l) over the 32 lanes' partial minima.
-      __syncwarp();
-      {
-        const float* col = cb + lane * kCbStride;
-        float v[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = col[k];
-        float mm = v[31];
-#pragma unroll
-        for (int k = 0; k < 30; k += 2) mm = min3(mm, v[k], v[k + 1]);
-        mm = fminf(mm, v[30]);
-        int id = 31;
-#pragma unroll
-        for (int k = 30; k >= 0; --k) id = (v[k] == mm) ? k : id;   // lowest lane attaining the minimum
-        const int j = tile_start + lane;
-        if (j < c1) {
-          const u64 key = ((u64)__float_as_uint(mm) << 32) | (unsigned)(rb * 32 + id);
-          atomicMin(a.colbest + (size_t)b * a.Mp + j, key);
-        }
+      if (pend_start >= 0 && pend_start + lane < c1) {
+        const u64 key = ((u64)__float_as_uint(pm) << 32) | (unsigned)(rb * 32 + pid);
+        atomicMin(colbest + pend_start + lane, key);
       }
-      __syncwarp();
+      pend_start = tile_start;
+      parity ^= 1;
+      __syncwarp();   // this tile's partial minima visible to all lanes; previous buffer free for reuse
     }
   }
 
   if (has_rows) {
+    if (pend_start >= 0) {   // drain: column reduce of the last tile
+      const float* col = cb + (parity ^ 1) * (kTile * kCbStride) + lane * kCbStride;
+      float pm = __int_as_float(0x7f800000);
+      int pid = 0;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float v = col[k];
+        const bool l = v < pm;
+        pm = l ? v : pm;
+        pid = l ? k : pid;
+      }
+      if (pend_start + lane < c1) {
+        const u64 key = ((u64)__float_as_uint(pm) << 32) | (unsigned)(rb * 32 + pid);
+        atomicMin(colbest + pend_start + lane, key);
+      }
+    }
     const int i0 = rb * kRowsPerWarp + lane * kRowsPerThread;
     u64* rbest = a.rowbest + (size_t)b * a.Npad + i0;
 #pragma unroll
@@ -255,63 +289,7 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 3. finalize: coarse winner -> exact (distance, first index)
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) chamfer_finalize_kernel(
-    Geometry g, Workspace w, float* __restrict__ dist1, float* __restrict__ dist2,
-    int* __restrict__ idx1, int* __restrict__ idx2) {
-  const long long nrow = (long long)g.B * g.N;
-  const long long ncol = (long long)g.B * g.M;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < nrow) {
-    const int b = (int)(t / g.N), i = (int)(t % g.N);
-    const u64 key = w.rowbest[(size_t)b * g.Npad + i];
-    const int jt = (int)(unsigned)(key & 0xffffffffu);
-    const int rb = i / kRowsPerWarp, lane = (i % kRowsPerWarp) / kRowsPerThread, r = i % kRowsPerThread;
-    const size_t base = ((size_t)(b * g.nRB + rb) * 12) * 32 + lane;
-    const int q = r >> 2, e = r & 3;
-    const float x = w.rowpack[(base + (size_t)q * 32) * 4 + e];
-    const float y = w.rowpack[(base + (size_t)(4 + q) * 32) * 4 + e];
-    const float z = w.rowpack[(base + (size_t)(8 + q) * 32) * 4 + e];
-    const float4* cp = w.colpack + ((size_t)b * g.Mp + jt) * 2;
-    float best = __int_as_float(0x7f800000);
-    int bj = jt;
-#pragma unroll 4
-    for (int k = 0; k < kTile; ++k) {
-      const float4 c0 = cp[2 * k], c1 = cp[2 * k + 1];
-      const float d = sqdist_neg(x, y, z, c0.x, c0.z, c1.x);
-      if (d < best) { best = d; bj = jt + k; }
-    }
-    dist1[t] = best;
-    if (idx1) idx1[t] = bj;
-  } else if (t < nrow + ncol) {
-    const long long u = t - nrow;
-    const int b = (int)(u / g.M), j = (int)(u % g.M);
-    const u64 key = w.colbest[(size_t)b * g.Mp + j];
-    const int grp = (int)(unsigned)(key & 0xffffffffu);
-    const int rb = grp >> 5, lane = grp & 31;
-    const float4 c0 = w.colpack[((size_t)b * g.Mp + j) * 2], c1 = w.colpack[((size_t)b * g.Mp + j) * 2 + 1];
-    const float4* rp = reinterpret_cast<const float4*>(w.rowpack) + ((size_t)(b * g.nRB + rb) * 12) * 32 + lane;
-    float best = __int_as_float(0x7f800000);
-    int bi = grp * kRowsPerThread;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 vx = rp[(size_t)q * 32], vy = rp[(size_t)(4 + q) * 32], vz = rp[(size_t)(8 + q) * 32];
-      const float xs[4] = {vx.x, vx.y, vx.z, vx.w}, ys[4] = {vy.x, vy.y, vy.z, vy.w},
-                  zs[4] = {vz.x, vz.y, vz.z, vz.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float d = sqdist_neg(xs[e], ys[e], zs[e], c0.x, c0.z, c1.x);
-        if (d < best) { best = d; bi = grp * kRowsPerThread + q * 4 + e; }
-      }
-    }
-    dist2[u] = best;
-    if (idx2) idx2[u] = bi;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// backward: gradient scatter with warp-aggregated atomics
+// 3. finalize: coarse winner -> exact (distance, first index); optionally fused loss_on_cd value + gradients
 // ---------------------------------------------------------------------------------------------------------------
 // Sum (vx,vy,vz) over the lanes that share a key; the result is valid on the lowest lane of each peer group.
 __device__ __forceinline__ void reduce_peers(unsigned peers, float& vx, float& vy, float& vz) {
@@ -331,6 +309,154 @@ __device__ __forceinline__ void reduce_peers(unsigned peers, float& vx, float& v
   }
 }
 
+// Warp-aggregated scatter: lanes with equal `key` (>= 0) are summed and the group's lowest lane issues one atomic
+// per coordinate.  Every lane of the warp must call this; lanes with live == false contribute nothing.
+__device__ __forceinline__ void scatter_add3(float* dst, long long key, bool live, float vx, float vy, float vz) {
+  if (!live) key = -1 - (long long)lane_id();
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  if (__any_sync(0xffffffffu, peers != (1u << lane_id()))) reduce_peers(peers, vx, vy, vz);
+  if (live && (unsigned)(__ffs(peers) - 1) == lane_id()) {
+    atomicAdd(dst + 0, vx); atomicAdd(dst + 1, vy); atomicAdd(dst + 2, vz);
+  }
+}
+
+struct FinalizeArgs {
+  float* dist1; float* dist2; int* idx1; int* idx2;   // any may be null
+  float* loss;       // null, or [1] accumulator (zeroed by prep): += coef_loss * (sum dist1 + sum dist2)
+  float* grad_x;     // null, or [B,N,3] (zeroed by prep): d(coef_loss * sum)/dx
+  float* grad_y;     // null, or [B,M,3]
+  float coef_loss;   // 0.5 / B for loss_on_cd
+};
+
+constexpr int kFinWarps = 8;
+
+// One warp per block of 32 items.  Row item: the 32 columns of the winning tile are evaluated by the 32 lanes
+// (one coalesced 1 KB read), warp-min + ballot give the first minimum.  Column item: the 16 rows of the winning
+// row group are evaluated by a half warp.  Distances use sqdist_neg = the search kernel's operation order.
+__global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geometry g, Workspace w, FinalizeArgs f) {
+  __shared__ float4 stage[kFinWarps][32];
+  __shared__ double lsum[kFinWarps];
+  const long long nrow = (long long)g.B * g.N, ncol = (long long)g.B * g.M;
+  const long long row_warps = (nrow + 31) / 32;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const long long wi = (long long)blockIdx.x * kFinWarps + warp;
+  const float coef_grad = 2.f * f.coef_loss;
+  const bool fused = f.grad_x != nullptr || f.grad_y != nullptr;
+  float myd = 0.f;
+  bool valid = false;
+
+  if (wi < row_warps) {
+    const long long t = wi * 32 + lane;
+    valid = t < nrow;
+    int b = 0, i = 0, jt = 0;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (valid) {
+      b = (int)(t / g.N); i = (int)(t % g.N);
+      jt = (int)(unsigned)(w.rowbest[(size_t)b * g.Npad + i] & 0xffffffffu);
+      const int rb = i / kRowsPerWarp, ln = (i % kRowsPerWarp) / kRowsPerThread, r = i % kRowsPerThread;
+      const size_t base = ((size_t)(b * g.nRB + rb) * 12) * 32 + ln;
+      const int q = r >> 2, e = r & 3;
+      x = w.rowpack[(base + (size_t)q * 32) * 4 + e];
+      y = w.rowpack[(base + (size_t)(4 + q) * 32) * 4 + e];
+      z = w.rowpack[(base + (size_t)(8 + q) * 32) * 4 + e];
+    }
+    stage[warp][lane] = make_float4(__int_as_float(b * g.Mp + jt), x, y, z);
+    __syncwarp();
+    int myj = 0;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const float4 sv = stage[warp][r];
+      const float4* cp = w.colpack + ((size_t)__float_as_int(sv.x) + lane) * 2;
+      const float4 c0 = cp[0], c1 = cp[1];
+      const unsigned d = __float_as_uint(sqdist_neg(sv.y, sv.z, sv.w, c0.x, c0.z, c1.x));
+      const unsigned dm = __reduce_min_sync(0xffffffffu, d);       // d >= 0: unsigned order == float order
+      const unsigned hit = __ballot_sync(0xffffffffu, d == dm);
+      if (lane == r) { myd = __uint_as_float(dm); myj = __ffs(hit) - 1; }
+    }
+    const int j = jt + myj;
+    if (valid) {
+      if (f.dist1) f.dist1[t] = myd;
+      if (f.idx1) f.idx1[t] = j;
+    }
+    if (fused) {
+      float vx = 0.f, vy = 0.f, vz = 0.f;
+      if (valid) {
+        const float4* cp = w.colpack + ((size_t)b * g.Mp + j) * 2;
+        const float4 c0 = cp[0], c1 = cp[1];
+        vx = coef_grad * (x + c0.x); vy = coef_grad * (y + c0.z); vz = coef_grad * (z + c1.x);
+        if (f.grad_x) { float* o = f.grad_x + t * 3; atomicAdd(o, vx); atomicAdd(o + 1, vy); atomicAdd(o + 2, vz); }
+      }
+      if (f.grad_y)
+        scatter_add3(f.grad_y + ((long long)b * g.M + j) * 3, (long long)b * g.M + j, valid, -vx, -vy, -vz);
+    }
+  } else {
+    const long long t = (wi - row_warps) * 32 + lane;
+    valid = t < ncol;
+    int b = 0, j = 0, grp = 0, fbase = 0;
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    if (valid) {
+      b = (int)(t / g.M); j = (int)(t % g.M);
+      grp = (int)(unsigned)(w.colbest[(size_t)b * g.Mp + j] & 0xffffffffu);
+      const float4* cp = w.colpack + ((size_t)b * g.Mp + j) * 2;
+      const float4 c0 = cp[0], c1 = cp[1];
+      nx = c0.x; ny = c0.z; nz = c1.x;
+      fbase = (((b * g.nRB + (grp >> 5)) * 12) * 32 + (grp & 31)) * 4;   // float index of (group, q = 0, e = 0)
+    }
+    stage[warp][lane] = make_float4(__int_as_float(fbase), nx, ny, nz);
+    __syncwarp();
+    const int half = lane >> 4, rr = lane & 15;
+    const int roff = ((rr >> 2) * 32) * 4 + (rr & 3);                      // row rr inside a group
+    int myi = 0;
+#pragma unroll 4
+    for (int p = 0; p < 16; ++p) {
+      const int r = half * 16 + p;                                          // item handled by this half warp
+      const float4 sv = stage[warp][r];
+      const float* rp = w.rowpack + __float_as_int(sv.x) + roff;
+      const float x = rp[0], y = rp[4 * 32 * 4], z = rp[8 * 32 * 4];
+      const unsigned d = __float_as_uint(sqdist_neg(x, y, z, sv.y, sv.z, sv.w));
+      unsigned dm = d;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) dm = min(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+      const unsigned hit = (__ballot_sync(0xffffffffu, d == dm) >> (half * 16)) & 0xffffu;
+      if (lane == r) { myd = __uint_as_float(dm); myi = __ffs(hit) - 1; }
+    }
+    const int i = grp * kRowsPerThread + myi;
+    if (valid) {
+      if (f.dist2) f.dist2[t] = myd;
+      if (f.idx2) f.idx2[t] = i;
+    }
+    if (fused) {
+      float vx = 0.f, vy = 0.f, vz = 0.f;
+      if (valid) {
+        const float* rp = w.rowpack + fbase + ((myi >> 2) * 32) * 4 + (myi & 3);
+        const float x = rp[0], y = rp[4 * 32 * 4], z = rp[8 * 32 * 4];
+        // d/dy_j |y_j - x_i|^2 = 2 (y_j - x_i) = -2 (x_i + (-y_j))
+        vx = -coef_grad * (x + nx); vy = -coef_grad * (y + ny); vz = -coef_grad * (z + nz);
+        if (f.grad_y) { float* o = f.grad_y + t * 3; atomicAdd(o, vx); atomicAdd(o + 1, vy); atomicAdd(o + 2, vz); }
+      }
+      if (f.grad_x)
+        scatter_add3(f.grad_x + ((long long)b * g.N + i) * 3, (long long)b * g.N + i, valid, -vx, -vy, -vz);
+    }
+  }
+
+  if (f.loss) {
+    double sd = valid ? (double)myd : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+    if (lane == 0) lsum[warp] = sd;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int k = 0; k < kFinWarps; ++k) tot += lsum[k];
+      atomicAdd(f.loss, (float)(tot * (double)f.coef_loss));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward: gradient scatter with warp-aggregated atomics (generic upstream gradients g1, g2)
+// ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) chamfer_backward_kernel(
     const float* __restrict__ x, long long xsb, long long xsn, long long xsc,
     const float* __restrict__ y, long long ysb, long long ysn, long long ysc,
@@ -377,13 +503,7 @@ __global__ void __launch_bounds__(256) chamfer_backward_kernel(
   if (live && own) {   // own-point term: one writer per address from this half, the other half scatters into it
     atomicAdd(own + 0, vx); atomicAdd(own + 1, vy); atomicAdd(own + 2, vz);
   }
-  const unsigned peers = __match_any_sync(0xffffffffu, key);
-  float sx = -vx, sy = -vy, sz = -vz;
-  if (__any_sync(0xffffffffu, peers != (1u << lane_id()))) reduce_peers(peers, sx, sy, sz);   // warp-uniform
-  const bool leader = (unsigned)(__ffs(peers) - 1) == lane_id();
-  if (live && other && leader) {
-    atomicAdd(other + 0, sx); atomicAdd(other + 1, sy); atomicAdd(other + 2, sz);
-  }
+  scatter_add3(other, key, live && other != nullptr, -vx, -vy, -vz);
 }
 
 __global__ void __launch_bounds__(256) sqrdis_map_kernel(
@@ -420,7 +540,7 @@ __global__ void unpack_keys_kernel(const u64* __restrict__ keys, long long n, fl
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-constexpr size_t kSearchSmem = (size_t)kChunk * 2 * sizeof(float4) + (size_t)kSearchWarps * kTile * kCbStride * sizeof(float);
+constexpr size_t kSearchSmem = (size_t)(kChunk + 2) * 2 * sizeof(float4) + (size_t)kSearchWarps * 2 * kTile * kCbStride * sizeof(float);
 
 struct DeviceCaps { int sms; int search_occ; };
 
@@ -516,16 +636,24 @@ static int forward_setup(const float* x, const float* y, int B, int N, int M, vo
   return RMA_OK;
 }
 
-int rma_chamfer_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
-                     const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
-                     int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream_) {
+static int launch_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                       const float* y, int64_t ysb, int64_t ysn, int64_t ysc, int B, int N, int M,
+                       void* workspace, size_t workspace_bytes, float* zero_loss, float* zero_gx, float* zero_gy,
+                       void* stream_) {
   Geometry g; Workspace w;
   if (int e = forward_setup(x, y, B, N, M, workspace, workspace_bytes, &g, &w)) return e;
   const long long slots = (long long)B * (g.Npad + g.Mp);
-  chamfer_prep_kernel<<<grid_for(slots, 256), 256, 0, (cudaStream_t)stream_>>>(x, xsb, xsn, xsc, y, ysb, ysn, ysc,
-                                                                               g, w);
+  chamfer_prep_kernel<<<grid_for(slots, 256), 256, 0, (cudaStream_t)stream_>>>(
+      x, xsb, xsn, xsc, y, ysb, ysn, ysc, g, w, zero_loss, zero_gx, zero_gy);
   RMA_LAUNCH_CHECK();
   return RMA_OK;
+}
+
+int rma_chamfer_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                     const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
+                     int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream_) {
+  return launch_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, workspace, workspace_bytes, nullptr, nullptr,
+                     nullptr, stream_);
 }
 
 int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream_) {
@@ -548,16 +676,22 @@ int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_by
   return RMA_OK;
 }
 
-int rma_chamfer_finalize(int B, int N, int M, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
-                         void* workspace, size_t workspace_bytes, void* stream_) {
+static int launch_finalize(int B, int N, int M, const FinalizeArgs& f, void* workspace, size_t workspace_bytes,
+                           void* stream_) {
   Geometry g; Workspace w;
-  if (!dist1 || !dist2) return RMA_E_BADARG;
   if (int e = forward_setup((const float*)workspace, (const float*)workspace, B, N, M, workspace, workspace_bytes,
                             &g, &w)) return e;
-  chamfer_finalize_kernel<<<grid_for((long long)B * ((long long)N + M), 128), 128, 0, (cudaStream_t)stream_>>>(
-      g, w, dist1, dist2, idx1, idx2);
+  const long long warps = ((long long)B * N + 31) / 32 + ((long long)B * M + 31) / 32;
+  chamfer_finalize_kernel<<<grid_for(warps, kFinWarps), kFinWarps * 32, 0, (cudaStream_t)stream_>>>(g, w, f);
   RMA_LAUNCH_CHECK();
   return RMA_OK;
+}
+
+int rma_chamfer_finalize(int B, int N, int M, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
+                         void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!dist1 || !dist2) return RMA_E_BADARG;
+  FinalizeArgs f = {dist1, dist2, idx1, idx2, nullptr, nullptr, nullptr, 0.f};
+  return launch_finalize(B, N, M, f, workspace, workspace_bytes, stream_);
 }
 
 int rma_chamfer_search_config(int B, int N, int M, int* ctas, int* threads, int* splits, int* ctas_per_sm) {
@@ -582,6 +716,44 @@ int rma_chamfer_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
     return e;
   if (int e = rma_chamfer_search(B, N, M, workspace, workspace_bytes, stream)) return e;
   return rma_chamfer_finalize(B, N, M, dist1, dist2, idx1, idx2, workspace, workspace_bytes, stream);
+}
+
+int rma_chamfer_cd_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                           const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
+                           int B, int N, int M, float* loss, float* dist1, float* dist2, int32_t* idx1,
+                           int32_t* idx2, float* grad_x, float* grad_y, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  if (!loss) return RMA_E_BADARG;
+  if (int e = launch_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, workspace, workspace_bytes, loss, grad_x,
+                          grad_y, stream))
+    return e;
+  if (int e = rma_chamfer_search(B, N, M, workspace, workspace_bytes, stream)) return e;
+  FinalizeArgs f = {dist1, dist2, idx1, idx2, loss, grad_x, grad_y, 0.5f / (float)B};
+  return launch_finalize(B, N, M, f, workspace, workspace_bytes, stream);
+}
+
+__global__ void __launch_bounds__(256) scale_pair_kernel(const float* __restrict__ a, long long na,
+                                                         const float* __restrict__ b, long long nb,
+                                                         const float* __restrict__ scalar, float* __restrict__ oa,
+                                                         float* __restrict__ ob) {
+  const float sc = *scalar;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < na + nb;
+       t += (long long)gridDim.x * blockDim.x) {
+    if (t < na) oa[t] = sc * a[t];
+    else ob[t - na] = sc * b[t - na];
+  }
+}
+
+int rma_scale_pair(const float* a, int64_t na, const float* b, int64_t nb, const float* scalar_dev, float* out_a,
+                   float* out_b, void* stream_) {
+  if (!scalar_dev || na < 0 || nb < 0 || (na > 0 && (!a || !out_a)) || (nb > 0 && (!b || !out_b)))
+    return RMA_E_BADARG;
+  if (na + nb == 0) return RMA_OK;
+  long long grid = (na + nb + 255) / 256;
+  if (grid > 148LL * 16) grid = 148LL * 16;
+  scale_pair_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream_>>>(a, na, b, nb, scalar_dev, out_a, out_b);
+  RMA_LAUNCH_CHECK();
+  return RMA_OK;
 }
 
 int rma_chamfer_backward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,

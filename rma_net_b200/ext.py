@@ -100,6 +100,47 @@ def chamfer_backward(points_x, points_y, idx1, idx2, g1, g2, need_x: bool = True
     return gx, gy
 
 
+def chamfer_cd_forward(points_x: torch.Tensor, points_y: torch.Tensor, need_x: bool, need_y: bool):
+    """Fused loss_on_cd: returns (loss 0-dim, unit grad_x [B,N,3] or None, unit grad_y [B,M,3] or None)."""
+    _check_points("points_x", points_x)
+    _check_points("points_y", points_y)
+    _same_device(points_x, points_y)
+    B, N, M = points_x.shape[0], points_x.shape[1], points_y.shape[1]
+    if points_y.shape[0] != B:
+        raise RuntimeError(f"batch sizes differ: {B} vs {points_y.shape[0]}")
+    if B == 0 or N == 0 or M == 0:
+        raise RuntimeError("chamfer_dist needs non-empty point sets (min over an empty dimension)")
+    lib = _lib.load()
+    dev = points_x.device
+    with torch.cuda.device(dev):
+        wsb = lib.rma_chamfer_workspace_bytes(B, N, M)
+        if wsb == 0:
+            raise RuntimeError(f"problem size not supported: B={B}, N={N}, M={M}")
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        gx = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if need_x else None
+        gy = torch.empty((B, M, 3), dtype=torch.float32, device=dev) if need_y else None
+        xs, ys = points_x.stride(), points_y.stride()
+        rc = lib.rma_chamfer_cd_forward(_ptr(points_x), xs[0], xs[1], xs[2], _ptr(points_y), ys[0], ys[1], ys[2],
+                                        B, N, M, _ptr(loss), None, None, None, None, _ptr(gx), _ptr(gy),
+                                        _ptr(ws), wsb, _stream())
+        _lib.check(rc, "rma_chamfer_cd_forward")
+    return loss, gx, gy
+
+
+def scale_pair(a: Optional[torch.Tensor], b: Optional[torch.Tensor], scalar: torch.Tensor):
+    """(scalar * a, scalar * b) in one launch; `scalar` is a 0-dim/1-element CUDA tensor read on the device."""
+    ref = a if a is not None else b
+    sc = scalar.to(torch.float32).reshape(1).contiguous()
+    oa = torch.empty_like(a) if a is not None else None
+    ob = torch.empty_like(b) if b is not None else None
+    with torch.cuda.device(ref.device):
+        rc = _lib.load().rma_scale_pair(_ptr(a), 0 if a is None else a.numel(), _ptr(b),
+                                        0 if b is None else b.numel(), _ptr(sc), _ptr(oa), _ptr(ob), _stream())
+        _lib.check(rc, "rma_scale_pair")
+    return oa, ob
+
+
 def sqrdis_map(points_x: torch.Tensor, points_y: torch.Tensor) -> torch.Tensor:
     _check_points("points_x", points_x)
     _check_points("points_y", points_y)

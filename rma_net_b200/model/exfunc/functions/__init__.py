@@ -1,2 +1,2 @@
-from .chamfer_func import Chamfer, ChamferFunction  # noqa: F401
+from .chamfer_func import Chamfer, ChamferCDFunction, ChamferFunction  # noqa: F401
 from .warp_func import Warp, WarpFunction  # noqa: F401

@@ -37,6 +37,23 @@ def _run(x_np, y_np, dev, grads=True):
     return out
 
 
+def _run_fused(x_np, y_np, dev):
+    from rma_net_b200.model.loss import loss_on_cd
+    x = torch.from_numpy(np.ascontiguousarray(x_np)).to(dev).requires_grad_(True)
+    y = torch.from_numpy(np.ascontiguousarray(y_np)).to(dev).requires_grad_(True)
+    loss = loss_on_cd(x, y)
+    (loss * 1.75).backward()          # non-trivial upstream scalar
+    return loss.item(), x.grad.cpu().numpy() / 1.75, y.grad.cpu().numpy() / 1.75
+
+
+def _check_fused(x, y, dev, got):
+    """fused loss_on_cd == unfused composition (same indices -> gradients equal up to fp32 atomics order)."""
+    loss, gx, gy = _run_fused(x, y, dev)
+    assert abs(loss - got["loss"]) <= 2e-6 * abs(got["loss"]) + 1e-30
+    np.testing.assert_allclose(gx, got["grad_x"], rtol=0, atol=2e-6 * np.abs(got["grad_x"]).max() + 1e-30)
+    np.testing.assert_allclose(gy, got["grad_y"], rtol=0, atol=2e-6 * np.abs(got["grad_y"]).max() + 1e-30)
+
+
 def _check_vs_exact(x, y, got, exact=None):
     exact = exact or c_oracle.chamfer_fwd(x, y, "f64")
     np.testing.assert_allclose(got["dist1"], exact["dist1"], rtol=REL, atol=1e-37)
@@ -71,6 +88,7 @@ def test_golden_fixtures(cuda, golden_dir, case):
     _check_vs_exact(x, y, got)
     _check_bit_exact_f32(x, y, got)
     _check_grads(x, y, got)
+    _check_fused(x, y, cuda, got)
     # against the reference's own fp32 outputs, at the reference's error bound
     scale = float((x.astype(np.float64) ** 2).sum(-1).max() + (y.astype(np.float64) ** 2).sum(-1).max())
     atol = 8 * 2.0 ** -24 * scale
@@ -110,6 +128,7 @@ def test_ragged_shapes(cuda, B, N, M, dist):
     _check_vs_exact(x, y, got)
     _check_bit_exact_f32(x, y, got)
     _check_grads(x, y, got)
+    _check_fused(x, y, cuda, got)
 
 
 def test_exact_ties_lowest_index(cuda):
@@ -211,6 +230,15 @@ def test_heavy_scatter_contention(cuda, golden_dir):
     got = _run(x, y, cuda)
     assert np.all(got["idx1"] == 0)
     _check_grads(x, y, got)
+    _check_fused(x, y, cuda, got)
+    # fused op with only one side requiring grad, and under no_grad
+    from rma_net_b200.model.loss import loss_on_cd
+    xt = torch.from_numpy(x).to(cuda).requires_grad_(True)
+    l = loss_on_cd(xt, torch.from_numpy(y).to(cuda))
+    l.backward()
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), got["grad_x"], atol=2e-6 * np.abs(got["grad_x"]).max())
+    with torch.no_grad():
+        assert abs(loss_on_cd(xt, torch.from_numpy(y).to(cuda)).item() - got["loss"]) <= 2e-6 * got["loss"]
 
 
 def test_sqrdis_map_and_host_entry(cuda):
@@ -265,6 +293,7 @@ def test_baseline_sizes_bit_exact_and_properties(cuda, cfg):
     _check_bit_exact_f32(xn, yn, got)
     _check_vs_exact(xn, yn, got)
     _check_grads(xn, yn, got)
+    _check_fused(xn, yn, cuda, got)
     xd, yd = x.to(cuda), y.to(cuda)
     # swap symmetry: chamfer(y, x) is chamfer(x, y) with the outputs exchanged, bit for bit
     d1s, d2s, i1s, i2s = chamfer_dist_with_idx(yd, xd)
