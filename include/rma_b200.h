@@ -72,19 +72,23 @@ int rma_chamfer_finalize(int B, int N, int M, float* dist1, float* dist2, int32_
 int rma_chamfer_search_config(int B, int N, int M, int* ctas, int* threads, int* splits, int* ctas_per_sm);
 
 /* Fused loss_on_cd (model/loss.py:200-205 on top of chamfer_dist): in the same three launches,
- *   *loss   = 0.5 * (sum dist1 + sum dist2) / B                 (device scalar, overwritten)
- *   grad_x  = d loss / d x  [B,N,3],  grad_y = d loss / d y  [B,M,3]   (contiguous, overwritten; either may be NULL)
- * so that the caller's backward is a scale by the upstream scalar (rma_scale_pair) instead of a second scatter pass
- * plus ~10 small torch kernels.  dist1/dist2/idx1/idx2 are optional outputs (NULL to skip). */
+ *   *loss = 0.5 * (sum dist1 + sum dist2) / B                       (device scalar, overwritten)
+ * and its gradient, split so that only the scattered half needs atomics:
+ *   d loss / d x[b,i] = own_x[b,i,:] + scat_x[b,i,0:3]     own_x [B,N,3], scat_x [B,N,4] (16-byte aligned)
+ *   d loss / d y[b,j] = own_y[b,j,:] + scat_y[b,j,0:3]     own_y [B,M,3], scat_y [B,M,4]
+ * (all overwritten; pass own_x = scat_x = NULL and/or own_y = scat_y = NULL when that cloud needs no gradient).
+ * The caller's backward is then rma_chamfer_cd_backward: one launch instead of a second scatter pass plus ~10
+ * small torch kernels.  dist1/dist2/idx1/idx2 are optional outputs (NULL to skip). */
 int rma_chamfer_cd_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
                            const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
                            int B, int N, int M, float* loss, float* dist1, float* dist2, int32_t* idx1,
-                           int32_t* idx2, float* grad_x, float* grad_y, void* workspace, size_t workspace_bytes,
-                           void* stream);
-/* out_a[i] = *scalar_dev * a[i] (i < na), out_b[i] = *scalar_dev * b[i] (i < nb) in one launch; the scalar is read
- * on the device (no host sync).  Either half may be empty (n = 0). */
-int rma_scale_pair(const float* a, int64_t na, const float* b, int64_t nb, const float* scalar_dev, float* out_a,
-                   float* out_b, void* stream);
+                           int32_t* idx2, float* own_x, float* scat_x, float* own_y, float* scat_y,
+                           void* workspace, size_t workspace_bytes, void* stream);
+/* out_x[p,c] = *scalar_dev * (own_x[p,c] + scat_x[p,c]) for p < nx points (out_x [nx,3]); same for y.  The upstream
+ * scalar is read on the device (no host sync).  Either half may be empty (n = 0). */
+int rma_chamfer_cd_backward(const float* own_x, const float* scat_x, int64_t nx, const float* own_y,
+                            const float* scat_y, int64_t ny, const float* scalar_dev, float* out_x, float* out_y,
+                            void* stream);
 
 /* Backward of the above.  Replaces the implicit torch autograd of loss.py:45-70 (MinBackward x2, BmmBackward,
  * MulBackward — SURVEY.md §8a row a4).  g1 [B,N], g2 [B,M] contiguous upstream gradients (either may be NULL = 0).

@@ -26,7 +26,8 @@ constexpr int kSearchThreads = 32 * kSearchWarps;
 constexpr int kRowsPerCta = kRowsPerWarp * kSearchWarps;  // 2048
 constexpr int kTile = 32;                               // columns per tile (= lanes, for the column transpose)
 constexpr int kChunk = 1024;                            // columns staged in shared memory at a time
-constexpr int kCbStride = 33;                           // padded row of the per-warp column-min transpose buffer
+constexpr int kCbStride = 36;                           // row stride (floats) of the per-warp column-min transpose
+                                                        // buffer: 16-B aligned rows, conflict-free LDS.128 / STS.32
 constexpr float kRowSentinel = 1e18f;                   // padded source rows:  d ~ 3e36 against real targets
 constexpr float kColSentinelNeg = 3e18f;                // padded target columns (stored negated): d ~ 2.7e37
 
@@ -37,7 +38,7 @@ struct Geometry {
   int nRBC;   // CTA row blocks (2048 rows) per batch element
   int Mp;     // padded column count: roundup(M, 32) + 32
   __host__ __device__ size_t rowpack_floats() const { return (size_t)B * Npad * 3; }
-  __host__ __device__ size_t colpack_float4() const { return (size_t)B * Mp * 2; }
+  __host__ __device__ size_t colpack_float4() const { return (size_t)B * Mp; }
 };
 
 static Geometry make_geometry(int B, int N, int M) {
@@ -54,7 +55,7 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct Workspace {
   float* rowpack;   // [B][nRB][12][32] float4 : per-thread 16 rows as x[16], y[16], z[16], lane-coalesced
-  float4* colpack;  // [B][Mp][2] float4       : (-x,-x,-y,-y), (-z,-z,0,0)
+  float4* colpack;  // [B][Mp] float4          : (-x, -y, -z, 0)
   u64* rowbest;     // [B][Npad]               : (dist bits << 32) | tile start column
   u64* colbest;     // [B][Mp]                 : (dist bits << 32) | 16-row group id
   size_t bytes;
@@ -78,8 +79,8 @@ static Workspace carve(const Geometry& g, void* base) {
 __global__ void __launch_bounds__(256) chamfer_prep_kernel(
     const float* __restrict__ x, long long xsb, long long xsn, long long xsc,
     const float* __restrict__ y, long long ysb, long long ysn, long long ysc,
-    Geometry g, Workspace w, float* __restrict__ zero_loss, float* __restrict__ zero_gx,
-    float* __restrict__ zero_gy) {
+    Geometry g, Workspace w, float* __restrict__ zero_loss, float4* __restrict__ zero_gx,
+    float4* __restrict__ zero_gy) {
   const long long nrow = (long long)g.B * g.Npad;
   const long long ncol = (long long)g.B * g.Mp;
   if (zero_loss && blockIdx.x == 0 && threadIdx.x == 0) *zero_loss = 0.f;
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(256) chamfer_prep_kernel(
       if (i < g.N) {
         const float* s = x + b * xsb + i * xsn;
         px = s[0]; py = s[xsc]; pz = s[2 * xsc];
-        if (zero_gx) { float* o = zero_gx + ((long long)b * g.N + i) * 3; o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; }
+        if (zero_gx) zero_gx[(long long)b * g.N + i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       const int rb = i / kRowsPerWarp, lane = (i % kRowsPerWarp) / kRowsPerThread, r = i % kRowsPerThread;
       // float4 slot q = c*4 + r/4 of this (row block, lane); element r%4
@@ -108,10 +109,9 @@ __global__ void __launch_bounds__(256) chamfer_prep_kernel(
       if (j < g.M) {
         const float* s = y + b * ysb + j * ysn;
         nx = -s[0]; ny = -s[ysc]; nz = -s[2 * ysc];
-        if (zero_gy) { float* o = zero_gy + ((long long)b * g.M + j) * 3; o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; }
+        if (zero_gy) zero_gy[(long long)b * g.M + j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      w.colpack[2 * u] = make_float4(nx, nx, ny, ny);
-      w.colpack[2 * u + 1] = make_float4(nz, nz, 0.f, 0.f);
+      w.colpack[u] = make_float4(nx, ny, nz, 0.f);
       w.colbest[u] = ~0ull;
     }
   }
@@ -122,8 +122,13 @@ __global__ void __launch_bounds__(256) chamfer_prep_kernel(
 // ---------------------------------------------------------------------------------------------------------------
 // One column against the thread's 16 rows (8 packed row pairs): 3 FADD2 + FMUL2 + 2 FFMA2 per row pair.
 // Returns the minimum over the 16 rows (7 FMNMX3 + 1 FMNMX).
+// One column against the thread's 16 rows (8 packed row pairs): 3 FADD2 + FMUL2 + 2 FFMA2 per row pair.
+// (ncx, ncy, ncz) are the NEGATED column coordinates; pack2(c, c) lowers to the broadcast-scalar operand form
+// (FADD2 R, R.F32x2, Rc.F32), so a column costs one LDS.128.  Returns the minimum over the 16 rows
+// (7 FMNMX3 + 1 FMNMX).
 __device__ __forceinline__ float column_step(const u64 (&px)[8], const u64 (&py)[8], const u64 (&pz)[8],
-                                             u64 cx, u64 cy, u64 cz, float (&d)[16]) {
+                                             float ncx, float ncy, float ncz, float (&d)[16]) {
+  const u64 cx = pack2(ncx, ncx), cy = pack2(ncy, ncy), cz = pack2(ncz, ncz);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const u64 dx = add2(px[k], cx), dy = add2(py[k], cy), dz = add2(pz[k], cz);
@@ -148,14 +153,17 @@ struct SearchArgs {
   u64* rowbest;
   u64* colbest;
   int N, M, nRB, Npad, nRBC, Mp, S;
+  long long* trace;   // experiments: per-CTA (start, after prologue, end, smid) clock64 stamps, or null
 };
 
 __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(SearchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* scol = reinterpret_cast<float4*>(smem_raw);                                    // [kChunk + 2][2]
-  float* cball = reinterpret_cast<float*>(smem_raw + (size_t)(kChunk + 2) * 2 * sizeof(float4));  // [warps][2][32][33]
+  float4* scol = reinterpret_cast<float4*>(smem_raw);                                       // [kChunk + 4]
+  float* cball = reinterpret_cast<float*>(smem_raw + (size_t)(kChunk + 4) * sizeof(float4));  // [warps][2][32][36]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  long long tr0 = 0, tr1 = 0;
+  if (a.trace) tr0 = clock64();
   const int s = blockIdx.x % a.S;
   const int rbc = (blockIdx.x / a.S) % a.nRBC;
   const int b = blockIdx.x / (a.S * a.nRBC);
@@ -185,10 +193,10 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
 #pragma unroll
   for (int r = 0; r < kRowsPerThread; ++r) { m[r] = __int_as_float(0x7f800000); mt[r] = 0; }
 
-  const float4* cp = a.colpack + ((size_t)b * a.Mp + c0) * 2;
+  const float4* cp = a.colpack + ((size_t)b * a.Mp + c0);
 
   // Column direction, software-pipelined: while tile t is being computed, lane l reduces column l of tile t-1
-  // (32 per-lane partial minima in the other half of the double buffer), two values per inner step, so the
+  // (32 per-lane partial minima in the other half of the double buffer), four values per loop body, so the
   // dependent compare/select chain hides behind the FP32 work instead of stalling at every tile boundary.
   int pend_start = -1;   // first column of the tile whose column reduce is pending (warp-uniform)
   int parity = 0;
@@ -196,8 +204,9 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
   for (int cs = 0; cs < ncols; cs += kChunk) {
     const int nc = min(kChunk, ncols - cs);
     __syncthreads();   // previous chunk fully consumed
-    for (int idx = tid; idx < nc * 2; idx += kSearchThreads) scol[idx] = cp[(size_t)cs * 2 + idx];
+    for (int idx = tid; idx < nc; idx += kSearchThreads) scol[idx] = cp[(size_t)cs + idx];
     __syncthreads();
+    if (a.trace && cs == 0) tr1 = clock64();
     if (!has_rows) continue;
 
 #pragma unroll 1
@@ -205,42 +214,45 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
       float tm[kRowsPerThread];
 #pragma unroll
       for (int r = 0; r < kRowsPerThread; ++r) tm[r] = __int_as_float(0x7f800000);
-      const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(scol + (size_t)t0 * 2);
-      float* cbw = cb + parity * (kTile * kCbStride) + lane;                       // this tile: [col][lane]
-      const float* cbr = cb + (parity ^ 1) * (kTile * kCbStride) + lane * kCbStride;  // previous tile: my column
+      const float4* sp = scol + t0;
+      float* cbw = cb + parity * (kTile * kCbStride) + lane;                          // this tile: [col][lane]
+      const float4* cbr = reinterpret_cast<const float4*>(cb + (parity ^ 1) * (kTile * kCbStride) +
+                                                          lane * kCbStride);          // previous tile: my column
       float pm = __int_as_float(0x7f800000);
       int pid = 0;
 
-      // operands of the first step; every step prefetches the next one (the last prefetch of a chunk reads the
-      // 2-column pad behind the staged data and is never used)
-      ulonglong2 n0 = sp[0];
-      u64 n0z = *reinterpret_cast<const u64*>(&sp[1]);
-      ulonglong2 n1 = sp[2];
-      u64 n1z = *reinterpret_cast<const u64*>(&sp[3]);
+      // operands of the first four columns; every body prefetches the next four (the last prefetch of a chunk
+      // reads the 4-column pad behind the staged data and is never used)
+      float4 n0 = sp[0], n1 = sp[1], n2 = sp[2], n3 = sp[3];
 
-#pragma unroll 2
-      for (int jj = 0; jj < kTile; jj += 2) {
-        const ulonglong2 a0 = n0, b0 = n1;
-        const u64 az = n0z, bz = n1z;
-        n0 = sp[2 * jj + 4];
-        n0z = *reinterpret_cast<const u64*>(&sp[2 * jj + 5]);
-        n1 = sp[2 * jj + 6];
-        n1z = *reinterpret_cast<const u64*>(&sp[2 * jj + 7]);
-        const float v0 = cbr[jj], v1 = cbr[jj + 1];
-        float dA[16], dB[16];
-        const float cmA = column_step(px, py, pz, a0.x, a0.y, az, dA);
-        const float cmB = column_step(px, py, pz, b0.x, b0.y, bz, dB);
+#pragma unroll 1
+      for (int jj = 0; jj < kTile; jj += 4) {
+        const float4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
+        n0 = sp[jj + 4]; n1 = sp[jj + 5]; n2 = sp[jj + 6]; n3 = sp[jj + 7];
+        const float4 pv = cbr[jj >> 2];          // 4 partial minima of the pending tile (garbage for the first)
+        {
+          float dA[16], dB[16];
+          const float cmA = column_step(px, py, pz, q0.x, q0.y, q0.z, dA);
+          const float cmB = column_step(px, py, pz, q1.x, q1.y, q1.z, dB);
 #pragma unroll
-        for (int r = 0; r < kRowsPerThread; ++r) tm[r] = min3(tm[r], dA[r], dB[r]);
-        cbw[jj * kCbStride] = cmA;
-        cbw[(jj + 1) * kCbStride] = cmB;
+          for (int r = 0; r < kRowsPerThread; ++r) tm[r] = min3(tm[r], dA[r], dB[r]);
+          cbw[jj * kCbStride] = cmA;
+          cbw[(jj + 1) * kCbStride] = cmB;
+        }
+        {
+          float dA[16], dB[16];
+          const float cmA = column_step(px, py, pz, q2.x, q2.y, q2.z, dA);
+          const float cmB = column_step(px, py, pz, q3.x, q3.y, q3.z, dB);
+#pragma unroll
+          for (int r = 0; r < kRowsPerThread; ++r) tm[r] = min3(tm[r], dA[r], dB[r]);
+          cbw[(jj + 2) * kCbStride] = cmA;
+          cbw[(jj + 3) * kCbStride] = cmB;
+        }
         // pending column reduce: ascending lane order + strict '<' = lowest lane (lowest rows) wins ties
-        const bool l0 = v0 < pm;
-        pm = l0 ? v0 : pm;
-        pid = l0 ? jj : pid;
-        const bool l1 = v1 < pm;
-        pm = l1 ? v1 : pm;
-        pid = l1 ? jj + 1 : pid;
+        bool l = pv.x < pm; pm = l ? pv.x : pm; pid = l ? jj : pid;
+        l = pv.y < pm; pm = l ? pv.y : pm; pid = l ? jj + 1 : pid;
+        l = pv.z < pm; pm = l ? pv.z : pm; pid = l ? jj + 2 : pid;
+        l = pv.w < pm; pm = l ? pv.w : pm; pid = l ? jj + 3 : pid;
       }
 
       // Row direction: strict '<' keeps the earliest tile on ties (lowest index, torch.min semantics).
@@ -286,6 +298,14 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
       if (i0 + r < a.N) atomicMin(rbest + r, ((u64)__float_as_uint(m[r]) << 32) | (unsigned)mt[r]);
     }
   }
+  if (a.trace && tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    long long* t = a.trace + (size_t)blockIdx.x * 5;
+    t[0] = tr0; t[1] = tr1; t[2] = clock64(); t[3] = smid; t[4] = gt;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -320,19 +340,31 @@ __device__ __forceinline__ void scatter_add3(float* dst, long long key, bool liv
   }
 }
 
+// Warp-aggregated scatter into a float4-strided buffer: one 16-byte vector atomic (RED.128) per distinct target.
+__device__ __forceinline__ void scatter_add4(float4* dst, long long key, bool live, float vx, float vy, float vz) {
+  if (!live) key = -1 - (long long)lane_id();
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  if (__any_sync(0xffffffffu, peers != (1u << lane_id()))) reduce_peers(peers, vx, vy, vz);
+  if (live && (unsigned)(__ffs(peers) - 1) == lane_id()) atomicAdd(dst, make_float4(vx, vy, vz, 0.f));
+}
+
 struct FinalizeArgs {
   float* dist1; float* dist2; int* idx1; int* idx2;   // any may be null
   float* loss;       // null, or [1] accumulator (zeroed by prep): += coef_loss * (sum dist1 + sum dist2)
-  float* grad_x;     // null, or [B,N,3] (zeroed by prep): d(coef_loss * sum)/dx
-  float* grad_y;     // null, or [B,M,3]
+  // Fused gradient of coef_loss * (sum dist1 + sum dist2), split so that only the scattered half needs atomics:
+  //   d/dx[b,i] = own_x[b,i] + scat_x[b,i].xyz      own_*: plain stores, one writer per point
+  //   d/dy[b,j] = own_y[b,j] + scat_y[b,j].xyz      scat_*: float4-strided, zeroed by prep, vector atomics
+  float* own_x; float* own_y;      // null or [B,N,3] / [B,M,3]
+  float4* scat_x; float4* scat_y;  // null or [B,N] / [B,M]
   float coef_loss;   // 0.5 / B for loss_on_cd
 };
 
 constexpr int kFinWarps = 8;
 
 // One warp per block of 32 items.  Row item: the 32 columns of the winning tile are evaluated by the 32 lanes
-// (one coalesced 1 KB read), warp-min + ballot give the first minimum.  Column item: the 16 rows of the winning
-// row group are evaluated by a half warp.  Distances use sqdist_neg = the search kernel's operation order.
+// (one coalesced 1 KB read); the winning VALUE is already known from the key, so a ballot on equality gives the
+// first minimum.  Column item: the 16 rows of the winning row group are evaluated by a half warp.
+// Distances use sqdist_neg = the search kernel's operation order, so equality is exact.
 __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geometry g, Workspace w, FinalizeArgs f) {
   __shared__ float4 stage[kFinWarps][32];
   __shared__ double lsum[kFinWarps];
@@ -341,7 +373,6 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const long long wi = (long long)blockIdx.x * kFinWarps + warp;
   const float coef_grad = 2.f * f.coef_loss;
-  const bool fused = f.grad_x != nullptr || f.grad_y != nullptr;
   float myd = 0.f;
   bool valid = false;
 
@@ -352,7 +383,9 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
     float x = 0.f, y = 0.f, z = 0.f;
     if (valid) {
       b = (int)(t / g.N); i = (int)(t % g.N);
-      jt = (int)(unsigned)(w.rowbest[(size_t)b * g.Npad + i] & 0xffffffffu);
+      const u64 key = w.rowbest[(size_t)b * g.Npad + i];
+      jt = (int)(unsigned)(key & 0xffffffffu);
+      myd = __uint_as_float((unsigned)(key >> 32));
       const int rb = i / kRowsPerWarp, ln = (i % kRowsPerWarp) / kRowsPerThread, r = i % kRowsPerThread;
       const size_t base = ((size_t)(b * g.nRB + rb) * 12) * 32 + ln;
       const int q = r >> 2, e = r & 3;
@@ -363,31 +396,28 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
     stage[warp][lane] = make_float4(__int_as_float(b * g.Mp + jt), x, y, z);
     __syncwarp();
     int myj = 0;
-#pragma unroll 8
+#pragma unroll 16
     for (int r = 0; r < 32; ++r) {
       const float4 sv = stage[warp][r];
-      const float4* cp = w.colpack + ((size_t)__float_as_int(sv.x) + lane) * 2;
-      const float4 c0 = cp[0], c1 = cp[1];
-      const unsigned d = __float_as_uint(sqdist_neg(sv.y, sv.z, sv.w, c0.x, c0.z, c1.x));
-      const unsigned dm = __reduce_min_sync(0xffffffffu, d);       // d >= 0: unsigned order == float order
-      const unsigned hit = __ballot_sync(0xffffffffu, d == dm);
-      if (lane == r) { myd = __uint_as_float(dm); myj = __ffs(hit) - 1; }
+      const float4 c = w.colpack[(size_t)__float_as_int(sv.x) + lane];
+      const float d = sqdist_neg(sv.y, sv.z, sv.w, c.x, c.y, c.z);
+      const float vr = __shfl_sync(0xffffffffu, myd, r);
+      const unsigned hit = __ballot_sync(0xffffffffu, d == vr);
+      if (lane == r) myj = hit ? __ffs(hit) - 1 : 0;
     }
     const int j = jt + myj;
     if (valid) {
       if (f.dist1) f.dist1[t] = myd;
       if (f.idx1) f.idx1[t] = j;
     }
-    if (fused) {
+    if (f.own_x || f.scat_y) {
       float vx = 0.f, vy = 0.f, vz = 0.f;
       if (valid) {
-        const float4* cp = w.colpack + ((size_t)b * g.Mp + j) * 2;
-        const float4 c0 = cp[0], c1 = cp[1];
-        vx = coef_grad * (x + c0.x); vy = coef_grad * (y + c0.z); vz = coef_grad * (z + c1.x);
-        if (f.grad_x) { float* o = f.grad_x + t * 3; atomicAdd(o, vx); atomicAdd(o + 1, vy); atomicAdd(o + 2, vz); }
+        const float4 c = w.colpack[(size_t)b * g.Mp + j];
+        vx = coef_grad * (x + c.x); vy = coef_grad * (y + c.y); vz = coef_grad * (z + c.z);
+        if (f.own_x) { float* o = f.own_x + t * 3; o[0] = vx; o[1] = vy; o[2] = vz; }
       }
-      if (f.grad_y)
-        scatter_add3(f.grad_y + ((long long)b * g.M + j) * 3, (long long)b * g.M + j, valid, -vx, -vy, -vz);
+      if (f.scat_y) scatter_add4(f.scat_y + ((long long)b * g.M + j), (long long)b * g.M + j, valid, -vx, -vy, -vz);
     }
   } else {
     const long long t = (wi - row_warps) * 32 + lane;
@@ -396,10 +426,11 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
     float nx = 0.f, ny = 0.f, nz = 0.f;
     if (valid) {
       b = (int)(t / g.M); j = (int)(t % g.M);
-      grp = (int)(unsigned)(w.colbest[(size_t)b * g.Mp + j] & 0xffffffffu);
-      const float4* cp = w.colpack + ((size_t)b * g.Mp + j) * 2;
-      const float4 c0 = cp[0], c1 = cp[1];
-      nx = c0.x; ny = c0.z; nz = c1.x;
+      const u64 key = w.colbest[(size_t)b * g.Mp + j];
+      grp = (int)(unsigned)(key & 0xffffffffu);
+      myd = __uint_as_float((unsigned)(key >> 32));
+      const float4 c = w.colpack[(size_t)b * g.Mp + j];
+      nx = c.x; ny = c.y; nz = c.z;
       fbase = (((b * g.nRB + (grp >> 5)) * 12) * 32 + (grp & 31)) * 4;   // float index of (group, q = 0, e = 0)
     }
     stage[warp][lane] = make_float4(__int_as_float(fbase), nx, ny, nz);
@@ -407,35 +438,32 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
     const int half = lane >> 4, rr = lane & 15;
     const int roff = ((rr >> 2) * 32) * 4 + (rr & 3);                      // row rr inside a group
     int myi = 0;
-#pragma unroll 4
+#pragma unroll 16
     for (int p = 0; p < 16; ++p) {
       const int r = half * 16 + p;                                          // item handled by this half warp
       const float4 sv = stage[warp][r];
       const float* rp = w.rowpack + __float_as_int(sv.x) + roff;
       const float x = rp[0], y = rp[4 * 32 * 4], z = rp[8 * 32 * 4];
-      const unsigned d = __float_as_uint(sqdist_neg(x, y, z, sv.y, sv.z, sv.w));
-      unsigned dm = d;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) dm = min(dm, __shfl_xor_sync(0xffffffffu, dm, o));
-      const unsigned hit = (__ballot_sync(0xffffffffu, d == dm) >> (half * 16)) & 0xffffu;
-      if (lane == r) { myd = __uint_as_float(dm); myi = __ffs(hit) - 1; }
+      const float d = sqdist_neg(x, y, z, sv.y, sv.z, sv.w);
+      const float vr = __shfl_sync(0xffffffffu, myd, r);
+      const unsigned hit = (__ballot_sync(0xffffffffu, d == vr) >> (half * 16)) & 0xffffu;
+      if (lane == r) myi = hit ? __ffs(hit) - 1 : 0;
     }
     const int i = grp * kRowsPerThread + myi;
     if (valid) {
       if (f.dist2) f.dist2[t] = myd;
       if (f.idx2) f.idx2[t] = i;
     }
-    if (fused) {
+    if (f.own_y || f.scat_x) {
       float vx = 0.f, vy = 0.f, vz = 0.f;
       if (valid) {
         const float* rp = w.rowpack + fbase + ((myi >> 2) * 32) * 4 + (myi & 3);
         const float x = rp[0], y = rp[4 * 32 * 4], z = rp[8 * 32 * 4];
         // d/dy_j |y_j - x_i|^2 = 2 (y_j - x_i) = -2 (x_i + (-y_j))
         vx = -coef_grad * (x + nx); vy = -coef_grad * (y + ny); vz = -coef_grad * (z + nz);
-        if (f.grad_y) { float* o = f.grad_y + t * 3; atomicAdd(o, vx); atomicAdd(o + 1, vy); atomicAdd(o + 2, vz); }
+        if (f.own_y) { float* o = f.own_y + t * 3; o[0] = vx; o[1] = vy; o[2] = vz; }
       }
-      if (f.grad_x)
-        scatter_add3(f.grad_x + ((long long)b * g.N + i) * 3, (long long)b * g.N + i, valid, -vx, -vy, -vz);
+      if (f.scat_x) scatter_add4(f.scat_x + ((long long)b * g.N + i), (long long)b * g.N + i, valid, -vx, -vy, -vz);
     }
   }
 
@@ -540,7 +568,7 @@ __global__ void unpack_keys_kernel(const u64* __restrict__ keys, long long n, fl
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-constexpr size_t kSearchSmem = (size_t)(kChunk + 2) * 2 * sizeof(float4) + (size_t)kSearchWarps * 2 * kTile * kCbStride * sizeof(float);
+constexpr size_t kSearchSmem = (size_t)(kChunk + 4) * sizeof(float4) + (size_t)kSearchWarps * 2 * kTile * kCbStride * sizeof(float);
 
 struct DeviceCaps { int sms; int search_occ; };
 
@@ -626,6 +654,9 @@ size_t rma_chamfer_workspace_bytes(int B, int N, int M) {
   return carve(g, nullptr).bytes;
 }
 
+static long long* g_trace = nullptr;   // experiment hooks, see rma_exp_set_search_debug
+static int g_force_splits = 0;
+
 static int forward_setup(const float* x, const float* y, int B, int N, int M, void* workspace,
                          size_t workspace_bytes, Geometry* g, Workspace* w) {
   if (!x || !y || !workspace || !sizes_ok(B, N, M)) return RMA_E_BADARG;
@@ -638,7 +669,7 @@ static int forward_setup(const float* x, const float* y, int B, int N, int M, vo
 
 static int launch_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
                        const float* y, int64_t ysb, int64_t ysn, int64_t ysc, int B, int N, int M,
-                       void* workspace, size_t workspace_bytes, float* zero_loss, float* zero_gx, float* zero_gy,
+                       void* workspace, size_t workspace_bytes, float* zero_loss, float4* zero_gx, float4* zero_gy,
                        void* stream_) {
   Geometry g; Workspace w;
   if (int e = forward_setup(x, y, B, N, M, workspace, workspace_bytes, &g, &w)) return e;
@@ -668,11 +699,19 @@ int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_by
   a.rowbest = w.rowbest;
   a.colbest = w.colbest;
   a.N = N; a.M = M; a.nRB = g.nRB; a.Npad = g.Npad; a.nRBC = g.nRBC; a.Mp = g.Mp;
-  a.S = choose_splits(g, caps);
+  a.S = g_force_splits > 0 ? g_force_splits : choose_splits(g, caps);
+  a.trace = g_trace;
   const long long ctas = (long long)B * g.nRBC * a.S;
   if (ctas > 0x7fffffffLL) return RMA_E_BADARG;
   chamfer_search_kernel<<<(int)ctas, kSearchThreads, kSearchSmem, (cudaStream_t)stream_>>>(a);
   RMA_LAUNCH_CHECK();
+  return RMA_OK;
+}
+
+// Experiment hooks (tools/search_variants.py only; not part of include/rma_b200.h, not used by the product path).
+int rma_exp_set_search_debug(long long* trace, int force_splits) {
+  g_trace = trace;
+  g_force_splits = force_splits;
   return RMA_OK;
 }
 
@@ -690,7 +729,7 @@ static int launch_finalize(int B, int N, int M, const FinalizeArgs& f, void* wor
 int rma_chamfer_finalize(int B, int N, int M, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
                          void* workspace, size_t workspace_bytes, void* stream_) {
   if (!dist1 || !dist2) return RMA_E_BADARG;
-  FinalizeArgs f = {dist1, dist2, idx1, idx2, nullptr, nullptr, nullptr, 0.f};
+  FinalizeArgs f = {dist1, dist2, idx1, idx2, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
   return launch_finalize(B, N, M, f, workspace, workspace_bytes, stream_);
 }
 
@@ -721,37 +760,52 @@ int rma_chamfer_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
 int rma_chamfer_cd_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
                            const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
                            int B, int N, int M, float* loss, float* dist1, float* dist2, int32_t* idx1,
-                           int32_t* idx2, float* grad_x, float* grad_y, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+                           int32_t* idx2, float* own_x, float* scat_x, float* own_y, float* scat_y,
+                           void* workspace, size_t workspace_bytes, void* stream) {
   if (!loss) return RMA_E_BADARG;
-  if (int e = launch_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, workspace, workspace_bytes, loss, grad_x,
-                          grad_y, stream))
+  if ((own_x == nullptr) != (scat_x == nullptr) || (own_y == nullptr) != (scat_y == nullptr)) return RMA_E_BADARG;
+  if ((((uintptr_t)scat_x) | ((uintptr_t)scat_y)) & 15u) return RMA_E_BADARG;
+  if (int e = launch_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, workspace, workspace_bytes, loss,
+                          (float4*)scat_x, (float4*)scat_y, stream))
     return e;
   if (int e = rma_chamfer_search(B, N, M, workspace, workspace_bytes, stream)) return e;
-  FinalizeArgs f = {dist1, dist2, idx1, idx2, loss, grad_x, grad_y, 0.5f / (float)B};
+  FinalizeArgs f = {dist1, dist2, idx1, idx2, loss, own_x, own_y, (float4*)scat_x, (float4*)scat_y,
+                    0.5f / (float)B};
   return launch_finalize(B, N, M, f, workspace, workspace_bytes, stream);
 }
 
-__global__ void __launch_bounds__(256) scale_pair_kernel(const float* __restrict__ a, long long na,
-                                                         const float* __restrict__ b, long long nb,
-                                                         const float* __restrict__ scalar, float* __restrict__ oa,
-                                                         float* __restrict__ ob) {
+// out[p, c] = scalar * (own[p, c] + scat[p].c): combines the two gradient halves of the fused forward and applies
+// the upstream scalar, both clouds in one launch.
+__global__ void __launch_bounds__(256) cd_backward_kernel(const float* __restrict__ own_x,
+                                                          const float4* __restrict__ scat_x, long long nx,
+                                                          const float* __restrict__ own_y,
+                                                          const float4* __restrict__ scat_y, long long ny,
+                                                          const float* __restrict__ scalar,
+                                                          float* __restrict__ out_x, float* __restrict__ out_y) {
   const float sc = *scalar;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < na + nb;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nx + ny;
        t += (long long)gridDim.x * blockDim.x) {
-    if (t < na) oa[t] = sc * a[t];
-    else ob[t - na] = sc * b[t - na];
+    const bool isx = t < nx;
+    const long long p = isx ? t : t - nx;
+    const float* own = (isx ? own_x : own_y) + p * 3;
+    const float4 s4 = (isx ? scat_x : scat_y)[p];
+    float* o = (isx ? out_x : out_y) + p * 3;
+    o[0] = sc * (own[0] + s4.x); o[1] = sc * (own[1] + s4.y); o[2] = sc * (own[2] + s4.z);
   }
 }
 
-int rma_scale_pair(const float* a, int64_t na, const float* b, int64_t nb, const float* scalar_dev, float* out_a,
-                   float* out_b, void* stream_) {
-  if (!scalar_dev || na < 0 || nb < 0 || (na > 0 && (!a || !out_a)) || (nb > 0 && (!b || !out_b)))
-    return RMA_E_BADARG;
-  if (na + nb == 0) return RMA_OK;
-  long long grid = (na + nb + 255) / 256;
+int rma_chamfer_cd_backward(const float* own_x, const float* scat_x, int64_t nx, const float* own_y,
+                            const float* scat_y, int64_t ny, const float* scalar_dev, float* out_x, float* out_y,
+                            void* stream_) {
+  if (!scalar_dev || nx < 0 || ny < 0) return RMA_E_BADARG;
+  if (nx > 0 && (!own_x || !scat_x || !out_x)) return RMA_E_BADARG;
+  if (ny > 0 && (!own_y || !scat_y || !out_y)) return RMA_E_BADARG;
+  if (nx + ny == 0) return RMA_OK;
+  long long grid = (nx + ny + 255) / 256;
   if (grid > 148LL * 16) grid = 148LL * 16;
-  scale_pair_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream_>>>(a, na, b, nb, scalar_dev, out_a, out_b);
+  cd_backward_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream_>>>(own_x, (const float4*)scat_x, nx, own_y,
+                                                                   (const float4*)scat_y, ny, scalar_dev, out_x,
+                                                                   out_y);
   RMA_LAUNCH_CHECK();
   return RMA_OK;
 }

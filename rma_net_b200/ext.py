@@ -101,7 +101,8 @@ def chamfer_backward(points_x, points_y, idx1, idx2, g1, g2, need_x: bool = True
 
 
 def chamfer_cd_forward(points_x: torch.Tensor, points_y: torch.Tensor, need_x: bool, need_y: bool):
-    """Fused loss_on_cd: returns (loss 0-dim, unit grad_x [B,N,3] or None, unit grad_y [B,M,3] or None)."""
+    """Fused loss_on_cd: returns (loss 0-dim, gx_parts, gy_parts); g*_parts = (own [.,.,3], scat [.,.,4]) or None,
+    with d loss/d cloud = own + scat[..., :3] (combined and scaled by chamfer_cd_backward)."""
     _check_points("points_x", points_x)
     _check_points("points_y", points_y)
     _same_device(points_x, points_y)
@@ -118,27 +119,32 @@ def chamfer_cd_forward(points_x: torch.Tensor, points_y: torch.Tensor, need_x: b
             raise RuntimeError(f"problem size not supported: B={B}, N={N}, M={M}")
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        gx = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if need_x else None
-        gy = torch.empty((B, M, 3), dtype=torch.float32, device=dev) if need_y else None
+        f32 = dict(dtype=torch.float32, device=dev)
+        gx = (torch.empty((B, N, 3), **f32), torch.empty((B, N, 4), **f32)) if need_x else None
+        gy = (torch.empty((B, M, 3), **f32), torch.empty((B, M, 4), **f32)) if need_y else None
         xs, ys = points_x.stride(), points_y.stride()
         rc = lib.rma_chamfer_cd_forward(_ptr(points_x), xs[0], xs[1], xs[2], _ptr(points_y), ys[0], ys[1], ys[2],
-                                        B, N, M, _ptr(loss), None, None, None, None, _ptr(gx), _ptr(gy),
+                                        B, N, M, _ptr(loss), None, None, None, None,
+                                        _ptr(gx[0] if gx else None), _ptr(gx[1] if gx else None),
+                                        _ptr(gy[0] if gy else None), _ptr(gy[1] if gy else None),
                                         _ptr(ws), wsb, _stream())
         _lib.check(rc, "rma_chamfer_cd_forward")
     return loss, gx, gy
 
 
-def scale_pair(a: Optional[torch.Tensor], b: Optional[torch.Tensor], scalar: torch.Tensor):
-    """(scalar * a, scalar * b) in one launch; `scalar` is a 0-dim/1-element CUDA tensor read on the device."""
-    ref = a if a is not None else b
+def chamfer_cd_backward(gx, gy, scalar: torch.Tensor):
+    """(scalar * (own_x + scat_x), scalar * (own_y + scat_y)) in one launch; scalar is read on the device."""
+    ref = (gx or gy)[0]
     sc = scalar.to(torch.float32).reshape(1).contiguous()
-    oa = torch.empty_like(a) if a is not None else None
-    ob = torch.empty_like(b) if b is not None else None
+    ox = torch.empty_like(gx[0]) if gx else None
+    oy = torch.empty_like(gy[0]) if gy else None
     with torch.cuda.device(ref.device):
-        rc = _lib.load().rma_scale_pair(_ptr(a), 0 if a is None else a.numel(), _ptr(b),
-                                        0 if b is None else b.numel(), _ptr(sc), _ptr(oa), _ptr(ob), _stream())
-        _lib.check(rc, "rma_scale_pair")
-    return oa, ob
+        rc = _lib.load().rma_chamfer_cd_backward(
+            _ptr(gx[0] if gx else None), _ptr(gx[1] if gx else None), gx[0].numel() // 3 if gx else 0,
+            _ptr(gy[0] if gy else None), _ptr(gy[1] if gy else None), gy[0].numel() // 3 if gy else 0,
+            _ptr(sc), _ptr(ox), _ptr(oy), _stream())
+        _lib.check(rc, "rma_chamfer_cd_backward")
+    return ox, oy
 
 
 def sqrdis_map(points_x: torch.Tensor, points_y: torch.Tensor) -> torch.Tensor:

@@ -28,24 +28,24 @@ class ChamferFunction(torch.autograd.Function):
 
 class ChamferCDFunction(torch.autograd.Function):
     """loss_on_cd (reference model/loss.py:200-205) as ONE op: 0.5 * (sum dist1 + sum dist2) / B and its gradients
-    w.r.t. both clouds come out of the forward's three launches; backward is a scale by the upstream scalar."""
+    w.r.t. both clouds come out of the forward's three launches; backward is one combine-and-scale launch."""
 
     @staticmethod
     def forward(ctx, deformation_p, p1):
         need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         loss, gx, gy = ext.chamfer_cd_forward(deformation_p, p1, need_x, need_y)
         ctx.has = (gx is not None, gy is not None)
-        ctx.save_for_backward(*[t for t in (gx, gy) if t is not None])
+        ctx.save_for_backward(*[t for pair in (gx, gy) if pair is not None for t in pair])
         return loss
 
     @staticmethod
     def backward(ctx, grad_loss):
         saved = list(ctx.saved_tensors)
-        gx = saved.pop(0) if ctx.has[0] else None
-        gy = saved.pop(0) if ctx.has[1] else None
+        gx = (saved.pop(0), saved.pop(0)) if ctx.has[0] else None
+        gy = (saved.pop(0), saved.pop(0)) if ctx.has[1] else None
         if gx is None and gy is None:
             return None, None
-        return ext.scale_pair(gx, gy, grad_loss)
+        return ext.chamfer_cd_backward(gx, gy, grad_loss)
 
 
 class Chamfer(torch.nn.Module):
