@@ -154,6 +154,7 @@ struct SearchArgs {
   u64* colbest;
   int N, M, nRB, Npad, nRBC, Mp, S;
   long long* trace;   // experiments: per-CTA (start, after prologue, end, smid) clock64 stamps, or null
+  int stagger_ns;     // experiments: delay of the second-wave CTAs (desynchronise co-resident warps)
 };
 
 __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(SearchArgs a) {
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   long long tr0 = 0, tr1 = 0;
   if (a.trace) tr0 = clock64();
+  if (a.stagger_ns > 0 && blockIdx.x >= 148) __nanosleep(a.stagger_ns);
   const int s = blockIdx.x % a.S;
   const int rbc = (blockIdx.x / a.S) % a.nRBC;
   const int b = blockIdx.x / (a.S * a.nRBC);
@@ -367,6 +369,8 @@ constexpr int kFinWarps = 8;
 // Distances use sqdist_neg = the search kernel's operation order, so equality is exact.
 __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geometry g, Workspace w, FinalizeArgs f) {
   __shared__ float4 stage[kFinWarps][32];
+  __shared__ float stagev[kFinWarps][32];
+  __shared__ unsigned hits[kFinWarps][32];
   __shared__ double lsum[kFinWarps];
   const long long nrow = (long long)g.B * g.N, ncol = (long long)g.B * g.M;
   const long long row_warps = (nrow + 31) / 32;
@@ -394,18 +398,25 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
       z = w.rowpack[(base + (size_t)(8 + q) * 32) * 4 + e];
     }
     stage[warp][lane] = make_float4(__int_as_float(b * g.Mp + jt), x, y, z);
+    stagev[warp][lane] = myd;
     __syncwarp();
-    int myj = 0;
-#pragma unroll 16
-    for (int r = 0; r < 32; ++r) {
-      const float4 sv = stage[warp][r];
-      const float4 c = w.colpack[(size_t)__float_as_int(sv.x) + lane];
-      const float d = sqdist_neg(sv.y, sv.z, sv.w, c.x, c.y, c.z);
-      const float vr = __shfl_sync(0xffffffffu, myd, r);
-      const unsigned hit = __ballot_sync(0xffffffffu, d == vr);
-      if (lane == r) myj = hit ? __ffs(hit) - 1 : 0;
+    const float4* cbase = w.colpack + lane;
+#pragma unroll
+    for (int r0 = 0; r0 < 32; r0 += 16) {
+      float4 c[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) c[k] = cbase[__float_as_int(stage[warp][r0 + k].x)];   // 16 loads in flight
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float4 sv = stage[warp][r0 + k];
+        const float d = sqdist_neg(sv.y, sv.z, sv.w, c[k].x, c[k].y, c[k].z);
+        const unsigned hit = __ballot_sync(0xffffffffu, d == stagev[warp][r0 + k]);
+        hits[warp][r0 + k] = hit;     // same value from every lane
+      }
     }
-    const int j = jt + myj;
+    __syncwarp();
+    const unsigned myhit = hits[warp][lane];
+    const int j = jt + (myhit ? __ffs(myhit) - 1 : 0);
     if (valid) {
       if (f.dist1) f.dist1[t] = myd;
       if (f.idx1) f.idx1[t] = j;
@@ -434,21 +445,27 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
       fbase = (((b * g.nRB + (grp >> 5)) * 12) * 32 + (grp & 31)) * 4;   // float index of (group, q = 0, e = 0)
     }
     stage[warp][lane] = make_float4(__int_as_float(fbase), nx, ny, nz);
+    stagev[warp][lane] = myd;
     __syncwarp();
     const int half = lane >> 4, rr = lane & 15;
-    const int roff = ((rr >> 2) * 32) * 4 + (rr & 3);                      // row rr inside a group
-    int myi = 0;
-#pragma unroll 16
+    const float* rbase = w.rowpack + ((rr >> 2) * 32) * 4 + (rr & 3);      // row rr inside a group
+    float rx[16], ry[16], rz[16];
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {                                          // 48 loads in flight
+      const float* rp = rbase + __float_as_int(stage[warp][half * 16 + p].x);
+      rx[p] = rp[0]; ry[p] = rp[4 * 32 * 4]; rz[p] = rp[8 * 32 * 4];
+    }
+#pragma unroll
     for (int p = 0; p < 16; ++p) {
       const int r = half * 16 + p;                                          // item handled by this half warp
       const float4 sv = stage[warp][r];
-      const float* rp = w.rowpack + __float_as_int(sv.x) + roff;
-      const float x = rp[0], y = rp[4 * 32 * 4], z = rp[8 * 32 * 4];
-      const float d = sqdist_neg(x, y, z, sv.y, sv.z, sv.w);
-      const float vr = __shfl_sync(0xffffffffu, myd, r);
-      const unsigned hit = (__ballot_sync(0xffffffffu, d == vr) >> (half * 16)) & 0xffffu;
-      if (lane == r) myi = hit ? __ffs(hit) - 1 : 0;
+      const float d = sqdist_neg(rx[p], ry[p], rz[p], sv.y, sv.z, sv.w);
+      const unsigned hit = __ballot_sync(0xffffffffu, d == stagev[warp][r]);
+      hits[warp][r] = (hit >> (half * 16)) & 0xffffu;   // same value from every lane of the half warp
     }
+    __syncwarp();
+    const unsigned myhit = hits[warp][lane];
+    const int myi = myhit ? __ffs(myhit) - 1 : 0;
     const int i = grp * kRowsPerThread + myi;
     if (valid) {
       if (f.dist2) f.dist2[t] = myd;
@@ -656,6 +673,7 @@ size_t rma_chamfer_workspace_bytes(int B, int N, int M) {
 
 static long long* g_trace = nullptr;   // experiment hooks, see rma_exp_set_search_debug
 static int g_force_splits = 0;
+static int g_stagger_ns = 0;
 
 static int forward_setup(const float* x, const float* y, int B, int N, int M, void* workspace,
                          size_t workspace_bytes, Geometry* g, Workspace* w) {
@@ -701,6 +719,7 @@ int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_by
   a.N = N; a.M = M; a.nRB = g.nRB; a.Npad = g.Npad; a.nRBC = g.nRBC; a.Mp = g.Mp;
   a.S = g_force_splits > 0 ? g_force_splits : choose_splits(g, caps);
   a.trace = g_trace;
+  a.stagger_ns = g_stagger_ns;
   const long long ctas = (long long)B * g.nRBC * a.S;
   if (ctas > 0x7fffffffLL) return RMA_E_BADARG;
   chamfer_search_kernel<<<(int)ctas, kSearchThreads, kSearchSmem, (cudaStream_t)stream_>>>(a);
@@ -709,9 +728,10 @@ int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_by
 }
 
 // Experiment hooks (tools/search_variants.py only; not part of include/rma_b200.h, not used by the product path).
-int rma_exp_set_search_debug(long long* trace, int force_splits) {
+int rma_exp_set_search_debug(long long* trace, int force_splits, int stagger_ns) {
   g_trace = trace;
   g_force_splits = force_splits;
+  g_stagger_ns = stagger_ns;
   return RMA_OK;
 }
 

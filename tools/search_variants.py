@@ -14,12 +14,7 @@ from bench import WORKLOADS, make_workload  # noqa: E402
 from rma_net_b200 import _lib, build as b  # noqa: E402
 
 VARIANTS = {
-    "base_phase": [],
-    "order0": ["-DRMA_EXP_ORDER=0"],
-    "phase_no_tree": ["-DRMA_EXP_NO_TREE"],
-    "phase_no_rowmin": ["-DRMA_EXP_NO_ROWMIN"],
-    "order0_no_tree": ["-DRMA_EXP_ORDER=0", "-DRMA_EXP_NO_TREE"],
-    "order0_no_rowmin": ["-DRMA_EXP_ORDER=0", "-DRMA_EXP_NO_ROWMIN"],
+    "base": [],
 }
 
 
@@ -41,15 +36,15 @@ def main():
         lib = ctypes.CDLL(build_variant(name, flags))
         for fn, (rt, at) in _lib.SIGNATURES.items():
             f = getattr(lib, fn); f.restype = rt; f.argtypes = at
-        lib.rma_exp_set_search_debug.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.rma_exp_set_search_debug.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         wsb = lib.rma_chamfer_workspace_bytes(B, N, M)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         P = lambda t: ctypes.c_void_p(t.data_ptr())
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         xs, ys = xd.stride(), yd.stride()
-        for splits in ([0, 4] if name in ("base_phase", "order0") else [0]):
+        for splits, stagger in [(0, 0), (0, 300), (0, 600), (0, 1000), (0, 1500), (0, 2500), (8, 0), (8, 1000), (16, 0), (16, 1000)]:
             trace = torch.zeros(4096 * 5, dtype=torch.int64, device=dev)
-            lib.rma_exp_set_search_debug(P(trace) if splits == 0 else None, splits)
+            lib.rma_exp_set_search_debug(P(trace) if splits == 0 else None, splits, stagger)
             times = []
             for it in range(12):
                 lib.rma_chamfer_prep(P(xd), xs[0], xs[1], xs[2], P(yd), ys[0], ys[1], ys[2], B, N, M, P(ws), wsb, st)
@@ -61,7 +56,7 @@ def main():
                 assert rc == 0, rc
                 if it >= 2:
                     times.append(e0.elapsed_time(e1) * 1e3)
-            key = f"{name}/S={splits or 'auto'}"
+            key = f"{name}/S={splits or 'auto'}/stagger={stagger}"
             res[key] = {"us_min": min(times), "us_med": sorted(times)[len(times) // 2]}
             if splits == 0:
                 t = trace.cpu().view(-1, 5)
