@@ -43,6 +43,13 @@ SIGNATURES = {
     "rma_chamfer_loss_host": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
 }
 
+# Experiment / test hooks exported by the library but deliberately not part of include/rma_b200.h.
+EXPERIMENT_SIGNATURES = {
+    "rma_exp_set_chamfer_path": (c_int, [c_int, c_int64]),        # 0 auto, 1 exact search, 2 filter + resolve
+    "rma_exp_chamfer_path_info": (c_int, [c_int, c_int, c_int, _P, _P, _P]),
+    "rma_exp_set_search_debug": (c_int, [_P, c_int, c_int]),
+}
+
 _lib = None
 
 
@@ -62,6 +69,10 @@ def load() -> ctypes.CDLL:
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    for name, (res, args) in EXPERIMENT_SIGNATURES.items():
+        fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
     _lib = lib

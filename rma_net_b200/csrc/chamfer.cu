@@ -12,7 +12,7 @@
 //   3. chamfer_finalize_kernel resolves the coarse index (a 32-column tile / a 16-row group) to the exact first
 //                              minimum by re-evaluating that tile with the identical operation order
 // Backward: memset + one scatter kernel with warp-aggregated atomics.
-#include "common.cuh"
+#include "chamfer_common.cuh"
 #include "../../include/rma_b200.h"
 
 #include <cstdio>
@@ -51,8 +51,6 @@ static Geometry make_geometry(int B, int N, int M) {
   return g;
 }
 
-static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-
 struct Workspace {
   float* rowpack;   // [B][nRB][12][32] float4 : per-thread 16 rows as x[16], y[16], z[16], lane-coalesced
   float4* colpack;  // [B][Mp] float4          : (-x, -y, -z, 0)
@@ -83,6 +81,7 @@ __global__ void __launch_bounds__(256) chamfer_prep_kernel(
     float4* __restrict__ zero_gy) {
   const long long nrow = (long long)g.B * g.Npad;
   const long long ncol = (long long)g.B * g.Mp;
+  pdl_wait();
   if (zero_loss && blockIdx.x == 0 && threadIdx.x == 0) *zero_loss = 0.f;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nrow + ncol;
        t += (long long)gridDim.x * blockDim.x) {
@@ -163,6 +162,7 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
   float* cball = reinterpret_cast<float*>(smem_raw + (size_t)(kChunk + 4) * sizeof(float4));  // [warps][2][32][36]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();
   long long tr0 = 0, tr1 = 0;
   if (a.trace) tr0 = clock64();
   if (a.stagger_ns > 0 && blockIdx.x >= 148) __nanosleep(a.stagger_ns);
@@ -313,56 +313,6 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
 // ---------------------------------------------------------------------------------------------------------------
 // 3. finalize: coarse winner -> exact (distance, first index); optionally fused loss_on_cd value + gradients
 // ---------------------------------------------------------------------------------------------------------------
-// Sum (vx,vy,vz) over the lanes that share a key; the result is valid on the lowest lane of each peer group.
-__device__ __forceinline__ void reduce_peers(unsigned peers, float& vx, float& vy, float& vz) {
-  const unsigned lane = lane_id();
-  unsigned rel = __popc(peers & ((1u << lane) - 1u));
-  unsigned higher = peers & ~((2u << lane) - 1u);
-  while (__any_sync(0xffffffffu, higher != 0)) {
-    const int next = __ffs(higher);
-    const int src = next ? next - 1 : (int)lane;
-    const float tx = __shfl_sync(0xffffffffu, vx, src);
-    const float ty = __shfl_sync(0xffffffffu, vy, src);
-    const float tz = __shfl_sync(0xffffffffu, vz, src);
-    if (next) { vx += tx; vy += ty; vz += tz; }
-    const unsigned done = __ballot_sync(0xffffffffu, rel & 1u);
-    higher &= ~done;
-    rel >>= 1;
-  }
-}
-
-// Warp-aggregated scatter: lanes with equal `key` (>= 0) are summed and the group's lowest lane issues one atomic
-// per coordinate.  Every lane of the warp must call this; lanes with live == false contribute nothing.
-__device__ __forceinline__ void scatter_add3(float* dst, long long key, bool live, float vx, float vy, float vz) {
-  if (!live) key = -1 - (long long)lane_id();
-  const unsigned peers = __match_any_sync(0xffffffffu, key);
-  if (__any_sync(0xffffffffu, peers != (1u << lane_id()))) reduce_peers(peers, vx, vy, vz);
-  if (live && (unsigned)(__ffs(peers) - 1) == lane_id()) {
-    atomicAdd(dst + 0, vx); atomicAdd(dst + 1, vy); atomicAdd(dst + 2, vz);
-  }
-}
-
-// Warp-aggregated scatter into a float4-strided buffer: one 16-byte vector atomic (RED.128) per distinct target.
-__device__ __forceinline__ void scatter_add4(float4* dst, long long key, bool live, float vx, float vy, float vz) {
-  if (!live) key = -1 - (long long)lane_id();
-  const unsigned peers = __match_any_sync(0xffffffffu, key);
-  if (__any_sync(0xffffffffu, peers != (1u << lane_id()))) reduce_peers(peers, vx, vy, vz);
-  if (live && (unsigned)(__ffs(peers) - 1) == lane_id()) atomicAdd(dst, make_float4(vx, vy, vz, 0.f));
-}
-
-struct FinalizeArgs {
-  float* dist1; float* dist2; int* idx1; int* idx2;   // any may be null
-  float* loss;       // null, or [1] accumulator (zeroed by prep): += coef_loss * (sum dist1 + sum dist2)
-  // Fused gradient of coef_loss * (sum dist1 + sum dist2), split so that only the scattered half needs atomics:
-  //   d/dx[b,i] = own_x[b,i] + scat_x[b,i].xyz      own_*: plain stores, one writer per point
-  //   d/dy[b,j] = own_y[b,j] + scat_y[b,j].xyz      scat_*: float4-strided, zeroed by prep, vector atomics
-  float* own_x; float* own_y;      // null or [B,N,3] / [B,M,3]
-  float4* scat_x; float4* scat_y;  // null or [B,N] / [B,M]
-  float coef_loss;   // 0.5 / B for loss_on_cd
-};
-
-constexpr int kFinWarps = 8;
-
 // One warp per block of 32 items.  Row item: the 32 columns of the winning tile are evaluated by the 32 lanes
 // (one coalesced 1 KB read); the winning VALUE is already known from the key, so a ballot on equality gives the
 // first minimum.  Column item: the 16 rows of the winning row group are evaluated by a half warp.
@@ -379,6 +329,8 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
   const float coef_grad = 2.f * f.coef_loss;
   float myd = 0.f;
   bool valid = false;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (wi < row_warps) {
     const long long t = wi * 32 + lane;
@@ -622,16 +574,36 @@ static int choose_splits(const Geometry& g, const DeviceCaps& caps) {
   return best;
 }
 
-static int grid_for(long long n, int block) {
-  long long g = (n + block - 1) / block;
-  if (g < 1) g = 1;
-  if (g > 0x7fffffffLL) g = 0x7fffffffLL;
-  return (int)g;
-}
-
 }  // namespace rma
 
 using namespace rma;
+
+// Filter + exact-resolve path (chamfer_filter.cu).
+namespace rma {
+bool f_sizes_ok(int B, int N, int M);
+size_t f_record_bytes(int B, int N, int M);
+size_t f_workspace_bytes(int B, int N, int M);
+int f_launch_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc, const float* y, int64_t ysb, int64_t ysn,
+                  int64_t ysc, int B, int N, int M, void* workspace, size_t workspace_bytes, float* zero_loss,
+                  float4* zero_gx, float4* zero_gy, void* stream_);
+int f_search_config(int B, int N, int M, int* ctas, int* threads, int* splits, int* ctas_per_sm);
+int f_launch_search(int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream_);
+void f_set_force_unit_run(int u);
+int f_launch_resolve(int B, int N, int M, const FinalizeArgs& f, void* workspace, size_t workspace_bytes,
+                     void* stream_);
+int f_read_stats(void* workspace, int B, int N, int M, unsigned* out4, void* stream_);
+}  // namespace rma
+
+// Which search runs: the filter path whenever its records (B*N*M/16 + B*N*M/43 bytes) stay below the cap, else the
+// exact path (huge single pairs).  Both return identical results.
+static int g_force_path = 0;                                  // experiment hook: 0 auto, 1 exact, 2 filter
+static size_t g_filter_record_cap = (size_t)1 << 30;          // 1 GiB
+
+static bool use_filter(int B, int N, int M) {
+  if (g_force_path == 1 || !f_sizes_ok(B, N, M)) return false;
+  if (g_force_path == 2) return true;
+  return f_record_bytes(B, N, M) <= g_filter_record_cap;
+}
 
 extern "C" {
 
@@ -668,7 +640,9 @@ static bool sizes_ok(int B, int N, int M) {
 size_t rma_chamfer_workspace_bytes(int B, int N, int M) {
   if (!sizes_ok(B, N, M)) return 0;
   const Geometry g = make_geometry(B, N, M);
-  return carve(g, nullptr).bytes;
+  size_t bytes = carve(g, nullptr).bytes;
+  if (use_filter(B, N, M)) { const size_t fb = f_workspace_bytes(B, N, M); if (fb > bytes) bytes = fb; }
+  return bytes;
 }
 
 static long long* g_trace = nullptr;   // experiment hooks, see rma_exp_set_search_debug
@@ -689,12 +663,15 @@ static int launch_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
                        const float* y, int64_t ysb, int64_t ysn, int64_t ysc, int B, int N, int M,
                        void* workspace, size_t workspace_bytes, float* zero_loss, float4* zero_gx, float4* zero_gy,
                        void* stream_) {
+  if (x && y && sizes_ok(B, N, M) && use_filter(B, N, M))
+    return f_launch_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, workspace, workspace_bytes, zero_loss,
+                         zero_gx, zero_gy, stream_);
   Geometry g; Workspace w;
   if (int e = forward_setup(x, y, B, N, M, workspace, workspace_bytes, &g, &w)) return e;
   const long long slots = (long long)B * (g.Npad + g.Mp);
-  chamfer_prep_kernel<<<grid_for(slots, 256), 256, 0, (cudaStream_t)stream_>>>(
-      x, xsb, xsn, xsc, y, ysb, ysn, ysc, g, w, zero_loss, zero_gx, zero_gy);
-  RMA_LAUNCH_CHECK();
+  RMA_CUDA_TRY(launch_pdl(chamfer_prep_kernel, (unsigned)grid_for(slots, 256), 256u, 0, (cudaStream_t)stream_,
+                          x, (long long)xsb, (long long)xsn, (long long)xsc, y, (long long)ysb, (long long)ysn,
+                          (long long)ysc, g, w, zero_loss, zero_gx, zero_gy));
   return RMA_OK;
 }
 
@@ -706,6 +683,8 @@ int rma_chamfer_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
 }
 
 int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (sizes_ok(B, N, M) && use_filter(B, N, M))
+    return f_launch_search(B, N, M, workspace, workspace_bytes, stream_);
   Geometry g; Workspace w;
   if (int e = forward_setup((const float*)workspace, (const float*)workspace, B, N, M, workspace, workspace_bytes,
                             &g, &w)) return e;
@@ -722,8 +701,8 @@ int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_by
   a.stagger_ns = g_stagger_ns;
   const long long ctas = (long long)B * g.nRBC * a.S;
   if (ctas > 0x7fffffffLL) return RMA_E_BADARG;
-  chamfer_search_kernel<<<(int)ctas, kSearchThreads, kSearchSmem, (cudaStream_t)stream_>>>(a);
-  RMA_LAUNCH_CHECK();
+  RMA_CUDA_TRY(launch_pdl(chamfer_search_kernel, (unsigned)ctas, (unsigned)kSearchThreads, kSearchSmem,
+                          (cudaStream_t)stream_, a));
   return RMA_OK;
 }
 
@@ -731,18 +710,35 @@ int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_by
 int rma_exp_set_search_debug(long long* trace, int force_splits, int stagger_ns) {
   g_trace = trace;
   g_force_splits = force_splits;
+  f_set_force_unit_run(force_splits);   // filter path: tiles per CTA
   g_stagger_ns = stagger_ns;
   return RMA_OK;
 }
 
+// 0 = auto, 1 = exact search, 2 = filter + resolve; record_cap_bytes > 0 changes the automatic switch-over.
+int rma_exp_set_chamfer_path(int path, long long record_cap_bytes) {
+  g_force_path = path;
+  if (record_cap_bytes > 0) g_filter_record_cap = (size_t)record_cap_bytes;
+  return RMA_OK;
+}
+// 1 if (B,N,M) runs the filter path.  stats4_host (optional, filter path only): extra row candidates, extra column
+// candidates, row-block rescans of the last resolve on this workspace (synchronises the stream).
+int rma_exp_chamfer_path_info(int B, int N, int M, void* workspace, unsigned* stats4_host, void* stream_) {
+  if (!sizes_ok(B, N, M)) return RMA_E_BADARG;
+  const int filt = use_filter(B, N, M) ? 1 : 0;
+  if (filt && workspace && stats4_host) { if (int e = f_read_stats(workspace, B, N, M, stats4_host, stream_)) return e; }
+  return filt;
+}
+
 static int launch_finalize(int B, int N, int M, const FinalizeArgs& f, void* workspace, size_t workspace_bytes,
                            void* stream_) {
+  if (sizes_ok(B, N, M) && use_filter(B, N, M)) return f_launch_resolve(B, N, M, f, workspace, workspace_bytes, stream_);
   Geometry g; Workspace w;
   if (int e = forward_setup((const float*)workspace, (const float*)workspace, B, N, M, workspace, workspace_bytes,
                             &g, &w)) return e;
   const long long warps = ((long long)B * N + 31) / 32 + ((long long)B * M + 31) / 32;
-  chamfer_finalize_kernel<<<grid_for(warps, kFinWarps), kFinWarps * 32, 0, (cudaStream_t)stream_>>>(g, w, f);
-  RMA_LAUNCH_CHECK();
+  RMA_CUDA_TRY(launch_pdl(chamfer_finalize_kernel, (unsigned)grid_for(warps, kFinWarps), (unsigned)(kFinWarps * 32), 0,
+                          (cudaStream_t)stream_, g, w, f));
   return RMA_OK;
 }
 
@@ -755,6 +751,7 @@ int rma_chamfer_finalize(int B, int N, int M, float* dist1, float* dist2, int32_
 
 int rma_chamfer_search_config(int B, int N, int M, int* ctas, int* threads, int* splits, int* ctas_per_sm) {
   if (!sizes_ok(B, N, M)) return RMA_E_BADARG;
+  if (use_filter(B, N, M)) return f_search_config(B, N, M, ctas, threads, splits, ctas_per_sm);
   const Geometry g = make_geometry(B, N, M);
   DeviceCaps caps;
   if (int e = get_caps(&caps)) return e;
@@ -802,6 +799,7 @@ __global__ void __launch_bounds__(256) cd_backward_kernel(const float* __restric
                                                           const float4* __restrict__ scat_y, long long ny,
                                                           const float* __restrict__ scalar,
                                                           float* __restrict__ out_x, float* __restrict__ out_y) {
+  pdl_wait();
   const float sc = *scalar;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nx + ny;
        t += (long long)gridDim.x * blockDim.x) {
@@ -823,10 +821,9 @@ int rma_chamfer_cd_backward(const float* own_x, const float* scat_x, int64_t nx,
   if (nx + ny == 0) return RMA_OK;
   long long grid = (nx + ny + 255) / 256;
   if (grid > 148LL * 16) grid = 148LL * 16;
-  cd_backward_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream_>>>(own_x, (const float4*)scat_x, nx, own_y,
-                                                                   (const float4*)scat_y, ny, scalar_dev, out_x,
-                                                                   out_y);
-  RMA_LAUNCH_CHECK();
+  RMA_CUDA_TRY(launch_pdl(cd_backward_kernel, (unsigned)grid, 256u, 0, (cudaStream_t)stream_, own_x,
+                          (const float4*)scat_x, (long long)nx, own_y, (const float4*)scat_y, (long long)ny, scalar_dev,
+                          out_x, out_y));
   return RMA_OK;
 }
 

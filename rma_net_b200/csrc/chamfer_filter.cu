@@ -1,0 +1,824 @@
+// Chamfer nearest-neighbour search, "filter + exact resolve" path (B200, sm_100a).  Same results as the exact path in
+// chamfer.cu (fp32 difference-form distances, first-index ties = torch.min semantics of model/loss.py:68-69), at
+// 6 instead of 8 issue cycles per point pair.  DESIGN.md §4.
+//
+//   search   every pair is evaluated ONCE in the EXPANDED form the reference itself uses (loss.py:54-57):
+//              f_ij = |y_j|^2 - 2 x_i.y_j   (3 FFMA, chain seeded with |y_j|^2)         -> row direction  min_j f_ij
+//              g_ij = f_ij + |x_i|^2        (1 FADD)                                    -> column direction min_i g_ij
+//            The expanded form cancels, so f/g are only a FILTER.  Per row the minimum of f over every 64-column tile
+//            is written to a record; per column and 512-row block the three smallest 16-row-group minima are written
+//            (group id packed into the 5 low mantissa bits).  No atomics, no index bookkeeping in the inner loop.
+//   resolve  per row: every tile whose filter minimum lies within a rigorous rounding-error guard G of the smallest
+//            one is a candidate; its 64 columns are re-evaluated in the exact difference form and the (distance,
+//            index)-lexicographic minimum is kept.  Same per column with 16-row groups.  The candidate set provably
+//            contains every exact minimiser (guard derivation below), so the result is the exact path's bit for bit.
+//
+// Guard.  eps = 2^-24, a = |x_i|, b = |y_j|, D = |x_i - y_j|^2, all on the fp32 inputs.
+//   w_j = fl(|y_j|^2), u_i = fl(|x_i|^2): three roundings each, relative error <= 3.01 eps.
+//   f   = fma(x0,q0, fma(x1,q1, fma(x2,q2, w))), q = -2y exact: every partial sum is bounded by b^2 + 2ab, so
+//         |f - (|y|^2 - 2x.y)| <= 3.01 eps b^2 + 3 eps (b^2 + 2ab) <= 6.1 eps (b^2 + ab) =: e(a,b).
+//   g   = fl(f + u): |g - D| <= e(a,b) + 3.01 eps a^2 + 1.01 eps D, and the 5 packed bits cost 2^-18 |g| more.
+//   The exact path returns d = fl-difference-form with |d - D| <= 5.01 eps D.  If jf minimises f and j* minimises d,
+//   then D_j* <= D_jf (1 + 10.1 eps), hence f_j* <= f_jf + 2 e(a, beta) + 10.1 eps D_jf with beta >= b_jf, b_j*;
+//   beta = a + sqrt(1.0001 D_jf) by the triangle inequality, and D_jf <= 1.001 (f_jf + u_i)^+ + 1e-5 u_i.
+//   guard_row / guard_col below evaluate these bounds with >= 1% slack plus an absolute 1e-30 for underflow.
+#include "chamfer_common.cuh"
+#include "../../include/rma_b200.h"
+
+namespace rma {
+
+constexpr int kFRowsPerThread = 16;
+constexpr int kFRowsPerWarp = 32 * kFRowsPerThread;     // 512: one row block
+constexpr int kFWarps = 4;
+constexpr int kFThreads = 32 * kFWarps;
+constexpr int kFRowsPerCta = kFRowsPerWarp * kFWarps;   // 2048
+constexpr int kFColTile = 32;                           // columns per column-direction tile (= lanes)
+constexpr int kFRowTile = 64;                           // columns per row-direction record
+#ifndef RMA_F_CHUNK
+#define RMA_F_CHUNK 1024
+#endif
+#ifndef RMA_F_MINCTAS
+#define RMA_F_MINCTAS 2
+#endif
+constexpr int kFChunk = RMA_F_CHUNK;                     // columns staged in shared memory at a time
+constexpr int kFCbStride = 36;
+constexpr float kFBig = 1e30f;                          // |x|^2 of padded rows / |y|^2 of padded columns
+constexpr float kEps = 5.9604644775390625e-8f;          // 2^-24
+
+struct FGeometry {
+  int B, N, M;
+  int nRB;    // 512-row blocks per batch element
+  int Npad;   // nRB * 512
+  int nRBC;   // CTA row blocks (2048 rows) per batch element
+  int nT;     // 64-column tiles per batch element
+  int Mp;     // nT * 64
+  int U;      // work units (CTA row block x 64-column tile) per search CTA
+  int Smax;   // max segments (CTAs) that share one CTA row block
+  long long units() const { return (long long)B * nRBC * nT; }
+};
+
+// Work decomposition of the search: the B*nRBC*nT units are dealt out in contiguous runs of U to the CTAs, so every
+// CTA has the same amount of work (+-1 unit) whatever B, N, M are; a run may cross into the next row block / batch
+// element, in which case the CTA reloads its rows ("segment").  U is chosen for a whole number of balanced waves.
+static int f_choose_unit_run(long long units, int nT, int slots) {
+  // cost of w waves ~ w * (U * 64 columns + fixed per-CTA overhead of ~40 column-times), U = ceil(units/(slots*w))
+  double best_cost = 1e300;
+  int best = 1;
+  for (int w = 1; w <= 64; ++w) {
+    long long U = (units + (long long)slots * w - 1) / ((long long)slots * w);
+    if (U < 1) U = 1;
+    const double cost = (double)w * ((double)U * kFRowTile + 40.0);
+    if (cost < best_cost * 0.995) { best_cost = cost; best = (int)(U > 0x3fffffff ? 0x3fffffff : U); }
+    if (U <= 2) break;
+  }
+  (void)nT;
+  return best;
+}
+
+static FGeometry f_make_geometry(int B, int N, int M, int slots, int force_run) {
+  FGeometry g;
+  g.B = B; g.N = N; g.M = M;
+  g.nRB = (N + kFRowsPerWarp - 1) / kFRowsPerWarp;
+  g.Npad = g.nRB * kFRowsPerWarp;
+  g.nRBC = (g.nRB + kFWarps - 1) / kFWarps;
+  g.nT = (M + kFRowTile - 1) / kFRowTile;
+  g.Mp = g.nT * kFRowTile;
+  g.U = force_run > 0 ? force_run : f_choose_unit_run(g.units(), g.nT, slots);
+  g.Smax = (g.nT + g.U - 1) / g.U + 1;
+  return g;
+}
+
+struct FWorkspace {
+  float4* rowpack;   // [B][Npad]               (x, y, z, |x|^2); padded rows (0,0,0,1e30)           (resolve)
+  float4* rowsoa;    // [B][nRB][16][32]        per search thread its 16 rows as x[16], y[16], z[16], u[16],
+                     //                         lane-coalesced: 16 LDG.128 whose halves are the packed row pairs
+  float4* colpack;   // [B][Mp]                 (-2x, -2y, -2z, |y|^2); padded columns (0,0,0,1e30)
+  float* rowrec;     // [B][nT][Npad]           min over the tile's 64 columns of f (read only when a guard fails)
+  float* rowtop;     // [B*nRBC][Smax][3][2048] per segment: smallest tile minimum, its tile, second smallest
+  float* colrec;     // [B][nRB][3][Mp]         three smallest packed group minima of g over the row block
+  unsigned* stats;   // [4] rows on the slow path, columns on the slow path, row-block rescans, unused
+  size_t bytes;
+};
+
+static FWorkspace f_carve(const FGeometry& g, void* base) {
+  FWorkspace w;
+  char* p = (char*)base;
+  size_t off = 0;
+  w.rowpack = (float4*)(p + off); off += align256((size_t)g.B * g.Npad * sizeof(float4));
+  w.rowsoa = (float4*)(p + off);  off += align256((size_t)g.B * g.Npad * sizeof(float4));
+  w.colpack = (float4*)(p + off); off += align256((size_t)g.B * g.Mp * sizeof(float4));
+  w.rowrec = (float*)(p + off);   off += align256((size_t)g.B * g.nT * g.Npad * sizeof(float));
+  w.rowtop = (float*)(p + off);   off += align256((size_t)g.B * g.nRBC * g.Smax * 3 * kFRowsPerCta * sizeof(float));
+  w.colrec = (float*)(p + off);   off += align256((size_t)g.B * g.nRB * 3 * g.Mp * sizeof(float));
+  w.stats = (unsigned*)(p + off); off += 256;
+  w.bytes = off;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prep
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float norm2_rn(float x, float y, float z) {
+  return __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+}
+
+__global__ void __launch_bounds__(256) chamfer_fprep_kernel(
+    const float* __restrict__ x, long long xsb, long long xsn, long long xsc,
+    const float* __restrict__ y, long long ysb, long long ysn, long long ysc,
+    FGeometry g, FWorkspace w, float* __restrict__ zero_loss, float4* __restrict__ zero_gx,
+    float4* __restrict__ zero_gy) {
+  const long long nrow = (long long)g.B * g.Npad;
+  const long long ncol = (long long)g.B * g.Mp;
+  pdl_wait();
+  if (blockIdx.x == 0 && threadIdx.x < 4) w.stats[threadIdx.x] = 0u;
+  if (zero_loss && blockIdx.x == 0 && threadIdx.x == 0) *zero_loss = 0.f;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nrow + ncol;
+       t += (long long)gridDim.x * blockDim.x) {
+    if (t < nrow) {
+      const int b = (int)(t / g.Npad), i = (int)(t % g.Npad);
+      float4 v = make_float4(0.f, 0.f, 0.f, kFBig);
+      if (i < g.N) {
+        const float* s = x + b * xsb + i * xsn;
+        v.x = s[0]; v.y = s[xsc]; v.z = s[2 * xsc];
+        v.w = norm2_rn(v.x, v.y, v.z);
+        if (zero_gx) zero_gx[(long long)b * g.N + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      w.rowpack[t] = v;
+      const int rb = i / kFRowsPerWarp, ln = (i % kFRowsPerWarp) / kFRowsPerThread, r = i % kFRowsPerThread;
+      float* soa = reinterpret_cast<float*>(w.rowsoa + ((size_t)(b * g.nRB + rb) * 16) * 32 + ln);
+      // float4 slot c*4 + r/4 (c = x,y,z,u), element r%4; slots are 32 float4 apart
+      soa[(size_t)(r >> 2) * 128 + (r & 3)] = v.x;
+      soa[(size_t)(4 + (r >> 2)) * 128 + (r & 3)] = v.y;
+      soa[(size_t)(8 + (r >> 2)) * 128 + (r & 3)] = v.z;
+      soa[(size_t)(12 + (r >> 2)) * 128 + (r & 3)] = v.w;
+    } else {
+      const long long u = t - nrow;
+      const int b = (int)(u / g.Mp), j = (int)(u % g.Mp);
+      float4 v = make_float4(0.f, 0.f, 0.f, kFBig);
+      if (j < g.M) {
+        const float* s = y + b * ysb + j * ysn;
+        const float px = s[0], py = s[ysc], pz = s[2 * ysc];
+        v = make_float4(-2.f * px, -2.f * py, -2.f * pz, norm2_rn(px, py, pz));
+        if (zero_gy) zero_gy[(long long)b * g.M + j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      w.colpack[u] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------------------------------------------
+// One column against the thread's 16 rows (8 packed row pairs): 3 FFMA2 + 1 FADD2 per row pair
+// (FFMA2 R, Rx.F32x2, Rq.F32, Rw.F32: the column operands are broadcast scalars, one LDS.128 per column).
+// f[r] receives the row-direction value; the return value is the minimum over the 16 rows of g = f + |x|^2.
+__device__ __forceinline__ float fcolumn_step(const u64 (&px)[8], const u64 (&py)[8], const u64 (&pz)[8],
+                                              const u64 (&pu)[8], const float4 q, float (&f)[16]) {
+  const u64 c0 = pack2(q.x, q.x), c1 = pack2(q.y, q.y), c2 = pack2(q.z, q.z), cw = pack2(q.w, q.w);
+  float gg[16];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    u64 acc = fma2(pz[k], c2, cw);
+    acc = fma2(py[k], c1, acc);
+    acc = fma2(px[k], c0, acc);
+    unpack2(acc, f[2 * k], f[2 * k + 1]);
+#ifdef RMA_F_ABL_NOADD
+    gg[2 * k] = f[2 * k]; gg[2 * k + 1] = f[2 * k + 1];
+#else
+    unpack2(add2(acc, pu[k]), gg[2 * k], gg[2 * k + 1]);
+#endif
+  }
+#ifdef RMA_F_ABL_NOCOLMIN
+  return gg[0] + gg[5] + gg[10] + gg[15];
+#endif
+  const float t0 = min3(gg[0], gg[1], gg[2]);
+  const float t1 = min3(gg[3], gg[4], gg[5]);
+  const float t2 = min3(gg[6], gg[7], gg[8]);
+  const float t3 = min3(gg[9], gg[10], gg[11]);
+  const float t4 = min3(gg[12], gg[13], gg[14]);
+  const float u0 = min3(t0, t1, gg[15]);
+  const float u1 = min3(t2, t3, t4);
+  return fminf(u0, u1);
+}
+
+#ifdef RMA_F_ABL_NOROWMIN
+#define ROWMIN(t, a, b) ((r == 0) ? min3(t, a, b) : __uint_as_float(__float_as_uint(t) ^ __float_as_uint(a) ^ __float_as_uint(b)))
+#else
+#define ROWMIN(t, a, b) min3(t, a, b)
+#endif
+
+// Insert v into the ascending triple (p1 <= p2 <= p3): 5 FMNMX, no predicates.
+__device__ __forceinline__ void top3_insert(float& p1, float& p2, float& p3, float v) {
+  p3 = fminf(p3, fmaxf(p2, v));
+  p2 = fminf(p2, fmaxf(p1, v));
+  p1 = fminf(p1, v);
+}
+
+constexpr size_t kFSearchSmemBase =
+    (size_t)(kFChunk + 4) * sizeof(float4) + (size_t)kFWarps * 2 * kFColTile * kFCbStride * sizeof(float);
+constexpr size_t kFSearchSmem = kFSearchSmemBase + (size_t)3 * 4 * kFThreads * sizeof(float4);
+
+struct FSearchArgs {
+  const float4* rowsoa;
+  const float4* colpack;
+  float* rowrec;
+  float* rowtop;
+  float* colrec;
+  int N, M, nRB, Npad, nRBC, nT, Mp, U, Smax;
+  long long units;
+};
+
+__global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kernel(FSearchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* scol = reinterpret_cast<float4*>(smem_raw);                                          // [kFChunk + 4]
+  float* cball = reinterpret_cast<float*>(smem_raw + (size_t)(kFChunk + 4) * sizeof(float4));   // [warps][2][32][36]
+  // per-row running (smallest tile minimum, its tile, second smallest): touched once per 64-column tile, so it lives
+  // in shared memory ([plane][q][thread] float4, conflict-free) instead of 48 registers
+  float4* stop = reinterpret_cast<float4*>(smem_raw + kFSearchSmemBase) + threadIdx.x;            // [3][4][kFThreads]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* cb = cball + warp * (2 * kFColTile * kFCbStride);
+  const float inf = __int_as_float(0x7f800000);
+  const unsigned lane_tag = (unsigned)lane;
+
+  long long unit = (long long)blockIdx.x * a.U;
+  const long long unit_end = min(unit + a.U, a.units);
+  pdl_wait();
+
+  while (unit < unit_end) {
+    // ---- one segment: a run of `ntile` 64-column tiles of one CTA row block ----
+    const int brb = (int)(unit / a.nT);
+    const int tile0 = (int)(unit - (long long)brb * a.nT);
+    const int ntile = (int)min((long long)(a.nT - tile0), unit_end - unit);
+    unit += ntile;
+    const int b = brb / a.nRBC, rbc = brb - b * a.nRBC;
+    const int rb = rbc * kFWarps + warp;
+    const bool has_rows = rb < a.nRB;   // warp-uniform
+    const int seg = blockIdx.x - (int)(((long long)brb * a.nT) / a.U);   // which of the row block's segments
+    const int c0 = tile0 * kFRowTile;
+    const int ncols = ntile * kFRowTile;
+
+    u64 px[8], py[8], pz[8], pu[8];
+    if (has_rows) {
+      const float4* rp = a.rowsoa + ((size_t)(b * a.nRB + rb) * 16) * 32 + lane;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 vx = rp[q * 32], vy = rp[(4 + q) * 32], vz = rp[(8 + q) * 32], vu = rp[(12 + q) * 32];
+        px[2 * q] = pack2(vx.x, vx.y); px[2 * q + 1] = pack2(vx.z, vx.w);
+        py[2 * q] = pack2(vy.x, vy.y); py[2 * q + 1] = pack2(vy.z, vy.w);
+        pz[2 * q] = pack2(vz.x, vz.y); pz[2 * q + 1] = pack2(vz.z, vz.w);
+        pu[2 * q] = pack2(vu.x, vu.y); pu[2 * q + 1] = pack2(vu.z, vu.w);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      stop[q * kFThreads] = make_float4(inf, inf, inf, inf);
+      stop[(4 + q) * kFThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
+      stop[(8 + q) * kFThreads] = make_float4(inf, inf, inf, inf);
+    }
+
+    const float4* cp = a.colpack + ((size_t)b * a.Mp + c0);
+    float* rrec = a.rowrec + ((size_t)b * a.nT + tile0) * a.Npad + (size_t)rb * kFRowsPerWarp + lane * kFRowsPerThread;
+    float* crec = a.colrec + ((size_t)(b * a.nRB + rb) * 3) * a.Mp + c0 + lane;
+
+    // Column direction, software-pipelined: while tile t is computed, lane l folds column l of tile t-1 (32 per-lane
+    // packed partial minima in the other half of the double buffer) into its running top-3, four values per body.
+    int pend_col = -1;   // column offset (relative to c0) of the tile whose reduce is pending; warp-uniform
+    int parity = 0;
+
+    for (int cs = 0; cs < ncols; cs += kFChunk) {
+      const int nc = min(kFChunk, ncols - cs);
+      __syncthreads();   // previous chunk / segment fully consumed
+      for (int idx = tid; idx < nc; idx += kFThreads) scol[idx] = cp[(size_t)cs + idx];
+      __syncthreads();
+      if (!has_rows) continue;
+
+#pragma unroll 1
+      for (int t0 = 0; t0 < nc; t0 += kFRowTile) {
+        float tm[kFRowsPerThread];
+#pragma unroll
+        for (int r = 0; r < kFRowsPerThread; ++r) tm[r] = inf;
+
+#pragma unroll 1
+        for (int h = 0; h < kFRowTile; h += kFColTile) {
+          const float4* sp = scol + t0 + h;
+          float* cbw = cb + parity * (kFColTile * kFCbStride) + lane;
+          const float4* cbr = reinterpret_cast<const float4*>(cb + (parity ^ 1) * (kFColTile * kFCbStride) +
+                                                              lane * kFCbStride);
+          float p1 = inf, p2 = inf, p3 = inf;
+
+          // Four columns against the 16 rows, plus four pending values of the previous tile's column reduce.
+          auto body = [&](const float4& q0, const float4& q1, const float4& q2, const float4& q3, int jj) {
+            const float4 pv = cbr[jj >> 2];          // 4 packed partial minima of the pending tile
+            {
+              float fA[16], fB[16];
+              const float cmA = fcolumn_step(px, py, pz, pu, q0, fA);
+              const float cmB = fcolumn_step(px, py, pz, pu, q1, fB);
+#pragma unroll
+              for (int r = 0; r < kFRowsPerThread; ++r) tm[r] = min3(tm[r], fA[r], fB[r]);
+              cbw[jj * kFCbStride] = __uint_as_float((__float_as_uint(cmA) & ~31u) | lane_tag);
+              cbw[(jj + 1) * kFCbStride] = __uint_as_float((__float_as_uint(cmB) & ~31u) | lane_tag);
+            }
+            {
+              float fA[16], fB[16];
+              const float cmA = fcolumn_step(px, py, pz, pu, q2, fA);
+              const float cmB = fcolumn_step(px, py, pz, pu, q3, fB);
+#pragma unroll
+              for (int r = 0; r < kFRowsPerThread; ++r) tm[r] = min3(tm[r], fA[r], fB[r]);
+              cbw[(jj + 2) * kFCbStride] = __uint_as_float((__float_as_uint(cmA) & ~31u) | lane_tag);
+              cbw[(jj + 3) * kFCbStride] = __uint_as_float((__float_as_uint(cmB) & ~31u) | lane_tag);
+            }
+            top3_insert(p1, p2, p3, pv.x);
+            top3_insert(p1, p2, p3, pv.y);
+            top3_insert(p1, p2, p3, pv.z);
+            top3_insert(p1, p2, p3, pv.w);
+          };
+
+          // Operands are prefetched one body ahead into the OTHER register set (ping-pong, unrolled by two) so that no
+          // register copies are needed: a MOV/IMAD.MOV here queues behind the saturated FMA pipe and stalls the warp.
+          // The last prefetch of a chunk reads the 4-column pad behind the staged data and is never used.
+          float4 a0 = sp[0], a1 = sp[1], a2 = sp[2], a3 = sp[3];
+#pragma unroll 1
+          for (int jj = 0; jj < kFColTile; jj += 8) {
+            const float4 b0 = sp[jj + 4], b1 = sp[jj + 5], b2 = sp[jj + 6], b3 = sp[jj + 7];
+            body(a0, a1, a2, a3, jj);
+            a0 = sp[jj + 8]; a1 = sp[jj + 9]; a2 = sp[jj + 10]; a3 = sp[jj + 11];
+            body(b0, b1, b2, b3, jj + 4);
+          }
+
+          if (pend_col >= 0) {
+            float* o = crec + pend_col;
+            o[0] = p1; o[a.Mp] = p2; o[2 * (size_t)a.Mp] = p3;
+          }
+          pend_col = cs + t0 + h;
+          parity ^= 1;
+          __syncwarp();   // this tile's partial minima visible to all lanes; previous buffer free for reuse
+        }
+
+        // Row direction: the tile's 16 filter minima go to the record (64 contiguous bytes per thread) and into the
+        // running (smallest, its tile, second smallest) of the segment.
+        const int tile = tile0 + (cs + t0) / kFRowTile;
+        float4* o = reinterpret_cast<float4*>(rrec + (size_t)((cs + t0) / kFRowTile) * a.Npad);
+        o[0] = make_float4(tm[0], tm[1], tm[2], tm[3]);
+        o[1] = make_float4(tm[4], tm[5], tm[6], tm[7]);
+        o[2] = make_float4(tm[8], tm[9], tm[10], tm[11]);
+        o[3] = make_float4(tm[12], tm[13], tm[14], tm[15]);
+        const float tilef = __int_as_float(tile);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 m1 = stop[q * kFThreads], t1 = stop[(4 + q) * kFThreads], m2 = stop[(8 + q) * kFThreads];
+          m2.x = fminf(m2.x, fmaxf(m1.x, tm[4 * q]));     t1.x = tm[4 * q] < m1.x ? tilef : t1.x;
+          m2.y = fminf(m2.y, fmaxf(m1.y, tm[4 * q + 1])); t1.y = tm[4 * q + 1] < m1.y ? tilef : t1.y;
+          m2.z = fminf(m2.z, fmaxf(m1.z, tm[4 * q + 2])); t1.z = tm[4 * q + 2] < m1.z ? tilef : t1.z;
+          m2.w = fminf(m2.w, fmaxf(m1.w, tm[4 * q + 3])); t1.w = tm[4 * q + 3] < m1.w ? tilef : t1.w;
+          m1.x = fminf(m1.x, tm[4 * q]); m1.y = fminf(m1.y, tm[4 * q + 1]);
+          m1.z = fminf(m1.z, tm[4 * q + 2]); m1.w = fminf(m1.w, tm[4 * q + 3]);
+          stop[q * kFThreads] = m1; stop[(4 + q) * kFThreads] = t1; stop[(8 + q) * kFThreads] = m2;
+        }
+      }
+    }
+
+    if (has_rows) {
+      if (pend_col >= 0) {   // drain: column reduce of the segment's last tile
+        const float* col = cb + (parity ^ 1) * (kFColTile * kFCbStride) + lane * kFCbStride;
+        float p1 = inf, p2 = inf, p3 = inf;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) top3_insert(p1, p2, p3, col[k]);
+        float* o = crec + pend_col;
+        o[0] = p1; o[a.Mp] = p2; o[2 * (size_t)a.Mp] = p3;
+      }
+      float* top = a.rowtop + ((size_t)(brb * a.Smax + seg) * 3) * kFRowsPerCta + warp * kFRowsPerWarp +
+                   lane * kFRowsPerThread;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        reinterpret_cast<float4*>(top)[q] = stop[q * kFThreads];
+        reinterpret_cast<float4*>(top + kFRowsPerCta)[q] = stop[(4 + q) * kFThreads];          // tile ids (int bits)
+        reinterpret_cast<float4*>(top + 2 * kFRowsPerCta)[q] = stop[(8 + q) * kFThreads];
+      }
+      __syncwarp();   // the next segment reuses the transpose buffers
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// resolve
+// ---------------------------------------------------------------------------------------------------------------
+// Rigorous guards (derivation in the file header).  u = fl(|x_i|^2), mt = smallest filter value f of the row.
+__device__ __forceinline__ float guard_row(float u, float mt) {
+  const float D0 = fmaxf(mt + u, 0.f);
+  const float Dub = 1.001f * D0 + 1e-5f * u;
+  const float a = sqrtf(u) * 1.0001f;
+  const float beta = a + sqrtf(Dub) * 1.0001f;
+  return (12.3f * beta * (beta + a) + 10.3f * Dub) * (kEps * 1.01f) + 1e-30f;
+}
+// wj = fl(|y_j|^2), mt = smallest (packed, truncated) value of g for the column, i.e. an estimate of the distance.
+__device__ __forceinline__ float guard_col(float wj, float mt) {
+  const float D0 = fmaxf(mt, 0.f);
+  const float Dub = 1.001f * D0 + 1e-5f * wj;
+  const float bn = sqrtf(wj) * 1.0001f;
+  const float alpha = bn + sqrtf(Dub) * 1.0001f;
+  return (12.3f * bn * (bn + alpha) + 6.3f * alpha * alpha + 12.5f * Dub) * (kEps * 1.01f) +
+         Dub * 7.8e-6f /* 2^-17 * 1.02 */ + 1e-30f;
+}
+
+// Exact difference-form distance between (x,y,z) and the column stored as q = -2*(yx,yy,yz): x + 0.5 q == x - y
+// exactly, so this reproduces sqdist_neg / the oracle's operation order bit for bit.
+__device__ __forceinline__ float sqdist_q(float x, float y, float z, const float4 q) {
+  const float dx = __fmaf_rn(0.5f, q.x, x), dy = __fmaf_rn(0.5f, q.y, y), dz = __fmaf_rn(0.5f, q.z, z);
+  float d = __fmul_rn(dx, dx);
+  d = __fmaf_rn(dy, dy, d);
+  d = __fmaf_rn(dz, dz, d);
+  return d;
+}
+
+// (distance bits, index) lexicographic minimum over the 8 lanes of an aligned lane group.
+__device__ __forceinline__ void group8_min(unsigned& d, unsigned& idx) {
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const unsigned od = __shfl_xor_sync(0xffffffffu, d, o);
+    const unsigned oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    const bool take = od < d || (od == d && oi < idx);
+    d = take ? od : d;
+    idx = take ? oi : idx;
+  }
+}
+
+__global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGeometry g, FWorkspace w, FinalizeArgs f) {
+  __shared__ double lsum[kFinWarps];
+  const long long nrow = (long long)g.B * g.N, ncol = (long long)g.B * g.M;
+  const long long row_warps = (nrow + 31) / 32;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int grp = lane >> 3, sub = lane & 7;
+  const long long wi = (long long)blockIdx.x * kFinWarps + warp;
+  const float coef_grad = 2.f * f.coef_loss;
+  const unsigned full = 0xffffffffu;
+  const float inf = __int_as_float(0x7f800000);
+  float myd = 0.f;
+  bool valid = false;
+  pdl_wait();
+  pdl_launch_dependents();   // the backward combine may queue behind us (it waits for our completion itself)
+
+  if (wi < row_warps) {
+    // ---------------------------------------------------------------- rows: lane <-> row, candidates = 64-column tiles
+    const long long t = wi * 32 + lane;
+    valid = t < nrow;
+    int b = 0, i = 0;
+    float4 rp = make_float4(0.f, 0.f, 0.f, 0.f);
+    float M1 = inf, M2 = inf;
+    int T1 = 0;
+    if (valid) {
+      b = (int)(t / g.N); i = (int)(t % g.N);
+      rp = w.rowpack[(size_t)b * g.Npad + i];
+      const int rbc = i / kFRowsPerCta, brb = b * g.nRBC + rbc;
+      const int kfirst = (int)(((long long)brb * g.nT) / g.U);
+      const int klast = (int)(((long long)(brb + 1) * g.nT - 1) / g.U);
+      const float* top = w.rowtop + ((size_t)brb * g.Smax * 3) * kFRowsPerCta + (i - rbc * kFRowsPerCta);
+      const int nseg = klast - kfirst + 1;
+      for (int s0 = 0; s0 < nseg; s0 += 4) {      // four segments' records in flight
+        float a1[4], a2[4];
+        int at[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool on = s0 + k < nseg;
+          const float* tp = top + (size_t)(on ? s0 + k : s0) * (3 * kFRowsPerCta);
+          a1[k] = on ? tp[0] : inf;
+          at[k] = __float_as_int(tp[kFRowsPerCta]);
+          a2[k] = on ? tp[2 * kFRowsPerCta] : inf;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          M2 = fminf(fminf(M2, a2[k]), fmaxf(M1, a1[k]));
+          if (a1[k] < M1) { M1 = a1[k]; T1 = at[k]; }
+        }
+      }
+    }
+    const float thr = M1 + guard_row(rp.w, M1);
+    const bool fast = valid && M2 > thr;
+    unsigned best_d = 0xffffffffu, best_j = 0;
+
+    // Fast path (one candidate tile): 8 lanes per row, 8 columns per lane, 4 rows per round.
+#pragma unroll 1
+    for (int round = 0; round < 8; ++round) {
+      const int src = round * 4 + grp;
+      const int sb = __shfl_sync(full, b, src), st = __shfl_sync(full, T1, src);
+      const bool sf = __shfl_sync(full, (int)fast, src) != 0;
+      const float x = __shfl_sync(full, rp.x, src), y = __shfl_sync(full, rp.y, src), z = __shfl_sync(full, rp.z, src);
+      unsigned d = 0xffffffffu, dj = 0xffffffffu;
+      if (sf) {
+        const int j0 = st * kFRowTile + sub;
+        const float4* cq = w.colpack + (size_t)sb * g.Mp + j0;
+        float4 q[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) q[c] = cq[8 * c];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const unsigned dc = j0 + 8 * c < g.M ? __float_as_uint(sqdist_q(x, y, z, q[c])) : 0xffffffffu;
+          if (dc < d) { d = dc; dj = (unsigned)(j0 + 8 * c); }     // ascending columns: strict '<' keeps the first
+        }
+      }
+      group8_min(d, dj);
+      const unsigned rd = __shfl_sync(full, d, (lane & 3) * 8), rj = __shfl_sync(full, dj, (lane & 3) * 8);
+      if ((lane >> 2) == round) { best_d = rd; best_j = rj; }
+    }
+
+    // Slow path (guard failed: several tiles within the rounding error of the smallest): the warp scans the row's tile
+    // records and re-evaluates every candidate tile exactly.
+    unsigned slow = __ballot_sync(full, valid && !fast);
+    if (slow && lane == 0) atomicAdd(w.stats + 0, (unsigned)__popc(slow));
+    while (slow) {
+      const int src = __ffs(slow) - 1; slow &= slow - 1;
+      const int sb = __shfl_sync(full, b, src), si = __shfl_sync(full, i, src);
+      const float sthr = __shfl_sync(full, thr, src);
+      const float x = __shfl_sync(full, rp.x, src), y = __shfl_sync(full, rp.y, src), z = __shfl_sync(full, rp.z, src);
+      const float* rec = w.rowrec + (size_t)sb * g.nT * g.Npad + si;
+      unsigned bd = 0xffffffffu, bj = 0xffffffffu;
+      for (int base = 0; base < g.nT; base += 32) {
+        const int tile = base + lane;
+        unsigned hits = __ballot_sync(full, tile < g.nT && rec[(size_t)tile * g.Npad] <= sthr);
+        while (hits) {
+          const int ht = base + __ffs(hits) - 1; hits &= hits - 1;
+          const int ja = ht * kFRowTile + lane;
+          const float4 qa = w.colpack[(size_t)sb * g.Mp + ja], qb = w.colpack[(size_t)sb * g.Mp + ja + 32];
+          const unsigned d0 = ja < g.M ? __float_as_uint(sqdist_q(x, y, z, qa)) : 0xffffffffu;
+          const unsigned d1 = ja + 32 < g.M ? __float_as_uint(sqdist_q(x, y, z, qb)) : 0xffffffffu;
+          const unsigned dm = min(d0, d1);
+          const unsigned mn = __reduce_min_sync(full, dm);
+          const unsigned jm = __reduce_min_sync(full, dm == mn ? (unsigned)(d0 <= d1 ? ja : ja + 32) : 0xffffffffu);
+          if (mn < bd || (mn == bd && jm < bj)) { bd = mn; bj = jm; }
+        }
+      }
+      if (lane == src) { best_d = bd; best_j = bj; }
+    }
+
+    myd = __uint_as_float(best_d);
+    const int j = (int)best_j;
+    if (valid) {
+      if (f.dist1) f.dist1[t] = myd;
+      if (f.idx1) f.idx1[t] = j;
+    }
+    if (f.own_x || f.scat_y) {
+      float vx = 0.f, vy = 0.f, vz = 0.f;
+      if (valid) {
+        const float4 q = w.colpack[(size_t)b * g.Mp + j];
+        vx = coef_grad * __fmaf_rn(0.5f, q.x, rp.x);
+        vy = coef_grad * __fmaf_rn(0.5f, q.y, rp.y);
+        vz = coef_grad * __fmaf_rn(0.5f, q.z, rp.z);
+        if (f.own_x) { float* o = f.own_x + t * 3; o[0] = vx; o[1] = vy; o[2] = vz; }
+      }
+      if (f.scat_y) scatter_add4(f.scat_y + ((long long)b * g.M + j), (long long)b * g.M + j, valid, -vx, -vy, -vz);
+    }
+  } else {
+    // ------------------------------------------------------------- columns: lane <-> column, candidates = 16-row groups
+    const long long t = (wi - row_warps) * 32 + lane;
+    valid = t < ncol;
+    int b = 0, j = 0;
+    float4 cq = make_float4(0.f, 0.f, 0.f, 0.f);
+    float M1 = inf, M2 = inf;
+    int R1 = 0;
+    if (valid) {
+      b = (int)(t / g.M); j = (int)(t % g.M);
+      cq = w.colpack[(size_t)b * g.Mp + j];
+      const float* rec = w.colrec + (size_t)b * g.nRB * 3 * g.Mp + j;
+      for (int r0 = 0; r0 < g.nRB; r0 += 4) {     // four row blocks' records in flight
+        float a1[4], a2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool on = r0 + k < g.nRB;
+          const float* rp_ = rec + (size_t)(on ? r0 + k : r0) * 3 * g.Mp;
+          a1[k] = on ? rp_[0] : inf;
+          a2[k] = on ? rp_[g.Mp] : inf;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          M2 = fminf(fminf(M2, a2[k]), fmaxf(M1, a1[k]));
+          if (a1[k] < M1) { M1 = a1[k]; R1 = r0 + k; }
+        }
+      }
+    }
+    const float thr = M1 + guard_col(cq.w, M1);
+    const bool fast = valid && M2 > thr;
+    const int G1 = (R1 * 32 + (int)(__float_as_uint(M1) & 31u)) * kFRowsPerThread;   // first row of the candidate group
+    unsigned best_d = 0xffffffffu, best_i = 0;
+
+    // Fast path (one candidate group of 16 rows): 8 lanes per column, 2 rows per lane, 4 columns per round.
+#pragma unroll 2
+    for (int round = 0; round < 8; ++round) {
+      const int src = round * 4 + grp;
+      const int sb = __shfl_sync(full, b, src), sg = __shfl_sync(full, G1, src);
+      const bool sf = __shfl_sync(full, (int)fast, src) != 0;
+      const float4 q = make_float4(__shfl_sync(full, cq.x, src), __shfl_sync(full, cq.y, src),
+                                   __shfl_sync(full, cq.z, src), 0.f);
+      unsigned d = 0xffffffffu, di = 0xffffffffu;
+      if (sf) {
+        const int r0 = sg + sub, r1 = r0 + 8;
+        const float4 pa = w.rowpack[(size_t)sb * g.Npad + r0], pb = w.rowpack[(size_t)sb * g.Npad + r1];
+        const unsigned d0 = r0 < g.N ? __float_as_uint(sqdist_q(pa.x, pa.y, pa.z, q)) : 0xffffffffu;
+        const unsigned d1 = r1 < g.N ? __float_as_uint(sqdist_q(pb.x, pb.y, pb.z, q)) : 0xffffffffu;
+        d = d0; di = (unsigned)r0;
+        if (d1 < d0) { d = d1; di = (unsigned)r1; }
+      }
+      group8_min(d, di);
+      const unsigned rd = __shfl_sync(full, d, (lane & 3) * 8), ri = __shfl_sync(full, di, (lane & 3) * 8);
+      if ((lane >> 2) == round) { best_d = rd; best_i = ri; }
+    }
+
+    // Slow path: every (row block, k) entry within the guard is a candidate group; a third-smallest entry within
+    // the guard means the row block may hold more than the recorded three, so all of its 512 rows are re-evaluated.
+    unsigned slow = __ballot_sync(full, valid && !fast);
+    if (slow && lane == 0) atomicAdd(w.stats + 1, (unsigned)__popc(slow));
+    while (slow) {
+      const int src = __ffs(slow) - 1; slow &= slow - 1;
+      const int sb = __shfl_sync(full, b, src), sj = __shfl_sync(full, j, src);
+      const float sthr = __shfl_sync(full, thr, src);
+      const float4 q = make_float4(__shfl_sync(full, cq.x, src), __shfl_sync(full, cq.y, src),
+                                   __shfl_sync(full, cq.z, src), 0.f);
+      const float* rec = w.colrec + (size_t)sb * g.nRB * 3 * g.Mp + sj;
+      unsigned bd = 0xffffffffu, bi = 0xffffffffu;
+      const int nE = g.nRB * 3;
+      for (int base = 0; base < nE; base += 32) {
+        const int e = base + lane;
+        const float p = e < nE ? rec[(size_t)e * g.Mp] : inf;
+        unsigned hits = __ballot_sync(full, p <= sthr);
+        while (hits) {
+          const int hl = __ffs(hits) - 1; hits &= hits - 1;
+          const int he = base + hl, hrb = he / 3, hk = he - hrb * 3;
+          const unsigned pbits = __float_as_uint(__shfl_sync(full, p, hl));
+          int first, n;
+          if (hk < 2) { first = (hrb * 32 + (int)(pbits & 31u)) * kFRowsPerThread; n = kFRowsPerThread; }
+          else { first = hrb * kFRowsPerWarp; n = kFRowsPerWarp; if (lane == 0) atomicAdd(w.stats + 2, 1u); }
+          unsigned dm = 0xffffffffu, im = 0xffffffffu;
+          for (int o = lane; o < n; o += 32) {
+            const int row = first + o;
+            if (row < g.N) {
+              const float4 pr = w.rowpack[(size_t)sb * g.Npad + row];
+              const unsigned d = __float_as_uint(sqdist_q(pr.x, pr.y, pr.z, q));
+              if (d < dm) { dm = d; im = (unsigned)row; }
+            }
+          }
+          const unsigned mn = __reduce_min_sync(full, dm);
+          const unsigned ii = __reduce_min_sync(full, dm == mn ? im : 0xffffffffu);
+          if (mn < bd || (mn == bd && ii < bi)) { bd = mn; bi = ii; }
+        }
+      }
+      if (lane == src) { best_d = bd; best_i = bi; }
+    }
+
+    myd = __uint_as_float(best_d);
+    const int i = (int)best_i;
+    if (valid) {
+      if (f.dist2) f.dist2[t] = myd;
+      if (f.idx2) f.idx2[t] = i;
+    }
+    if (f.own_y || f.scat_x) {
+      float vx = 0.f, vy = 0.f, vz = 0.f;
+      if (valid) {
+        const float4 p = w.rowpack[(size_t)b * g.Npad + i];
+        // d/dy_j |y_j - x_i|^2 = 2 (y_j - x_i) = -2 (x_i - y_j)
+        vx = -coef_grad * __fmaf_rn(0.5f, cq.x, p.x);
+        vy = -coef_grad * __fmaf_rn(0.5f, cq.y, p.y);
+        vz = -coef_grad * __fmaf_rn(0.5f, cq.z, p.z);
+        if (f.own_y) { float* o = f.own_y + t * 3; o[0] = vx; o[1] = vy; o[2] = vz; }
+      }
+      if (f.scat_x) scatter_add4(f.scat_x + ((long long)b * g.N + i), (long long)b * g.N + i, valid, -vx, -vy, -vz);
+    }
+  }
+
+  if (f.loss) {
+    double sd = valid ? (double)myd : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+    if (lane == 0) lsum[warp] = sd;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int k = 0; k < kFinWarps; ++k) tot += lsum[k];
+      atomicAdd(f.loss, (float)(tot * (double)f.coef_loss));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side (called from the dispatcher in chamfer.cu)
+// ---------------------------------------------------------------------------------------------------------------
+static int g_force_unit_run = 0;   // experiment hook
+void f_set_force_unit_run(int u) { g_force_unit_run = u; }
+
+bool f_sizes_ok(int B, int N, int M) {
+  if (B <= 0 || N <= 0 || M <= 0) return false;
+  if ((long long)N > (1LL << 30) || (long long)M > (1LL << 30)) return false;
+  const FGeometry g = f_make_geometry(B, N, M, 296, 1);
+  if ((long long)B * g.Npad >= (1LL << 31) || (long long)B * g.Mp >= (1LL << 31)) return false;
+  if ((long long)B * g.nRBC >= (1LL << 24)) return false;
+  return true;
+}
+
+// Bytes of the filter's tile records alone (the dispatcher's size criterion; device independent).
+size_t f_record_bytes(int B, int N, int M) {
+  const FGeometry g = f_make_geometry(B, N, M, 296, 1);
+  return ((size_t)g.B * g.nT * g.Npad + (size_t)g.B * g.nRB * 3 * g.Mp) * sizeof(float);
+}
+
+// SM count and resident search CTAs per SM of the current device.  Immutable device properties, cached per device
+// (the occupancy query costs ~10 us of host time, which matters for eager callers at ~90 us per step).
+static int f_caps(int* sms, int* occ) {
+  static int cache_sms[64], cache_occ[64];
+  static bool cache_ok[64];
+  int dev = 0;
+  RMA_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && cache_ok[dev]) { *sms = cache_sms[dev]; *occ = cache_occ[dev]; return 0; }
+  RMA_CUDA_TRY(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kFSearchSmem));
+  RMA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, chamfer_fsearch_kernel, kFThreads, kFSearchSmem));
+  if (*occ < 1) *occ = 1;
+  if (dev >= 0 && dev < 64) { cache_sms[dev] = *sms; cache_occ[dev] = *occ; cache_ok[dev] = true; }
+  return 0;
+}
+
+// Geometry for the current device (the unit run depends on SM count x resident CTAs).  Re-derived per call: the
+// library keeps no state, and every stage of one forward derives the identical geometry.
+static int f_geometry(int B, int N, int M, FGeometry* g, int* occ_out) {
+  int sms = 0, occ = 0;
+  if (int e = f_caps(&sms, &occ)) return e;
+  *g = f_make_geometry(B, N, M, sms * occ, g_force_unit_run);
+  if (occ_out) *occ_out = occ;
+  return 0;
+}
+
+size_t f_workspace_bytes(int B, int N, int M) {
+  FGeometry g;
+  if (f_geometry(B, N, M, &g, nullptr)) return 0;
+  return f_carve(g, nullptr).bytes;
+}
+
+static int f_setup(int B, int N, int M, void* workspace, size_t workspace_bytes, FGeometry* g, FWorkspace* w) {
+  if (!workspace || !f_sizes_ok(B, N, M)) return RMA_E_BADARG;
+  if (int e = f_geometry(B, N, M, g, nullptr)) return e;
+  if (((uintptr_t)workspace & 255u) != 0) return RMA_E_WORKSPACE;
+  *w = f_carve(*g, workspace);
+  if (workspace_bytes < w->bytes) return RMA_E_WORKSPACE;
+  return RMA_OK;
+}
+
+int f_launch_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                  const float* y, int64_t ysb, int64_t ysn, int64_t ysc, int B, int N, int M,
+                  void* workspace, size_t workspace_bytes, float* zero_loss, float4* zero_gx, float4* zero_gy,
+                  void* stream_) {
+  if (!x || !y) return RMA_E_BADARG;
+  FGeometry g; FWorkspace w;
+  if (int e = f_setup(B, N, M, workspace, workspace_bytes, &g, &w)) return e;
+  const long long slots = (long long)B * (g.Npad + g.Mp);
+  RMA_CUDA_TRY(launch_pdl(chamfer_fprep_kernel, (unsigned)grid_for(slots, 256), 256u, 0, (cudaStream_t)stream_,
+                          x, (long long)xsb, (long long)xsn, (long long)xsc, y, (long long)ysb, (long long)ysn,
+                          (long long)ysc, g, w, zero_loss, zero_gx, zero_gy));
+  return RMA_OK;
+}
+
+int f_search_config(int B, int N, int M, int* ctas, int* threads, int* splits, int* ctas_per_sm) {
+  if (!f_sizes_ok(B, N, M)) return RMA_E_BADARG;
+  FGeometry g;
+  int occ = 0;
+  if (int e = f_geometry(B, N, M, &g, &occ)) return e;
+  if (ctas) *ctas = (int)((g.units() + g.U - 1) / g.U);
+  if (threads) *threads = kFThreads;
+  if (splits) *splits = g.U;          // for this path: 64-column tiles per CTA
+  if (ctas_per_sm) *ctas_per_sm = occ;
+  return RMA_OK;
+}
+
+int f_launch_search(int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream_) {
+  FGeometry g; FWorkspace w;
+  if (int e = f_setup(B, N, M, workspace, workspace_bytes, &g, &w)) return e;
+  FSearchArgs a;
+  a.rowsoa = w.rowsoa; a.colpack = w.colpack; a.rowrec = w.rowrec; a.rowtop = w.rowtop; a.colrec = w.colrec;
+  a.N = N; a.M = M; a.nRB = g.nRB; a.Npad = g.Npad; a.nRBC = g.nRBC; a.nT = g.nT; a.Mp = g.Mp;
+  a.U = g.U; a.Smax = g.Smax; a.units = g.units();
+  const long long ctas = (a.units + g.U - 1) / g.U;
+  if (ctas > 0x7fffffffLL) return RMA_E_BADARG;
+  RMA_CUDA_TRY(launch_pdl(chamfer_fsearch_kernel, (unsigned)ctas, (unsigned)kFThreads, kFSearchSmem,
+                          (cudaStream_t)stream_, a));
+  return RMA_OK;
+}
+
+int f_launch_resolve(int B, int N, int M, const FinalizeArgs& f, void* workspace, size_t workspace_bytes,
+                     void* stream_) {
+  FGeometry g; FWorkspace w;
+  if (int e = f_setup(B, N, M, workspace, workspace_bytes, &g, &w)) return e;
+  const long long warps = ((long long)B * N + 31) / 32 + ((long long)B * M + 31) / 32;
+  RMA_CUDA_TRY(launch_pdl(chamfer_fresolve_kernel, (unsigned)grid_for(warps, kFinWarps), (unsigned)(kFinWarps * 32), 0,
+                          (cudaStream_t)stream_, g, w, f));
+  return RMA_OK;
+}
+
+int f_read_stats(void* workspace, int B, int N, int M, unsigned* out4_host, void* stream_) {
+  FGeometry g;
+  if (int e = f_geometry(B, N, M, &g, nullptr)) return e;
+  FWorkspace w = f_carve(g, workspace);
+  RMA_CUDA_TRY(cudaMemcpyAsync(out4_host, w.stats, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost,
+                               (cudaStream_t)stream_));
+  RMA_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream_));
+  return RMA_OK;
+}
+
+}  // namespace rma

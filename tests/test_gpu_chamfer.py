@@ -18,6 +18,21 @@ from oracle import c_oracle, chamfer_oracle as co
 pytestmark = pytest.mark.gpu
 
 REL = 1e-5
+
+
+@pytest.fixture(autouse=True, params=["filter", "exact"])
+def chamfer_path(request):
+    """Every test runs on both search implementations: the filter + exact-resolve path (default for these sizes) and
+    the exact difference-form search (default for huge pairs).  They must agree bit for bit."""
+    import torch as _t
+    if not _t.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from rma_net_b200 import _lib
+    lib = _lib.load()
+    lib.rma_exp_set_chamfer_path(2 if request.param == "filter" else 1, 0)
+    yield request.param
+    lib.rma_exp_set_chamfer_path(0, 0)
+
 CASES = sorted(os.path.basename(p)[8:-4] for p in glob.glob(
     os.path.join(os.path.dirname(__file__), "golden", "chamfer_*.npz")))
 
@@ -308,3 +323,71 @@ def test_baseline_sizes_bit_exact_and_properties(cuda, cfg):
     d1p, d2p, i1p, i2p = chamfer_dist_with_idx(xd, yd[:, perm])
     assert torch.equal(d1p.cpu(), torch.from_numpy(got["dist1"]))
     assert torch.equal(perm[i1p.long()].cpu().int(), torch.from_numpy(got["idx1"]))
+
+
+def _path_stats(B, N, M):
+    """(runs_filter_path, [extra row candidates, extra column candidates, row-block rescans]) of the last call."""
+    import ctypes
+    from rma_net_b200 import _lib
+    lib = _lib.load()
+    return lib.rma_exp_chamfer_path_info(B, N, M, None, None, None)
+
+
+@pytest.mark.parametrize("case", ["offset", "all_equal", "duplicates", "tiny", "huge", "planar_grid", "two_clusters"])
+def test_filter_guard_adversarial(cuda, case, chamfer_path):
+    """Inputs built to stress the expanded-form filter: heavy cancellation (clouds far from the origin), massive exact
+    ties, duplicated points in different tiles / row groups, extreme scales, lattice points (many equal distances).
+    The resolve stage must still return the exact difference-form minimum with the lowest index."""
+    rng = np.random.default_rng(42)
+    B, N, M = 2, 1500, 1700
+    if case == "offset":
+        x = (rng.uniform(-1, 1, (B, N, 3)) * 0.05 + 300.0).astype(np.float32)
+        y = (rng.uniform(-1, 1, (B, M, 3)) * 0.05 + 300.0).astype(np.float32)
+    elif case == "all_equal":
+        x = np.full((B, N, 3), 0.37, np.float32)
+        y = np.full((B, M, 3), 0.37, np.float32)
+        y[:, 5::7] += 1.0
+    elif case == "duplicates":
+        base = rng.uniform(-1, 1, (B, 300, 3)).astype(np.float32)
+        x = np.concatenate([base] * 5, 1)
+        y = np.concatenate([base[:, ::-1]] * 5 + [base[:, :200]], 1)
+    elif case == "tiny":
+        x = (rng.uniform(-1, 1, (B, N, 3)) * 1e-12).astype(np.float32)
+        y = (rng.uniform(-1, 1, (B, M, 3)) * 1e-12).astype(np.float32)
+    elif case == "huge":
+        x = (rng.uniform(-1, 1, (B, N, 3)) * 1e12).astype(np.float32)
+        y = (rng.uniform(-1, 1, (B, M, 3)) * 1e12).astype(np.float32)
+    elif case == "planar_grid":
+        gx_, gy_ = np.meshgrid(np.arange(40), np.arange(40))
+        grid = np.stack([gx_.ravel(), gy_.ravel(), np.zeros(1600)], -1).astype(np.float32) * 0.125
+        x = np.stack([grid[rng.permutation(1600)][:N] for _ in range(B)])
+        y = np.stack([(grid + np.float32(0.0625))[rng.permutation(1600)] for _ in range(B)])
+    else:
+        c = rng.uniform(-1, 1, (B, 2, 3)) * 50
+        x = (c[:, rng.integers(0, 2, N)][0][None] + rng.normal(size=(B, N, 3)) * 1e-3).astype(np.float32)
+        y = (c[:, rng.integers(0, 2, M)][0][None] + rng.normal(size=(B, M, 3)) * 1e-3).astype(np.float32)
+    got = _run(x, y, cuda)
+    _check_bit_exact_f32(x, y, got)
+    _check_grads(x, y, got)
+    _check_fused(x, y, cuda, got)
+
+
+def test_paths_agree_and_auto_dispatch(cuda):
+    """The automatic choice (filter below the record cap, exact above) is invisible in the results."""
+    from rma_net_b200 import _lib
+    from rma_net_b200.model.loss import chamfer_dist_with_idx
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(77)
+    x = (torch.rand(3, 2500, 3, generator=g) * 2 - 1).to(cuda)
+    y = (torch.rand(3, 1900, 3, generator=g) * 2 - 1).to(cuda)
+    outs = []
+    try:
+        for path, cap in ((2, 0), (1, 0), (0, 1 << 30), (0, 1)):     # cap = 1 byte forces the exact path in auto mode
+            lib.rma_exp_set_chamfer_path(path, cap)
+            assert lib.rma_exp_chamfer_path_info(3, 2500, 1900, None, None, None) == (0 if path == 1 or cap == 1 else 1)
+            outs.append([t.cpu() for t in chamfer_dist_with_idx(x, y)])
+    finally:
+        lib.rma_exp_set_chamfer_path(0, 1 << 30)
+    for o in outs[1:]:
+        for a, b_ in zip(outs[0], o):
+            assert torch.equal(a, b_)
