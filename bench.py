@@ -262,6 +262,10 @@ def run_ours(args):
             k_ms.append(e0.elapsed_time(e1))
     search_ms = sum(k_ms) / len(k_ms)
     clocks = sampler.stop()
+    # which search implementation ran for this size, and how often the filter's guard sent an item to the slow path
+    stats = (ctypes.c_uint * 4)()
+    filt = lib.rma_exp_chamfer_path_info(B, N, M, P(ws), ctypes.cast(stats, ctypes.c_void_p), stream)
+    search_kernel = "chamfer_fsearch_kernel" if filt == 1 else "chamfer_search_kernel"
 
     # ---- e2e leg: host (pinned) inputs, public API, H2D + fwd+bwd + D2H loss every step -------------------------
     loss_pin = torch.zeros((), dtype=torch.float32).pin_memory()
@@ -328,18 +332,30 @@ def run_ours(args):
                    "global_batch": B * world, "parallelism": f"batch-sharded x{world}, no collective",
                    "l2": "256 MiB flush between timed steps (inputs are 1.5 MiB, L2-resident by nature)",
                    "cuda_graph": bool(use_graph),
-                   "search_launch": {"ctas": ctas.value, "threads": thr.value, "column_splits": spl.value,
-                                     "ctas_per_sm": occ.value}},
+                   "search_launch": {"kernel": search_kernel, "ctas": ctas.value, "threads": thr.value,
+                                     ("tiles64_per_cta" if filt == 1 else "column_splits"): spl.value,
+                                     "ctas_per_sm": occ.value},
+                   "search_path": ("filter (expanded form, 3 FFMA + 1 FADD per pair) + exact difference-form resolve"
+                                   if filt == 1 else "exact difference form (6 FP32 ops per pair)"),
+                   "guard_slow_path": ({"rows": int(stats[0]), "columns": int(stats[1]),
+                                        "row_block_rescans": int(stats[2]), "of_items": B * (N + M)}
+                                       if filt == 1 else None)},
         "fp32_fma_peak_frac_step": FLOP_PER_PAIR * pairs / (ms * 1e-3) / 1e12 / peak_tflops,
-        "roofline": {"bound": "fp32_fma", "kernel": "chamfer_search_kernel", "achieved": achieved_tflops,
+        "roofline": {"bound": "fp32_fma", "kernel": search_kernel, "achieved": achieved_tflops,
                      "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
                      "traffic": None, "kernel_ms": search_ms,
+                     "note": ("achieved = ALGORITHMIC 12 FLOP (6 FMA) per point-pair (SURVEY.md section 8d) / kernel "
+                              "time.  The filter kernel itself issues 3 FFMA + 1 FADD + 2 min per pair (its exact "
+                              "re-evaluation of the candidates runs in the resolve kernel), so frac is a fraction "
+                              "of the FMA-issue roofline of the reference formulation, not FMA-pipe utilisation; "
+                              "ncu pipe numbers are in profiles/." if filt == 1 else
+                              "achieved = algorithmic 12 FLOP per point-pair / kernel time"),
                      "peak_source": f"{info['sm_count']} SMs x 128 FP32 lanes x 2 x sm_max_mhz={sm_max_mhz:.0f} "
                                     f"({peak_src} MEASURED_PEAKS.json clock); FFMA microbenchmark on this pool "
                                     f"reaches 97% of it (profiles/r01_fp32_microbench.jsonl)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4), "d2h_bytes_per_step": 4},
-        "gpu_launches": 4 * args.steps,      # prep + search + finalize(+loss,+grads) + cd_backward per step
+        "gpu_launches": 4 * args.steps,      # prep + search + resolve/finalize(+loss,+grads) + cd_backward per step
         "clocks": clocks,
         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
         "step_ms_min_max": [min(step_ms), max(step_ms)],

@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
           // Four columns against the 16 rows, plus four pending values of the previous tile's column reduce.
           auto body = [&](const float4& q0, const float4& q1, const float4& q2, const float4& q3, int jj) {
             const float4 pv = cbr[jj >> 2];          // 4 packed partial minima of the pending tile
+#ifdef RMA_F_COLMAJOR
             {
               float fA[16], fB[16];
               const float cmA = fcolumn_step(px, py, pz, pu, q0, fA);
@@ -328,6 +329,33 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
               cbw[(jj + 2) * kFCbStride] = __uint_as_float((__float_as_uint(cmA) & ~31u) | lane_tag);
               cbw[(jj + 3) * kFCbStride] = __uint_as_float((__float_as_uint(cmB) & ~31u) | lane_tag);
             }
+#else
+            // Row pair outer, the 4 columns inner: consecutive FFMA2s share the row-pair operand (operand-reuse
+            // cache), so each reads only the column's broadcast scalars from the register file; the running column
+            // minima replace the 16-value trees and no f[16] temporaries stay live.
+            const u64 x0 = pack2(q0.x, q0.x), x1 = pack2(q1.x, q1.x), x2 = pack2(q2.x, q2.x), x3 = pack2(q3.x, q3.x);
+            const u64 y0 = pack2(q0.y, q0.y), y1 = pack2(q1.y, q1.y), y2 = pack2(q2.y, q2.y), y3 = pack2(q3.y, q3.y);
+            const u64 z0 = pack2(q0.z, q0.z), z1 = pack2(q1.z, q1.z), z2 = pack2(q2.z, q2.z), z3 = pack2(q3.z, q3.z);
+            const u64 w0 = pack2(q0.w, q0.w), w1 = pack2(q1.w, q1.w), w2 = pack2(q2.w, q2.w), w3 = pack2(q3.w, q3.w);
+            float cm0 = inf, cm1 = inf, cm2 = inf, cm3 = inf;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              u64 a0 = fma2(pz[k], z0, w0), a1 = fma2(pz[k], z1, w1), a2 = fma2(pz[k], z2, w2), a3 = fma2(pz[k], z3, w3);
+              a0 = fma2(py[k], y0, a0); a1 = fma2(py[k], y1, a1); a2 = fma2(py[k], y2, a2); a3 = fma2(py[k], y3, a3);
+              a0 = fma2(px[k], x0, a0); a1 = fma2(px[k], x1, a1); a2 = fma2(px[k], x2, a2); a3 = fma2(px[k], x3, a3);
+              float l0, h0, l1, h1, l2, h2, l3, h3;
+              unpack2(a0, l0, h0); unpack2(a1, l1, h1); unpack2(a2, l2, h2); unpack2(a3, l3, h3);
+              tm[2 * k] = min3(min3(tm[2 * k], l0, l1), l2, l3);
+              tm[2 * k + 1] = min3(min3(tm[2 * k + 1], h0, h1), h2, h3);
+              unpack2(add2(a0, pu[k]), l0, h0); unpack2(add2(a1, pu[k]), l1, h1);
+              unpack2(add2(a2, pu[k]), l2, h2); unpack2(add2(a3, pu[k]), l3, h3);
+              cm0 = min3(cm0, l0, h0); cm1 = min3(cm1, l1, h1); cm2 = min3(cm2, l2, h2); cm3 = min3(cm3, l3, h3);
+            }
+            cbw[jj * kFCbStride] = __uint_as_float((__float_as_uint(cm0) & ~31u) | lane_tag);
+            cbw[(jj + 1) * kFCbStride] = __uint_as_float((__float_as_uint(cm1) & ~31u) | lane_tag);
+            cbw[(jj + 2) * kFCbStride] = __uint_as_float((__float_as_uint(cm2) & ~31u) | lane_tag);
+            cbw[(jj + 3) * kFCbStride] = __uint_as_float((__float_as_uint(cm3) & ~31u) | lane_tag);
+#endif
             top3_insert(p1, p2, p3, pv.x);
             top3_insert(p1, p2, p3, pv.y);
             top3_insert(p1, p2, p3, pv.z);

@@ -15,9 +15,9 @@ from rma_net_b200 import _lib, build as b  # noqa: E402
 
 VARIANTS = {
     "base": [],
-    "min2": ["-DRMA_F_MIN2"],
+    "colmajor": ["-DRMA_F_COLMAJOR"],
+    "colmajor_occ3": ["-DRMA_F_COLMAJOR", "-DRMA_F_MINCTAS=3", "-DRMA_F_CHUNK=512"],
     "occ3": ["-DRMA_F_MINCTAS=3", "-DRMA_F_CHUNK=512"],
-    "min2_occ3": ["-DRMA_F_MIN2", "-DRMA_F_MINCTAS=3", "-DRMA_F_CHUNK=512"],
     "chunk512": ["-DRMA_F_CHUNK=512"],
     "abl_noadd": ["-DRMA_F_ABL_NOADD"],
     "abl_nocolmin": ["-DRMA_F_ABL_NOCOLMIN"],
