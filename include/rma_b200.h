@@ -164,6 +164,50 @@ int rma_warp_backward(const float* phi, const float* src, int64_t s_sb, int64_t 
                       float* scratch, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * point_render / point_masker — the reference's `model/exfunc` CUDA extension.
+ * These four entry points replace, one for one, the raw-pointer launchers the reference's pybind wrappers call:
+ *   point_render_cuda_forward   point_render.cpp:29-33  / point_render_cuda.cu:337-352
+ *   point_render_cuda_backward  point_render.cpp:35-38  / point_render_cuda.cu:354-367
+ *   point_masker_cuda_forward   point_masker.cpp:29-30  / point_masker_cuda.cu:90-94
+ *   point_masker_cuda_backward  point_masker.cpp:32-33  / point_masker_cuda.cu:96-100
+ * with two differences in the contract: image / scratch buffers need NOT be pre-filled by the caller (the reference's
+ * wrapper fills front = 0, back = -2, depth = 0, weight = epsilon, mask = 0, grads = 0 with torch before every call,
+ * point_render.cpp:80-88, 119-120; here the kernels do it), and `weight_points` is optional (NULL): the backward
+ * recomputes the Gaussian weights instead of reading a saved [B,N,cpw^2] tensor.
+ *
+ * proj_points [B,N,3] contiguous: (x, y) in pixels, z <= 0 by convention (smaller = closer; point_render_func.py:15).
+ * Images are contiguous [B,H,W] (the reference's [B,H,W,1]).
+ *
+ * Forward: pixel_index[b,n] = (clamp(int(x),0,W-1), clamp(int(y),0,H-1));  front/back = min/max z over every point
+ * whose visible_patch_width^2 patch covers the pixel;  is_visible = !(z > (front+back)/2 && z > front+threshold) at the
+ * point's pixel;  for visible points g = expf(-|xy - pixel centre|^2 / ((cpw+1)/2)^2) over the colour patch:
+ * weight_image = epsilon + sum g, depth_image = sum g*z  (fp32 atomics, summation order unspecified as in the
+ * reference). */
+int rma_point_render_forward(const float* proj_points, int B, int N, int H, int W, int visible_patch_width,
+                             int color_patch_width, float epsilon, float threshold,
+                             int32_t* pixel_index /* [B,N,2] */, int32_t* is_visible /* [B,N] */,
+                             float* weight_points /* [B,N,cpw*cpw] or NULL */,
+                             float* depth_image, float* weight_image,
+                             float* front_image /* scratch [B,H,W] */, float* back_image /* scratch [B,H,W] */,
+                             void* stream);
+/* grad_proj_points [B,N,3] (overwritten): per point, in the reference thread's accumulation order, bit for bit:
+ *   gwp = grad_depth*z + grad_weight;  grad_xy = -(gwp*g*2/divisor);  grad x,y += grad_xy*(xy - centre);
+ *   grad z += grad_depth*g.   Hidden points get 0. */
+int rma_point_render_backward(const float* grad_depth_image, const float* grad_weight_image, const float* proj_points,
+                              const int32_t* pixel_index, const int32_t* is_visible, int B, int N, int H, int W,
+                              int color_patch_width, float* grad_proj_points, void* stream);
+/* mask_image [B,H,W] (overwritten): -1 inside every point's mask_patch_width^2 patch, 0 elsewhere. */
+int rma_point_masker_forward(const float* proj_points, int B, int N, int H, int W, int mask_patch_width,
+                             float* mask_image, void* stream);
+/* grad_proj_points [B,N,3] (overwritten; only z is non-zero): for every pixel with |g| > threshold,
+ *   grad_z[i] += g * e_i / (epsilon + sum_i e_i),  e_i = expf(-|xy_i - pixel centre|^2 / 1000).
+ * Deterministic (no atomics): active pixels are compacted in pixel order.  scratch: see ..._scratch_bytes, 256-B aligned. */
+size_t rma_point_masker_backward_scratch_bytes(int B, int H, int W);
+int rma_point_masker_backward(const float* grad_mask_image, const float* proj_points, int B, int N, int H, int W,
+                              float epsilon, float threshold, float* grad_proj_points, void* scratch,
+                              size_t scratch_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Host-buffer convenience entry (what a non-torch FFI binding would call): pageable or pinned HOST pointers,
  * contiguous [B,N,3] / [B,M,3]; allocates device memory, copies in, runs forward (+ backward of
  * loss_on_cd = 0.5 (sum dist1 + sum dist2) / B, loss.py:200-205, when grad pointers are non-NULL), copies out and

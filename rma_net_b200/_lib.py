@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_int, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "librma_b200.so")
@@ -40,6 +40,12 @@ SIGNATURES = {
                                  _P, _I64, _I64, _I64, _P, _P, _P]),
     "rma_warp_backward": (c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _I64, _I64, _I64, _P, _I64, _I64, _I64,
                                   c_int, c_int, _P, _P, _P, _I64, _I64, _I64, _P, _P]),
+    "rma_point_render_forward": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+                                         _P, _P, _P, _P, _P, _P, _P, _P]),
+    "rma_point_render_backward": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "rma_point_masker_forward": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "rma_point_masker_backward_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "rma_point_masker_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, c_size_t, _P]),
     "rma_chamfer_loss_host": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
 }
 

@@ -397,3 +397,103 @@ def device_info():
     rc = _lib.load().rma_b200_device_info(ctypes.byref(sm), ctypes.byref(khz), ctypes.byref(maj), ctypes.byref(mnr))
     _lib.check(rc, "rma_b200_device_info")
     return dict(sm_count=sm.value, clock_khz=khz.value, cc=(maj.value, mnr.value))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# point_render / point_masker (the reference's model/exfunc extension)
+# ------------------------------------------------------------------------------------------------------------
+def _check_proj(name: str, t: torch.Tensor) -> None:
+    """CHECK_CUDA + CHECK_CONTIGUOUS of the reference wrapper (point_render.cpp:21-27), raising RuntimeError."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+
+
+def point_render_forward(proj_points: torch.Tensor, image_height: int, image_width: int, visible_patch_width: int,
+                         color_patch_width: int, epsilon: float, threshold: float, want_weight_points: bool = False):
+    """Same call as the reference's `point_render.forward` (point_render.cpp:40-99).  Returns
+    [pixel_index [B,2N] i32, is_visible [B,N] i32, weight_points [B,N,cpw^2] or None, depth_image [B,H,W,1],
+    weight_image [B,H,W,1]]."""
+    _check_proj("proj_points", proj_points)
+    if proj_points.dim() != 3 or proj_points.shape[-1] != 3:
+        raise RuntimeError(f"proj_points must have shape [B, N, 3], got {tuple(proj_points.shape)}")
+    B, N = proj_points.shape[0], proj_points.shape[1]
+    H, W = int(image_height), int(image_width)
+    dev = proj_points.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    pixel_index = torch.empty((B, 2 * N), **i32)
+    is_visible = torch.empty((B, N), **i32)
+    wp = torch.empty((B, N, color_patch_width * color_patch_width), **f32) if want_weight_points else None
+    depth = torch.empty((B, H, W, 1), **f32)
+    weight = torch.empty((B, H, W, 1), **f32)
+    front_back = torch.empty((2, B, H, W), **f32)
+    if B * N:
+        with torch.cuda.device(dev):
+            rc = _lib.load().rma_point_render_forward(
+                _ptr(proj_points), B, N, H, W, int(visible_patch_width), int(color_patch_width), float(epsilon),
+                float(threshold), _ptr(pixel_index), _ptr(is_visible), _ptr(wp), _ptr(depth), _ptr(weight),
+                _ptr(front_back[0]), _ptr(front_back[1]), _stream())
+            _lib.check(rc, "rma_point_render_forward")
+    else:
+        depth.zero_()
+        weight.fill_(float(epsilon))
+    return [pixel_index, is_visible, wp, depth, weight]
+
+
+def point_render_backward(grad_depth_image, grad_weight_image, proj_points, pixel_index, is_visible,
+                          color_patch_width: int):
+    """The reference's `point_render.backward` (point_render.cpp:101-133) -> [grad_proj_points]."""
+    _check_proj("proj_points", proj_points)
+    B, N = proj_points.shape[0], proj_points.shape[1]
+    H, W = grad_depth_image.shape[1], grad_depth_image.shape[2]
+    gd = grad_depth_image.to(torch.float32).contiguous()
+    gw = grad_weight_image.to(torch.float32).contiguous()
+    out = torch.empty_like(proj_points)
+    if B * N:
+        with torch.cuda.device(proj_points.device):
+            rc = _lib.load().rma_point_render_backward(_ptr(gd), _ptr(gw), _ptr(proj_points), _ptr(pixel_index),
+                                                       _ptr(is_visible), B, N, H, W, int(color_patch_width),
+                                                       _ptr(out), _stream())
+            _lib.check(rc, "rma_point_render_backward")
+    return [out]
+
+
+def point_masker_forward(proj_points: torch.Tensor, image_height: int, image_width: int, mask_patch_width: int):
+    """The reference's `point_masker.forward` (point_masker.cpp:35-66) -> [mask_image [B,H,W,1]]."""
+    _check_proj("proj_points", proj_points)
+    if proj_points.dim() != 3 or proj_points.shape[-1] != 3:
+        raise RuntimeError(f"proj_points must have shape [B, N, 3], got {tuple(proj_points.shape)}")
+    B, N = proj_points.shape[0], proj_points.shape[1]
+    H, W = int(image_height), int(image_width)
+    mask = torch.empty((B, H, W, 1), dtype=torch.float32, device=proj_points.device)
+    if B * N:
+        with torch.cuda.device(proj_points.device):
+            rc = _lib.load().rma_point_masker_forward(_ptr(proj_points), B, N, H, W, int(mask_patch_width), _ptr(mask),
+                                                      _stream())
+            _lib.check(rc, "rma_point_masker_forward")
+    else:
+        mask.zero_()
+    return [mask]
+
+
+def point_masker_backward(grad_mask_image, proj_points, epsilon: float, threshold: float):
+    """The reference's `point_masker.backward` (point_masker.cpp:68-97) -> [grad_proj_points]."""
+    _check_proj("proj_points", proj_points)
+    B, N = proj_points.shape[0], proj_points.shape[1]
+    H, W = grad_mask_image.shape[1], grad_mask_image.shape[2]
+    g = grad_mask_image.to(torch.float32).contiguous()
+    out = torch.empty_like(proj_points)
+    if B * N == 0:
+        return [out]
+    lib = _lib.load()
+    with torch.cuda.device(proj_points.device):
+        nbytes = lib.rma_point_masker_backward_scratch_bytes(B, H, W)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=proj_points.device)
+        rc = lib.rma_point_masker_backward(_ptr(g), _ptr(proj_points), B, N, H, W, float(epsilon), float(threshold),
+                                           _ptr(out), _ptr(scratch), nbytes, _stream())
+        _lib.check(rc, "rma_point_masker_backward")
+    return [out]
