@@ -202,7 +202,7 @@ int rma_point_masker_forward(const float* proj_points, int B, int N, int H, int 
 /* grad_proj_points [B,N,3] (overwritten; only z is non-zero): for every pixel with |g| > threshold,
  *   grad_z[i] += g * e_i / (epsilon + sum_i e_i),  e_i = expf(-|xy_i - pixel centre|^2 / 1000).
  * Deterministic (no atomics): active pixels are compacted in pixel order.  scratch: see ..._scratch_bytes, 256-B aligned. */
-size_t rma_point_masker_backward_scratch_bytes(int B, int H, int W);
+size_t rma_point_masker_backward_scratch_bytes(int B, int N, int H, int W);
 int rma_point_masker_backward(const float* grad_mask_image, const float* proj_points, int B, int N, int H, int W,
                               float epsilon, float threshold, float* grad_proj_points, void* scratch,
                               size_t scratch_bytes, void* stream);

@@ -44,7 +44,7 @@ SIGNATURES = {
                                          _P, _P, _P, _P, _P, _P, _P, _P]),
     "rma_point_render_backward": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "rma_point_masker_forward": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
-    "rma_point_masker_backward_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "rma_point_masker_backward_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "rma_point_masker_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, c_size_t, _P]),
     "rma_chamfer_loss_host": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
 }

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) mask_forward_kernel(const float* __restri
 // mask_backward_kernel (point_masker_cuda.cu:39-88) in three atomic-free stages.
 constexpr int kMaskThreads = 256;
 
-struct MaskEntry { float cx, cy, g, s; };   // pixel centre, upstream gradient, epsilon + sum_i e_i
+struct MaskEntry { float cx, cy, g, s; };   // pixel centre, upstream gradient (g / s after stage 2), epsilon + sum_i e_i
 
 // Stage 1: one CTA per batch element compacts the pixels with |g| > threshold, in pixel order (deterministic).
 __global__ void __launch_bounds__(1024) mask_compact_kernel(const float* __restrict__ grad_mask, int H, int W,
@@ -246,40 +246,58 @@ __global__ void __launch_bounds__(kMaskThreads) mask_norm_kernel(const float* __
       s += distance;
     }
   }
-  if (on) ent->s = s;
+  if (on) { ent->s = s; ent->g = ent->g / s; }     // g / s once per pixel, for the gather
 }
 
-// Stage 3: one thread per point gathers  sum_pixels g * e / s  over the active pixels, in pixel order.
+// Stage 3: gather.  Thread (point i, slice k) accumulates  sum g/s * e  over the k-th slice of the batch element's
+// active pixels, in pixel order; the slices' partial sums are then added in slice order (stage 4), so the result
+// is deterministic.  g/s is formed once per pixel (stage 2), which replaces the reference's per-pair division
+// `g * e / s` (:85) by one multiply-add; the two differ by an ulp per term.
+constexpr int kMaskSlices = 16;
+
 __global__ void __launch_bounds__(kMaskThreads) mask_gather_kernel(const float* __restrict__ proj, int N, int npix,
                                                                    const MaskEntry* __restrict__ entries,
                                                                    const int* __restrict__ counts,
-                                                                   float* __restrict__ grad_proj) {
+                                                                   float* __restrict__ partial) {
   __shared__ MaskEntry se[kMaskThreads];
-  const int b = blockIdx.y;
+  const int b = blockIdx.y, slice = blockIdx.z;
   const int i = blockIdx.x * kMaskThreads + threadIdx.x;
   const bool on = i < N;
   const float* p = proj + ((long long)b * N + (on ? i : 0)) * 3;
   const float proj_x = p[0], proj_y = p[1];
   const float gamma = 1000;
   const int count = counts[b];
+  const int per = (count + kMaskSlices - 1) / kMaskSlices;
+  const int begin = min(slice * per, count), end = min(begin + per, count);
   const MaskEntry* ent = entries + (long long)b * npix;
   float acc = 0.f;
-  for (int e0 = 0; e0 < count; e0 += kMaskThreads) {
+  for (int e0 = begin; e0 < end; e0 += kMaskThreads) {
     __syncthreads();
-    if (e0 + (int)threadIdx.x < count) se[threadIdx.x] = ent[e0 + threadIdx.x];
+    if (e0 + (int)threadIdx.x < end) se[threadIdx.x] = ent[e0 + threadIdx.x];
     __syncthreads();
-    const int n = min(kMaskThreads, count - e0);
+    const int n = min(kMaskThreads, end - e0);
+#pragma unroll 4
     for (int k = 0; k < n; ++k) {
       const MaskEntry m = se[k];
       float distance = (proj_x - m.cx) * (proj_x - m.cx) + (proj_y - m.cy) * (proj_y - m.cy);
       distance = expf(-distance / gamma);
-      acc += m.g * distance / m.s;                                                            // :85
+      acc = fmaf(m.g, distance, acc);        // m.g holds g / s here
     }
   }
-  if (on) {
-    float* o = grad_proj + ((long long)b * N + i) * 3;
-    o[0] = 0.f; o[1] = 0.f; o[2] = acc;
-  }
+  if (on) partial[((long long)b * kMaskSlices + slice) * N + i] = acc;
+}
+
+// Stage 4: grad_z[i] = sum over slices, in slice order; x and y get no gradient (:85 touches only 3*i + 2).
+__global__ void __launch_bounds__(256) mask_reduce_kernel(const float* __restrict__ partial, int N, long long npoints,
+                                                          float* __restrict__ grad_proj) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npoints) return;
+  const long long b = t / N;
+  const int i = (int)(t - b * N);
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaskSlices; ++k) acc += partial[(b * kMaskSlices + k) * N + i];
+  grad_proj[t * 3] = 0.f; grad_proj[t * 3 + 1] = 0.f; grad_proj[t * 3 + 2] = acc;
 }
 
 static unsigned capped_grid(long long n, int block, int cap) {
@@ -349,9 +367,12 @@ int rma_point_masker_forward(const float* proj_points, int B, int N, int H, int 
   return RMA_OK;
 }
 
-size_t rma_point_masker_backward_scratch_bytes(int B, int H, int W) {
-  if (B <= 0 || H <= 0 || W <= 0) return 0;
-  return ((size_t)B * H * W * sizeof(MaskEntry) + 255) / 256 * 256 + ((size_t)B * sizeof(int) + 255) / 256 * 256;
+static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+
+size_t rma_point_masker_backward_scratch_bytes(int B, int N, int H, int W) {
+  if (B <= 0 || N <= 0 || H <= 0 || W <= 0) return 0;
+  return up256((size_t)B * H * W * sizeof(MaskEntry)) + up256((size_t)B * sizeof(int)) +
+         up256((size_t)B * kMaskSlices * N * sizeof(float));
 }
 
 int rma_point_masker_backward(const float* grad_mask_image, const float* proj_points, int B, int N, int H, int W,
@@ -359,20 +380,24 @@ int rma_point_masker_backward(const float* grad_mask_image, const float* proj_po
                               size_t scratch_bytes, void* stream_) {
   if (!grad_mask_image || !proj_points || !grad_proj_points || !scratch) return RMA_E_BADARG;
   if (!render_sizes_ok(B, N, H, W, 1) || B > 65535) return RMA_E_BADARG;
-  if (scratch_bytes < rma_point_masker_backward_scratch_bytes(B, H, W) || ((uintptr_t)scratch & 255u))
+  if (scratch_bytes < rma_point_masker_backward_scratch_bytes(B, N, H, W) || ((uintptr_t)scratch & 255u))
     return RMA_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream_;
   const int npix = H * W;
   MaskEntry* entries = (MaskEntry*)scratch;
-  int* counts = (int*)((char*)scratch + ((size_t)B * npix * sizeof(MaskEntry) + 255) / 256 * 256);
+  int* counts = (int*)((char*)scratch + up256((size_t)B * npix * sizeof(MaskEntry)));
+  float* partial = (float*)((char*)counts + up256((size_t)B * sizeof(int)));
   RMA_CUDA_TRY(launch_pdl(mask_compact_kernel, (unsigned)B, 1024u, 0, st, grad_mask_image, H, W, threshold, entries,
                           counts));
   // the grids cover the worst case (every pixel active); blocks beyond the batch element's count exit at once
   mask_norm_kernel<<<dim3((npix + kMaskThreads - 1) / kMaskThreads, B), kMaskThreads, 0, st>>>(
       proj_points, N, npix, epsilon, entries, counts);
   RMA_LAUNCH_CHECK();
-  mask_gather_kernel<<<dim3((N + kMaskThreads - 1) / kMaskThreads, B), kMaskThreads, 0, st>>>(
-      proj_points, N, npix, entries, counts, grad_proj_points);
+  mask_gather_kernel<<<dim3((N + kMaskThreads - 1) / kMaskThreads, B, kMaskSlices), kMaskThreads, 0, st>>>(
+      proj_points, N, npix, entries, counts, partial);
+  RMA_LAUNCH_CHECK();
+  mask_reduce_kernel<<<(unsigned)(((long long)B * N + 255) / 256), 256, 0, st>>>(partial, N, (long long)B * N,
+                                                                                 grad_proj_points);
   RMA_LAUNCH_CHECK();
   return RMA_OK;
 }

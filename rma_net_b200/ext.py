@@ -491,7 +491,7 @@ def point_masker_backward(grad_mask_image, proj_points, epsilon: float, threshol
         return [out]
     lib = _lib.load()
     with torch.cuda.device(proj_points.device):
-        nbytes = lib.rma_point_masker_backward_scratch_bytes(B, H, W)
+        nbytes = lib.rma_point_masker_backward_scratch_bytes(B, N, H, W)
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=proj_points.device)
         rc = lib.rma_point_masker_backward(_ptr(g), _ptr(proj_points), B, N, H, W, float(epsilon), float(threshold),
                                            _ptr(out), _ptr(scratch), nbytes, _stream())
