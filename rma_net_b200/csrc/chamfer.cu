@@ -16,6 +16,7 @@
 #include "../../include/rma_b200.h"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace rma {
 
@@ -597,7 +598,13 @@ int f_read_stats(void* workspace, int B, int N, int M, unsigned* out4, void* str
 // Which search runs: the filter path whenever its records (B*N*M/16 + B*N*M/43 bytes) stay below the cap, else the
 // exact path (huge single pairs).  Both return identical results.
 static int g_force_path = 0;                                  // experiment hook: 0 auto, 1 exact, 2 filter
-static size_t g_filter_record_cap = (size_t)1 << 30;          // 1 GiB
+// Record cap: default 1 GiB; RMA_B200_FILTER_RECORD_CAP_MB overrides it (180 GB of HBM make tens of GB reasonable for
+// a single huge pair: the row records are write-mostly, ~2 % of the search time in traffic).
+static size_t g_filter_record_cap = [] {
+  const char* e = std::getenv("RMA_B200_FILTER_RECORD_CAP_MB");
+  const long long mb = e ? std::atoll(e) : 0;
+  return mb > 0 ? (size_t)mb << 20 : (size_t)1 << 30;
+}();
 
 static bool use_filter(int B, int N, int M) {
   if (g_force_path == 1 || !f_sizes_ok(B, N, M)) return false;

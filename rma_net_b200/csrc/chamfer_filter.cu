@@ -2,7 +2,8 @@
 // chamfer.cu (fp32 difference-form distances, first-index ties = torch.min semantics of model/loss.py:68-69), at
 // 6 instead of 8 issue cycles per point pair.  DESIGN.md §4.
 //
-//   search   every pair is evaluated ONCE in the EXPANDED form the reference itself uses (loss.py:54-57):
+//   search   every pair is evaluated ONCE in the EXPANDED form the reference itself uses (loss.py:54-57), as packed
+//            fp32x2 over two columns with the row value as broadcast scalar (FFMA2 acc, Qpair, x_row.F32, acc):
 //              f_ij = |y_j|^2 - 2 x_i.y_j   (3 FFMA, chain seeded with |y_j|^2)         -> row direction  min_j f_ij
 //              g_ij = f_ij + |x_i|^2        (1 FADD)                                    -> column direction min_i g_ij
 //            The expanded form cancels, so f/g are only a FILTER.  Per row the minimum of f over every 64-column tile
@@ -169,44 +170,6 @@ __global__ void __launch_bounds__(256) chamfer_fprep_kernel(
 // ---------------------------------------------------------------------------------------------------------------
 // search
 // ---------------------------------------------------------------------------------------------------------------
-// One column against the thread's 16 rows (8 packed row pairs): 3 FFMA2 + 1 FADD2 per row pair
-// (FFMA2 R, Rx.F32x2, Rq.F32, Rw.F32: the column operands are broadcast scalars, one LDS.128 per column).
-// f[r] receives the row-direction value; the return value is the minimum over the 16 rows of g = f + |x|^2.
-__device__ __forceinline__ float fcolumn_step(const u64 (&px)[8], const u64 (&py)[8], const u64 (&pz)[8],
-                                              const u64 (&pu)[8], const float4 q, float (&f)[16]) {
-  const u64 c0 = pack2(q.x, q.x), c1 = pack2(q.y, q.y), c2 = pack2(q.z, q.z), cw = pack2(q.w, q.w);
-  float gg[16];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    u64 acc = fma2(pz[k], c2, cw);
-    acc = fma2(py[k], c1, acc);
-    acc = fma2(px[k], c0, acc);
-    unpack2(acc, f[2 * k], f[2 * k + 1]);
-#ifdef RMA_F_ABL_NOADD
-    gg[2 * k] = f[2 * k]; gg[2 * k + 1] = f[2 * k + 1];
-#else
-    unpack2(add2(acc, pu[k]), gg[2 * k], gg[2 * k + 1]);
-#endif
-  }
-#ifdef RMA_F_ABL_NOCOLMIN
-  return gg[0] + gg[5] + gg[10] + gg[15];
-#endif
-  const float t0 = min3(gg[0], gg[1], gg[2]);
-  const float t1 = min3(gg[3], gg[4], gg[5]);
-  const float t2 = min3(gg[6], gg[7], gg[8]);
-  const float t3 = min3(gg[9], gg[10], gg[11]);
-  const float t4 = min3(gg[12], gg[13], gg[14]);
-  const float u0 = min3(t0, t1, gg[15]);
-  const float u1 = min3(t2, t3, t4);
-  return fminf(u0, u1);
-}
-
-#ifdef RMA_F_ABL_NOROWMIN
-#define ROWMIN(t, a, b) ((r == 0) ? min3(t, a, b) : __uint_as_float(__float_as_uint(t) ^ __float_as_uint(a) ^ __float_as_uint(b)))
-#else
-#define ROWMIN(t, a, b) min3(t, a, b)
-#endif
-
 // Insert v into the ascending triple (p1 <= p2 <= p3): 5 FMNMX, no predicates.
 __device__ __forceinline__ void top3_insert(float& p1, float& p2, float& p3, float v) {
   p3 = fminf(p3, fmaxf(p2, v));
@@ -289,7 +252,13 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
     for (int cs = 0; cs < ncols; cs += kFChunk) {
       const int nc = min(kFChunk, ncols - cs);
       __syncthreads();   // previous chunk / segment fully consumed
-      for (int idx = tid; idx < nc; idx += kFThreads) scol[idx] = cp[(size_t)cs + idx];
+      // two columns (c, c+1) are staged interleaved as (q0c, q0c', q1c, q1c') (q2c, q2c', wc, wc'): an LDS.128 then
+      // delivers two ready-made fp32x2 operands of the column pair
+      for (int idx = tid; idx < (nc >> 1); idx += kFThreads) {
+        const float4 ca = cp[(size_t)cs + 2 * idx], cb = cp[(size_t)cs + 2 * idx + 1];
+        scol[2 * idx] = make_float4(ca.x, cb.x, ca.y, cb.y);
+        scol[2 * idx + 1] = make_float4(ca.z, cb.z, ca.w, cb.w);
+      }
       __syncthreads();
       if (!has_rows) continue;
 
@@ -310,52 +279,35 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
           // Four columns against the 16 rows, plus four pending values of the previous tile's column reduce.
           auto body = [&](const float4& q0, const float4& q1, const float4& q2, const float4& q3, int jj) {
             const float4 pv = cbr[jj >> 2];          // 4 packed partial minima of the pending tile
-#ifdef RMA_F_COLMAJOR
-            {
-              float fA[16], fB[16];
-              const float cmA = fcolumn_step(px, py, pz, pu, q0, fA);
-              const float cmB = fcolumn_step(px, py, pz, pu, q1, fB);
+            // fp32x2 lanes = two COLUMNS, the row value is the broadcast scalar.  The operand that stays fixed over
+            // the 16-row inner loop is then the 64-bit column pair, which the operand-reuse cache keeps (2 register
+            // words saved per FFMA2 instead of 1): FFMA2 acc, Qpair.reuse, x_row.F32, acc.
+            float cm[4];
 #pragma unroll
-              for (int r = 0; r < kFRowsPerThread; ++r) tm[r] = min3(tm[r], fA[r], fB[r]);
-              cbw[jj * kFCbStride] = __uint_as_float((__float_as_uint(cmA) & ~31u) | lane_tag);
-              cbw[(jj + 1) * kFCbStride] = __uint_as_float((__float_as_uint(cmB) & ~31u) | lane_tag);
-            }
-            {
-              float fA[16], fB[16];
-              const float cmA = fcolumn_step(px, py, pz, pu, q2, fA);
-              const float cmB = fcolumn_step(px, py, pz, pu, q3, fB);
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const float4 A = h2 ? q2 : q0, Bq = h2 ? q3 : q1;
+              const u64 Q0 = pack2(A.x, A.y), Q1 = pack2(A.z, A.w), Q2 = pack2(Bq.x, Bq.y), WW = pack2(Bq.z, Bq.w);
+              float cl = inf, ch = inf;
 #pragma unroll
-              for (int r = 0; r < kFRowsPerThread; ++r) tm[r] = min3(tm[r], fA[r], fB[r]);
-              cbw[(jj + 2) * kFCbStride] = __uint_as_float((__float_as_uint(cmA) & ~31u) | lane_tag);
-              cbw[(jj + 3) * kFCbStride] = __uint_as_float((__float_as_uint(cmB) & ~31u) | lane_tag);
+              for (int k = 0; k < 8; ++k) {
+                float xa, xb, ya, yb, za, zb, ua, ub;
+                unpack2(px[k], xa, xb); unpack2(py[k], ya, yb); unpack2(pz[k], za, zb); unpack2(pu[k], ua, ub);
+                u64 fa = fma2(Q2, pack2(za, za), WW), fb = fma2(Q2, pack2(zb, zb), WW);
+                fa = fma2(Q1, pack2(ya, ya), fa); fb = fma2(Q1, pack2(yb, yb), fb);
+                fa = fma2(Q0, pack2(xa, xa), fa); fb = fma2(Q0, pack2(xb, xb), fb);
+                float al, ah, bl, bh;
+                unpack2(fa, al, ah); unpack2(fb, bl, bh);
+                tm[2 * k] = min3(tm[2 * k], al, ah);
+                tm[2 * k + 1] = min3(tm[2 * k + 1], bl, bh);
+                unpack2(add2(fa, pack2(ua, ua)), al, ah); unpack2(add2(fb, pack2(ub, ub)), bl, bh);
+                cl = min3(cl, al, bl);
+                ch = min3(ch, ah, bh);
+              }
+              cm[2 * h2] = cl; cm[2 * h2 + 1] = ch;
             }
-#else
-            // Row pair outer, the 4 columns inner: consecutive FFMA2s share the row-pair operand (operand-reuse
-            // cache), so each reads only the column's broadcast scalars from the register file; the running column
-            // minima replace the 16-value trees and no f[16] temporaries stay live.
-            const u64 x0 = pack2(q0.x, q0.x), x1 = pack2(q1.x, q1.x), x2 = pack2(q2.x, q2.x), x3 = pack2(q3.x, q3.x);
-            const u64 y0 = pack2(q0.y, q0.y), y1 = pack2(q1.y, q1.y), y2 = pack2(q2.y, q2.y), y3 = pack2(q3.y, q3.y);
-            const u64 z0 = pack2(q0.z, q0.z), z1 = pack2(q1.z, q1.z), z2 = pack2(q2.z, q2.z), z3 = pack2(q3.z, q3.z);
-            const u64 w0 = pack2(q0.w, q0.w), w1 = pack2(q1.w, q1.w), w2 = pack2(q2.w, q2.w), w3 = pack2(q3.w, q3.w);
-            float cm0 = inf, cm1 = inf, cm2 = inf, cm3 = inf;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              u64 a0 = fma2(pz[k], z0, w0), a1 = fma2(pz[k], z1, w1), a2 = fma2(pz[k], z2, w2), a3 = fma2(pz[k], z3, w3);
-              a0 = fma2(py[k], y0, a0); a1 = fma2(py[k], y1, a1); a2 = fma2(py[k], y2, a2); a3 = fma2(py[k], y3, a3);
-              a0 = fma2(px[k], x0, a0); a1 = fma2(px[k], x1, a1); a2 = fma2(px[k], x2, a2); a3 = fma2(px[k], x3, a3);
-              float l0, h0, l1, h1, l2, h2, l3, h3;
-              unpack2(a0, l0, h0); unpack2(a1, l1, h1); unpack2(a2, l2, h2); unpack2(a3, l3, h3);
-              tm[2 * k] = min3(min3(tm[2 * k], l0, l1), l2, l3);
-              tm[2 * k + 1] = min3(min3(tm[2 * k + 1], h0, h1), h2, h3);
-              unpack2(add2(a0, pu[k]), l0, h0); unpack2(add2(a1, pu[k]), l1, h1);
-              unpack2(add2(a2, pu[k]), l2, h2); unpack2(add2(a3, pu[k]), l3, h3);
-              cm0 = min3(cm0, l0, h0); cm1 = min3(cm1, l1, h1); cm2 = min3(cm2, l2, h2); cm3 = min3(cm3, l3, h3);
-            }
-            cbw[jj * kFCbStride] = __uint_as_float((__float_as_uint(cm0) & ~31u) | lane_tag);
-            cbw[(jj + 1) * kFCbStride] = __uint_as_float((__float_as_uint(cm1) & ~31u) | lane_tag);
-            cbw[(jj + 2) * kFCbStride] = __uint_as_float((__float_as_uint(cm2) & ~31u) | lane_tag);
-            cbw[(jj + 3) * kFCbStride] = __uint_as_float((__float_as_uint(cm3) & ~31u) | lane_tag);
-#endif
+            for (int c = 0; c < 4; ++c)
+              cbw[(jj + c) * kFCbStride] = __uint_as_float((__float_as_uint(cm[c]) & ~31u) | lane_tag);
             top3_insert(p1, p2, p3, pv.x);
             top3_insert(p1, p2, p3, pv.y);
             top3_insert(p1, p2, p3, pv.z);

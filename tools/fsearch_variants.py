@@ -15,16 +15,8 @@ from rma_net_b200 import _lib, build as b  # noqa: E402
 
 VARIANTS = {
     "base": [],
-    "colmajor": ["-DRMA_F_COLMAJOR"],
-    "colmajor_occ3": ["-DRMA_F_COLMAJOR", "-DRMA_F_MINCTAS=3", "-DRMA_F_CHUNK=512"],
     "occ3": ["-DRMA_F_MINCTAS=3", "-DRMA_F_CHUNK=512"],
     "chunk512": ["-DRMA_F_CHUNK=512"],
-    "abl_noadd": ["-DRMA_F_ABL_NOADD"],
-    "abl_nocolmin": ["-DRMA_F_ABL_NOCOLMIN"],
-    "abl_noadd_nocolmin": ["-DRMA_F_ABL_NOADD", "-DRMA_F_ABL_NOCOLMIN"],
-    "abl_norowmin": ["-DRMA_F_ABL_NOROWMIN"],
-    "abl_notop3": ["-DRMA_F_ABL_NOTOP3"],
-    "abl_fmaonly": ["-DRMA_F_ABL_NOADD", "-DRMA_F_ABL_NOCOLMIN", "-DRMA_F_ABL_NOROWMIN", "-DRMA_F_ABL_NOTOP3"],
 }
 
 
