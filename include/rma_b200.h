@@ -208,6 +208,18 @@ int rma_point_masker_backward(const float* grad_mask_image, const float* proj_po
                               size_t scratch_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Brute-force k nearest neighbours.  Replaces the [B,N,N] matrix + torch.topk of
+ *   knn(x, k)                        model/network.py:52-58  (k = 5, x [B,3,N]: pass strides (3N, 1, N))
+ *   get_neighbor_index(vertices, n)  model/loss.py:99-110    (k = n + 1, skip_first = 1)
+ * idx[b,i,:] = indices of the k candidates nearest to query i, ascending by (exact fp32 difference-form squared
+ * distance, then index); the first `skip_first` of them are dropped, so idx (and dist, optional) are contiguous
+ * [B,N,k-skip_first].  queries [B,N,3] / candidates [B,M,3] with element strides; pass the same tensor twice for
+ * the reference's self-kNN.  k <= 32; slots beyond M candidates are -1. */
+int rma_knn(const float* queries, int64_t qsb, int64_t qsn, int64_t qsc,
+            const float* candidates, int64_t csb, int64_t csn, int64_t csc,
+            int B, int N, int M, int k, int skip_first, int32_t* idx, float* dist, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Host-buffer convenience entry (what a non-torch FFI binding would call): pageable or pinned HOST pointers,
  * contiguous [B,N,3] / [B,M,3]; allocates device memory, copies in, runs forward (+ backward of
  * loss_on_cd = 0.5 (sum dist1 + sum dist2) / B, loss.py:200-205, when grad pointers are non-NULL), copies out and

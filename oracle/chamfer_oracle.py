@@ -172,3 +172,31 @@ def read_obj_vertices(path: str) -> np.ndarray:
             if len(tok) >= 4 and tok[0] == "v":
                 pts.append((float(tok[1]), float(tok[2]), float(tok[3])))
     return np.asarray(pts, np.float32)
+
+
+def knn_exact(queries, candidates, k, skip_first=0):
+    """Brute-force kNN in float64 difference form, order (distance, index) — the semantics of rma_knn.
+    Returns (idx [B,N,k-skip_first] int32, dist float64).  For sizes the oracle finishes in seconds."""
+    q = np.asarray(queries, np.float64)
+    c = np.asarray(candidates, np.float64)
+    B, N = q.shape[:2]
+    M = c.shape[1]
+    idx = np.empty((B, N, k - skip_first), np.int32)
+    dist = np.empty((B, N, k - skip_first), np.float64)
+    for b in range(B):
+        for s in range(0, N, 512):
+            d = ((q[b, s:s + 512, None, :] - c[b, None, :, :]) ** 2).sum(-1)             # [n, M]
+            order = np.lexsort((np.broadcast_to(np.arange(M), d.shape), d), axis=-1)[:, :k]
+            idx[b, s:s + 512] = order[:, skip_first:]
+            dist[b, s:s + 512] = np.take_along_axis(d, order, -1)[:, skip_first:]
+    return idx, dist
+
+
+def knn_reference_formulation(x_b3n, k):
+    """network.py:52-58 restated with torch on CPU (expanded form + topk): idx [B,N,k] int64."""
+    import torch
+    x = torch.as_tensor(x_b3n)
+    inner = -2 * torch.matmul(x.transpose(2, 1).contiguous(), x)
+    xx = torch.sum(x ** 2, dim=1, keepdim=True)
+    pairwise_distance = -xx - inner - xx.transpose(2, 1).contiguous()
+    return pairwise_distance.topk(k=k, dim=-1)[1].numpy()

@@ -1,0 +1,103 @@
+// Brute-force k-nearest-neighbour indices for B200 (sm_100a) — SURVEY.md §8f rank 2.
+//
+// Replaces the two [B,N,N]-matrix + torch.topk sites of the reference:
+//   knn(x, k)                         model/network.py:52-58   (DGCNN feature graph, k = 5; x is [B,3,N])
+//   get_neighbor_index(vertices, n)   model/loss.py:99-110     (ARAP graph, k = n + 1 smallest, first one dropped)
+// The matrix is never materialised: one thread per query keeps its k best (distance, index) pairs sorted in
+// registers while the candidates of its batch element stream through shared memory (one broadcast LDS.128 per
+// candidate per warp).  Distances are the exact fp32 difference form (dx*dx, fma(dy,dy,.), fma(dz,dz,.)) — the
+// reference's expanded form cancels (1e-2..1e-5 relative) — and the order is (distance, then index), so results
+// are deterministic, self comes first unless an earlier duplicate exists, and torch.topk's unspecified tie order
+// is replaced by the lowest index.
+#include "common.cuh"
+#include "../../include/rma_b200.h"
+
+namespace rma {
+
+constexpr int kKnnThreads = 128;
+constexpr int kKnnChunk = 1024;    // candidates staged per round (16 KB)
+
+template <int K>
+__global__ void __launch_bounds__(kKnnThreads) knn_kernel(
+    const float* __restrict__ q, long long qsb, long long qsn, long long qsc,
+    const float* __restrict__ c, long long csb, long long csn, long long csc,
+    int N, int M, int k, int skip_first, int* __restrict__ idx_out, float* __restrict__ dist_out) {
+  __shared__ float4 sc[kKnnChunk];
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * kKnnThreads + threadIdx.x;
+  const bool on = i < N;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (on) { const float* p = q + b * qsb + i * qsn; x = p[0]; y = p[qsc]; z = p[2 * qsc]; }
+  float bd[K];
+  int bi[K];
+#pragma unroll
+  for (int p = 0; p < K; ++p) { bd[p] = __int_as_float(0x7f800000); bi[p] = 0x7fffffff; }
+  const float* cb = c + b * csb;
+  for (int c0 = 0; c0 < M; c0 += kKnnChunk) {
+    const int n = min(kKnnChunk, M - c0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += kKnnThreads) {
+      const float* p = cb + (long long)(c0 + t) * csn;
+      sc[t] = make_float4(-p[0], -p[csc], -p[2 * csc], 0.f);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int t = 0; t < n; ++t) {
+      const float4 cc = sc[t];
+      const float d = sqdist_neg(x, y, z, cc.x, cc.y, cc.z);
+      if (d < bd[K - 1]) {      // strict: an equal later candidate never displaces an earlier (lower index) one
+        float cd = d;
+        int ci = c0 + t;
+#pragma unroll
+        for (int p = 0; p < K; ++p) {      // stable sorted insert: carry the displaced element down
+          const bool sw = cd < bd[p];
+          const float td = bd[p];
+          const int ti = bi[p];
+          bd[p] = sw ? cd : td; bi[p] = sw ? ci : ti;
+          cd = sw ? td : cd; ci = sw ? ti : ci;
+        }
+      }
+    }
+  }
+  if (on) {
+    // entries beyond k never left the registers' tail; only the first k (after the optional skip) are written
+    const int kout = k - skip_first;
+    int* o = idx_out + ((long long)b * N + i) * kout;
+    float* od = dist_out ? dist_out + ((long long)b * N + i) * kout : nullptr;
+#pragma unroll
+    for (int p = 0; p < K; ++p) {
+      const int w = p - skip_first;
+      if (p < k && w >= 0) { o[w] = bi[p] == 0x7fffffff ? -1 : bi[p]; if (od) od[w] = bd[p]; }
+    }
+  }
+}
+
+}  // namespace rma
+
+using namespace rma;
+
+extern "C" {
+
+int rma_knn(const float* queries, int64_t qsb, int64_t qsn, int64_t qsc,
+            const float* candidates, int64_t csb, int64_t csn, int64_t csc,
+            int B, int N, int M, int k, int skip_first, int32_t* idx, float* dist, void* stream_) {
+  if (!queries || !candidates || !idx || B <= 0 || N <= 0 || M <= 0) return RMA_E_BADARG;
+  if (k <= 0 || k > 32 || skip_first < 0 || skip_first >= k || B > 65535) return RMA_E_BADARG;
+  if ((long long)N > (1LL << 30) || (long long)M > (1LL << 30)) return RMA_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const dim3 grid((unsigned)((N + kKnnThreads - 1) / kKnnThreads), (unsigned)B);
+  // k sorted slots are compile-time (registers): 8 covers the reference's k = 5 in both call sites
+#define RMA_KNN_LAUNCH(KK)                                                                                       \
+  knn_kernel<KK><<<grid, kKnnThreads, 0, st>>>(queries, (long long)qsb, (long long)qsn, (long long)qsc, candidates, \
+                                               (long long)csb, (long long)csn, (long long)csc, N, M, k, skip_first, \
+                                               (int*)idx, dist)
+  if (k <= 8) RMA_KNN_LAUNCH(8);
+  else if (k <= 16) RMA_KNN_LAUNCH(16);
+  else RMA_KNN_LAUNCH(32);
+#undef RMA_KNN_LAUNCH
+  RMA_LAUNCH_CHECK();
+  return RMA_OK;
+}
+
+}  // extern "C"

@@ -497,3 +497,33 @@ def point_masker_backward(grad_mask_image, proj_points, epsilon: float, threshol
                                            _ptr(out), _ptr(scratch), nbytes, _stream())
         _lib.check(rc, "rma_point_masker_backward")
     return [out]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# brute-force kNN
+# ------------------------------------------------------------------------------------------------------------
+def knn_indices(queries: torch.Tensor, candidates: torch.Tensor, k: int, skip_first: int = 0,
+                want_dist: bool = False):
+    """queries [B,N,3], candidates [B,M,3] (any strides) -> idx [B,N,k-skip_first] int32 (and squared distances),
+    ascending by (distance, index)."""
+    _check_points("queries", queries)
+    _check_points("candidates", candidates)
+    _same_device(queries, candidates)
+    B, N, M = queries.shape[0], queries.shape[1], candidates.shape[1]
+    if candidates.shape[0] != B:
+        raise RuntimeError(f"batch sizes differ: {B} vs {candidates.shape[0]}")
+    k = int(k)
+    if not (0 < k <= 32) or not (0 <= skip_first < k):
+        raise RuntimeError(f"k must be in 1..32 and skip_first in 0..k-1, got k={k}, skip_first={skip_first}")
+    if k > M:
+        raise RuntimeError(f"k={k} exceeds the number of candidates {M} (torch.topk raises as well)")
+    dev = queries.device
+    idx = torch.empty((B, N, k - skip_first), dtype=torch.int32, device=dev)
+    dist = torch.empty((B, N, k - skip_first), dtype=torch.float32, device=dev) if want_dist else None
+    if B * N:
+        qs, cs = queries.stride(), candidates.stride()
+        with torch.cuda.device(dev):
+            rc = _lib.load().rma_knn(_ptr(queries), qs[0], qs[1], qs[2], _ptr(candidates), cs[0], cs[1], cs[2],
+                                     B, N, M, k, int(skip_first), _ptr(idx), _ptr(dist), _stream())
+            _lib.check(rc, "rma_knn")
+    return (idx, dist) if want_dist else idx

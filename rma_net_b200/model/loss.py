@@ -4,6 +4,8 @@
     chamfer_dist         loss.py:60-70     -> (dist1 [B,M], dist2 [B,N])
     loss_on_cd           loss.py:200-205   (a method of Loss in the reference; a function here)
     loss_cd_stages       loss.py:260-267   (the gamma-weighted stage loop of Loss.forward)
+    get_neighbor_index   loss.py:99-110    ARAP neighbour graph: the n nearest OTHER vertices -> [B,V,n] (int64)
+    indexing_neighbor    loss.py:113-120   gather by that index (torch)
 
 Differences from the reference that a caller can observe: distances are evaluated in fp32
 difference form (accurate to ~2e-7 relative) instead of the expanded |x|^2+|y|^2-2x.y form (1e-2..1e-5), so they
@@ -54,3 +56,18 @@ def loss_cd_stages(deformation_points_list, target_points, gamma=0.8, weight_cd=
         loss_cd = loss_cd + gamma ** (iter_time - i - 1) * loss_on_cd(
             deformation_points_list[i].transpose(1, 2), target_points)
     return loss_cd * weight_cd
+
+
+def get_neighbor_index(vertices, neighbor_num):
+    """vertices [B,V,3] -> [B,V,neighbor_num] (int64): the reference takes the neighbor_num + 1 smallest entries of
+    the expanded-form distance matrix and drops the first (loss.py:107-108).  Here: rma_knn with k = neighbor_num + 1,
+    skip_first = 1, ordered by (exact distance, index); the dropped entry is the vertex itself unless an identical
+    vertex with a lower index exists (the reference's choice in that case is whatever torch.topk returns first)."""
+    return ext.knn_indices(vertices.detach(), vertices.detach(), neighbor_num + 1, skip_first=1).long()
+
+
+def indexing_neighbor(tensor, index):
+    """tensor [B,V,dim], index [B,V,n] -> [B,V,n,dim]   (loss.py:113-120)"""
+    bs = index.size(0)
+    id_0 = torch.arange(bs, device=tensor.device).view(-1, 1, 1)
+    return tensor[id_0, index]

@@ -1,0 +1,34 @@
+"""kNN part of the reference's model/network.py, same names and argument meaning, CUDA-only.
+
+    knn(x, k)                 network.py:52-58    x [B,3,N] -> idx [B,N,k] (int64), nearest first, self included
+    get_graph_feature(x, k)   network.py:61-83    DGCNN edge features [B,6,N,k] on top of knn (pure indexing, torch)
+
+The reference builds the [B,N,N] matrix `-|xi|^2 + 2 xi.xj - |xj|^2` and takes torch.topk of it; here the matrix is
+never materialised (rma_knn, csrc/knn.cu).  Order: (exact fp32 difference-form distance, then index) — torch.topk's
+order among equal values is unspecified, and the reference's expanded form can swap near-equal neighbours.
+Feature dimensions other than 3 are not on the reference's path (knn is only called on the input cloud,
+network.py:264) and raise.
+"""
+import torch
+
+from .. import ext
+
+
+def knn(x, k):
+    if x.dim() != 3 or x.shape[1] != 3:
+        raise RuntimeError(f"knn expects x of shape [B, 3, N], got {tuple(x.shape)}")
+    pts = x.detach().transpose(2, 1)                  # [B,N,3] view with strides (3N, 1, N): no copy
+    return ext.knn_indices(pts, pts, k).long()        # (batch_size, num_points, k)
+
+
+def get_graph_feature(x, k=5):
+    idx = knn(x, k=k)                                 # (batch_size, num_points, k)
+    batch_size, num_points, _ = idx.size()
+    idx_base = torch.arange(0, batch_size, device=x.device).view(-1, 1, 1) * num_points
+    idx = (idx + idx_base).view(-1)
+    _, num_dims, _ = x.size()
+    x = x.transpose(2, 1).contiguous()
+    feature = x.view(batch_size * num_points, -1)[idx, :]
+    feature = feature.view(batch_size, num_points, k, num_dims)
+    x = x.view(batch_size, num_points, 1, num_dims).repeat(1, 1, k, 1)
+    return torch.cat((feature, x), dim=3).permute(0, 3, 1, 2)
