@@ -316,6 +316,144 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(
   block_sum12_atomic(acc, scratch + (long long)b * 12, red);
 }
 
+// ---- contiguous fast paths: 4 points = 48 bytes = 3 x LDG.128 / STG.128 per tensor (the strided kernels above issue
+// 3 scalar accesses per point and reach ~70 % / 48 % of the HBM copy bandwidth; these are for [B,N,3] contiguous,
+// 16-byte aligned tensors with N % 4 == 0).  Per-point arithmetic is the same expression, so results are identical.
+struct Pts4 { float x[4], y[4], z[4]; };
+__device__ __forceinline__ Pts4 load_pts4(const float* base) {
+  const float4* v = reinterpret_cast<const float4*>(base);
+  const float4 a = v[0], b = v[1], c = v[2];
+  Pts4 r;
+  r.x[0] = a.x; r.y[0] = a.y; r.z[0] = a.z; r.x[1] = a.w; r.y[1] = b.x; r.z[1] = b.y;
+  r.x[2] = b.z; r.y[2] = b.w; r.z[2] = c.x; r.x[3] = c.y; r.y[3] = c.z; r.z[3] = c.w;
+  return r;
+}
+__device__ __forceinline__ void store_pts4(float* base, const Pts4& r) {
+  float4* v = reinterpret_cast<float4*>(base);
+  v[0] = make_float4(r.x[0], r.y[0], r.z[0], r.x[1]);
+  v[1] = make_float4(r.y[1], r.z[1], r.x[2], r.y[2]);
+  v[2] = make_float4(r.z[2], r.x[3], r.y[3], r.z[3]);
+}
+
+__global__ void __launch_bounds__(256) warp_fwd_vec_kernel(
+    const float* __restrict__ phi, const float* __restrict__ src, const float* __restrict__ w,
+    const float* __restrict__ prev, int N, float* __restrict__ out, float* __restrict__ g_out,
+    float* __restrict__ rigid_out) {
+  __shared__ float sg[12];
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    float g[12];
+    se3_exp(phi + (long long)b * 6, g);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) sg[i] = g[i];
+    if (g_out && blockIdx.x == 0) {
+      float4* o = reinterpret_cast<float4*>(g_out + (long long)b * 16);
+      o[0] = make_float4(g[0], g[1], g[2], g[3]);
+      o[1] = make_float4(g[4], g[5], g[6], g[7]);
+      o[2] = make_float4(g[8], g[9], g[10], g[11]);
+      o[3] = make_float4(0.f, 0.f, 0.f, 1.f);
+    }
+  }
+  __syncthreads();
+  float g[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) g[i] = sg[i];
+  const long long base = (long long)b * N;
+  for (int k4 = blockIdx.x * blockDim.x + threadIdx.x; k4 < N / 4; k4 += gridDim.x * blockDim.x) {
+    const long long o3 = (base + 4LL * k4) * 3;
+    const Pts4 p = load_pts4(src + o3);
+    Pts4 r;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      r.x[e] = g[0] * p.x[e] + g[1] * p.y[e] + g[2] * p.z[e] + g[3];
+      r.y[e] = g[4] * p.x[e] + g[5] * p.y[e] + g[6] * p.z[e] + g[7];
+      r.z[e] = g[8] * p.x[e] + g[9] * p.y[e] + g[10] * p.z[e] + g[11];
+    }
+    if (rigid_out) store_pts4(rigid_out + o3, r);
+    if (w) {
+      const float4 wv = *reinterpret_cast<const float4*>(w + base + 4LL * k4);
+      const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      const Pts4 q = load_pts4(prev + o3);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float om = 1.f - ww[e];
+        r.x[e] = ww[e] * r.x[e] + om * q.x[e];
+        r.y[e] = ww[e] * r.y[e] + om * q.y[e];
+        r.z[e] = ww[e] * r.z[e] + om * q.z[e];
+      }
+    }
+    store_pts4(out + o3, r);
+  }
+}
+
+__global__ void __launch_bounds__(256) warp_bwd_vec_kernel(
+    const float* __restrict__ phi, const float* __restrict__ src, const float* __restrict__ w,
+    const float* __restrict__ prev, const float* __restrict__ go, int N, float* __restrict__ grad_w,
+    float* __restrict__ grad_src, float* __restrict__ scratch) {
+  __shared__ float sg[12];
+  __shared__ float red[8 * 12];
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    float g[12];
+    se3_exp(phi + (long long)b * 6, g);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) sg[i] = g[i];
+  }
+  __syncthreads();
+  float g[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) g[i] = sg[i];
+  float acc[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+  const long long base = (long long)b * N;
+  for (int k4 = blockIdx.x * blockDim.x + threadIdx.x; k4 < N / 4; k4 += gridDim.x * blockDim.x) {
+    const long long o3 = (base + 4LL * k4) * 3;
+    const Pts4 p = load_pts4(src + o3);
+    Pts4 o = load_pts4(go + o3);
+    if (w) {
+      const float4 wv = *reinterpret_cast<const float4*>(w + base + 4LL * k4);
+      const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      if (grad_w) {
+        const Pts4 pv = load_pts4(prev + o3);
+        float gw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float rx = g[0] * p.x[e] + g[1] * p.y[e] + g[2] * p.z[e] + g[3];
+          const float ry = g[4] * p.x[e] + g[5] * p.y[e] + g[6] * p.z[e] + g[7];
+          const float rz = g[8] * p.x[e] + g[9] * p.y[e] + g[10] * p.z[e] + g[11];
+          gw[e] = o.x[e] * (rx - pv.x[e]) + o.y[e] * (ry - pv.y[e]) + o.z[e] * (rz - pv.z[e]);
+        }
+        *reinterpret_cast<float4*>(grad_w + base + 4LL * k4) = make_float4(gw[0], gw[1], gw[2], gw[3]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { o.x[e] *= ww[e]; o.y[e] *= ww[e]; o.z[e] *= ww[e]; }
+    }
+    if (grad_src) {
+      Pts4 d;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        d.x[e] = g[0] * o.x[e] + g[4] * o.y[e] + g[8] * o.z[e];
+        d.y[e] = g[1] * o.x[e] + g[5] * o.y[e] + g[9] * o.z[e];
+        d.z[e] = g[2] * o.x[e] + g[6] * o.y[e] + g[10] * o.z[e];
+      }
+      store_pts4(grad_src + o3, d);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[0] += o.x[e] * p.x[e]; acc[1] += o.x[e] * p.y[e]; acc[2] += o.x[e] * p.z[e]; acc[3] += o.x[e];
+      acc[4] += o.y[e] * p.x[e]; acc[5] += o.y[e] * p.y[e]; acc[6] += o.y[e] * p.z[e]; acc[7] += o.y[e];
+      acc[8] += o.z[e] * p.x[e]; acc[9] += o.z[e] * p.y[e]; acc[10] += o.z[e] * p.z[e]; acc[11] += o.z[e];
+    }
+  }
+  block_sum12_atomic(acc, scratch + (long long)b * 12, red);
+}
+
+// true if t is [B,N,3] contiguous from a 16-byte aligned base (or null)
+static bool contig_aos(const void* t, long long sb, long long sn, long long sc, int N) {
+  return !t || (sc == 1 && sn == 3 && sb == 3LL * N && (((uintptr_t)t) & 15u) == 0);
+}
+
 // grad_g rows (scratch [B,12]) -> grad_phi through ExpMap.backward.
 __global__ void warp_bwd_phi_kernel(const float* __restrict__ phi, const float* __restrict__ scratch, int B,
                                     float* __restrict__ grad_phi) {
@@ -391,6 +529,16 @@ int rma_warp_forward(const float* phi, const float* src, int64_t s_sb, int64_t s
                      int64_t o_sb, int64_t o_sn, int64_t o_sc, float* g_out, float* rigid_out, void* stream) {
   if (!phi || !src || !out || B <= 0 || N <= 0 || B > 65535) return RMA_E_BADARG;
   if (w && !prev) return RMA_E_BADARG;
+  if (N % 4 == 0 && contig_aos(src, s_sb, s_sn, s_sc, N) && contig_aos(out, o_sb, o_sn, o_sc, N) &&
+      (!w || (contig_aos(prev, p_sb, p_sn, p_sc, N) && (((uintptr_t)w) & 15u) == 0)) &&
+      (((uintptr_t)rigid_out) & 15u) == 0) {
+    int vchunks = (N / 4 + 256 * 2 - 1) / (256 * 2);
+    if (vchunks > 4096) vchunks = 4096;
+    warp_fwd_vec_kernel<<<dim3((unsigned)vchunks, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
+        phi, src, w, prev, N, out, g_out, rigid_out);
+    RMA_LAUNCH_CHECK();
+    return RMA_OK;
+  }
   int chunks = (N + 256 * 2 - 1) / (256 * 2);
   if (chunks > 4096) chunks = 4096;
   dim3 grid((unsigned)chunks, (unsigned)B);
@@ -408,11 +556,20 @@ int rma_warp_backward(const float* phi, const float* src, int64_t s_sb, int64_t 
   if (w && !prev) return RMA_E_BADARG;
   cudaStream_t stream = (cudaStream_t)stream_;
   RMA_CUDA_TRY(cudaMemsetAsync(scratch, 0, (size_t)B * 12 * sizeof(float), stream));
-  int chunks = (N + 256 * 4 - 1) / (256 * 4);
-  if (chunks > 1024) chunks = 1024;
-  dim3 grid((unsigned)chunks, (unsigned)B);
-  warp_bwd_kernel<<<grid, 256, 0, stream>>>(phi, src, s_sb, s_sn, s_sc, w, prev, p_sb, p_sn, p_sc, go, g_sb, g_sn,
-                                            g_sc, N, grad_w, grad_src, gs_sb, gs_sn, gs_sc, scratch);
+  if (N % 4 == 0 && contig_aos(src, s_sb, s_sn, s_sc, N) && contig_aos(go, g_sb, g_sn, g_sc, N) &&
+      contig_aos(grad_src, gs_sb, gs_sn, gs_sc, N) &&
+      (!w || (contig_aos(prev, p_sb, p_sn, p_sc, N) && (((uintptr_t)w) & 15u) == 0 && (((uintptr_t)grad_w) & 15u) == 0))) {
+    int vchunks = (N / 4 + 256 * 2 - 1) / (256 * 2);
+    if (vchunks > 2048) vchunks = 2048;
+    warp_bwd_vec_kernel<<<dim3((unsigned)vchunks, (unsigned)B), 256, 0, stream>>>(phi, src, w, prev, go, N, grad_w,
+                                                                              grad_src, scratch);
+  } else {
+    int chunks = (N + 256 * 4 - 1) / (256 * 4);
+    if (chunks > 1024) chunks = 1024;
+    dim3 grid((unsigned)chunks, (unsigned)B);
+    warp_bwd_kernel<<<grid, 256, 0, stream>>>(phi, src, s_sb, s_sn, s_sc, w, prev, p_sb, p_sn, p_sc, go, g_sb, g_sn,
+                                              g_sc, N, grad_w, grad_src, gs_sb, gs_sn, gs_sc, scratch);
+  }
   RMA_LAUNCH_CHECK();
   warp_bwd_phi_kernel<<<(B + 127) / 128, 128, 0, stream>>>(phi, scratch, B, grad_phi);
   RMA_LAUNCH_CHECK();
