@@ -287,19 +287,36 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
             for (int h2 = 0; h2 < 2; ++h2) {
               const float4 A = h2 ? q2 : q0, Bq = h2 ? q3 : q1;
               const u64 Q0 = pack2(A.x, A.y), Q1 = pack2(A.z, A.w), Q2 = pack2(Bq.x, Bq.y), WW = pack2(Bq.z, Bq.w);
+              // chain step by step over the 16 rows (ptxas re-schedules this freely; forcing the order with
+              // basic-block fences so that the 64-bit column operand is reused 16 times in a row was measured: no gain)
+              u64 acc[16];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                float za, zb;
+                unpack2(pz[k], za, zb);
+                acc[2 * k] = fma2(Q2, pack2(za, za), WW); acc[2 * k + 1] = fma2(Q2, pack2(zb, zb), WW);
+              }
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                float ya, yb;
+                unpack2(py[k], ya, yb);
+                acc[2 * k] = fma2(Q1, pack2(ya, ya), acc[2 * k]); acc[2 * k + 1] = fma2(Q1, pack2(yb, yb), acc[2 * k + 1]);
+              }
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                float xa, xb;
+                unpack2(px[k], xa, xb);
+                acc[2 * k] = fma2(Q0, pack2(xa, xa), acc[2 * k]); acc[2 * k + 1] = fma2(Q0, pack2(xb, xb), acc[2 * k + 1]);
+              }
               float cl = inf, ch = inf;
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                float xa, xb, ya, yb, za, zb, ua, ub;
-                unpack2(px[k], xa, xb); unpack2(py[k], ya, yb); unpack2(pz[k], za, zb); unpack2(pu[k], ua, ub);
-                u64 fa = fma2(Q2, pack2(za, za), WW), fb = fma2(Q2, pack2(zb, zb), WW);
-                fa = fma2(Q1, pack2(ya, ya), fa); fb = fma2(Q1, pack2(yb, yb), fb);
-                fa = fma2(Q0, pack2(xa, xa), fa); fb = fma2(Q0, pack2(xb, xb), fb);
-                float al, ah, bl, bh;
-                unpack2(fa, al, ah); unpack2(fb, bl, bh);
+                float ua, ub, al, ah, bl, bh;
+                unpack2(pu[k], ua, ub);
+                unpack2(acc[2 * k], al, ah); unpack2(acc[2 * k + 1], bl, bh);
                 tm[2 * k] = min3(tm[2 * k], al, ah);
                 tm[2 * k + 1] = min3(tm[2 * k + 1], bl, bh);
-                unpack2(add2(fa, pack2(ua, ua)), al, ah); unpack2(add2(fb, pack2(ub, ub)), bl, bh);
+                unpack2(add2(acc[2 * k], pack2(ua, ua)), al, ah); unpack2(add2(acc[2 * k + 1], pack2(ub, ub)), bl, bh);
                 cl = min3(cl, al, bl);
                 ch = min3(ch, ah, bh);
               }
