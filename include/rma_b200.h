@@ -84,6 +84,16 @@ int rma_chamfer_cd_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc
                            int B, int N, int M, float* loss, float* dist1, float* dist2, int32_t* idx1,
                            int32_t* idx2, float* own_x, float* scat_x, float* own_y, float* scat_y,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* The same with per-batch-element weights (device array [B] or NULL = 1) and an explicit coefficient:
+ *   *loss = coef * sum_b batch_weight[b] * (sum dist1[b] + sum dist2[b]),   gradients scaled accordingly.
+ * This is the stage loop of Loss.forward (loss.py:260-267) as ONE call: stack the T stage outputs as a [T*B,N,3] batch,
+ * repeat the target, batch_weight[t*B + b] = weight_cd * gamma^(T-t-1), coef = 0.5 / B. */
+int rma_chamfer_cd_forward_weighted(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                                    const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
+                                    int B, int N, int M, const float* batch_weight, float coef, float* loss,
+                                    float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* own_x,
+                                    float* scat_x, float* own_y, float* scat_y, void* workspace,
+                                    size_t workspace_bytes, void* stream);
 /* out_x[p,c] = *scalar_dev * (own_x[p,c] + scat_x[p,c]) for p < nx points (out_x [nx,3]); same for y.  The upstream
  * scalar is read on the device (no host sync).  Either half may be empty (n = 0). */
 int rma_chamfer_cd_backward(const float* own_x, const float* scat_x, int64_t nx, const float* own_y,

@@ -25,6 +25,8 @@ SIGNATURES = {
     "rma_chamfer_search_config": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
     "rma_chamfer_cd_forward": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, c_int, c_int, c_int,
                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "rma_chamfer_cd_forward_weighted": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, c_int, c_int, c_int,
+                                                _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "rma_chamfer_cd_backward": (c_int, [_P, _P, _I64, _P, _P, _I64, _P, _P, _P, _P]),
     "rma_chamfer_backward": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, c_int, c_int, c_int,
                                      _P, _P, _P, _P, _P, _P, _P]),

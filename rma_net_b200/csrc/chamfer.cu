@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const long long wi = (long long)blockIdx.x * kFinWarps + warp;
   const float coef_grad = 2.f * f.coef_loss;
-  float myd = 0.f;
+  float myd = 0.f, wb = 1.f;
   bool valid = false;
   pdl_wait();
   pdl_launch_dependents();
@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
     __syncwarp();
     const unsigned myhit = hits[warp][lane];
     const int j = jt + (myhit ? __ffs(myhit) - 1 : 0);
+    wb = (valid && f.batch_weight) ? f.batch_weight[b] : 1.f;
     if (valid) {
       if (f.dist1) f.dist1[t] = myd;
       if (f.idx1) f.idx1[t] = j;
@@ -378,7 +379,8 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
       float vx = 0.f, vy = 0.f, vz = 0.f;
       if (valid) {
         const float4 c = w.colpack[(size_t)b * g.Mp + j];
-        vx = coef_grad * (x + c.x); vy = coef_grad * (y + c.y); vz = coef_grad * (z + c.z);
+        const float cg = coef_grad * wb;
+        vx = cg * (x + c.x); vy = cg * (y + c.y); vz = cg * (z + c.z);
         if (f.own_x) { float* o = f.own_x + t * 3; o[0] = vx; o[1] = vy; o[2] = vz; }
       }
       if (f.scat_y) scatter_add4(f.scat_y + ((long long)b * g.M + j), (long long)b * g.M + j, valid, -vx, -vy, -vz);
@@ -420,6 +422,7 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
     const unsigned myhit = hits[warp][lane];
     const int myi = myhit ? __ffs(myhit) - 1 : 0;
     const int i = grp * kRowsPerThread + myi;
+    wb = (valid && f.batch_weight) ? f.batch_weight[b] : 1.f;
     if (valid) {
       if (f.dist2) f.dist2[t] = myd;
       if (f.idx2) f.idx2[t] = i;
@@ -430,7 +433,8 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
         const float* rp = w.rowpack + fbase + ((myi >> 2) * 32) * 4 + (myi & 3);
         const float x = rp[0], y = rp[4 * 32 * 4], z = rp[8 * 32 * 4];
         // d/dy_j |y_j - x_i|^2 = 2 (y_j - x_i) = -2 (x_i + (-y_j))
-        vx = -coef_grad * (x + nx); vy = -coef_grad * (y + ny); vz = -coef_grad * (z + nz);
+        const float cg = coef_grad * wb;
+        vx = -cg * (x + nx); vy = -cg * (y + ny); vz = -cg * (z + nz);
         if (f.own_y) { float* o = f.own_y + t * 3; o[0] = vx; o[1] = vy; o[2] = vz; }
       }
       if (f.scat_x) scatter_add4(f.scat_x + ((long long)b * g.N + i), (long long)b * g.N + i, valid, -vx, -vy, -vz);
@@ -438,7 +442,7 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
   }
 
   if (f.loss) {
-    double sd = valid ? (double)myd : 0.0;
+    double sd = valid ? (double)myd * (double)wb : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
     if (lane == 0) lsum[warp] = sd;
@@ -752,7 +756,7 @@ static int launch_finalize(int B, int N, int M, const FinalizeArgs& f, void* wor
 int rma_chamfer_finalize(int B, int N, int M, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
                          void* workspace, size_t workspace_bytes, void* stream_) {
   if (!dist1 || !dist2) return RMA_E_BADARG;
-  FinalizeArgs f = {dist1, dist2, idx1, idx2, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
+  FinalizeArgs f = {dist1, dist2, idx1, idx2, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr};
   return launch_finalize(B, N, M, f, workspace, workspace_bytes, stream_);
 }
 
@@ -781,11 +785,12 @@ int rma_chamfer_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
   return rma_chamfer_finalize(B, N, M, dist1, dist2, idx1, idx2, workspace, workspace_bytes, stream);
 }
 
-int rma_chamfer_cd_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
-                           const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
-                           int B, int N, int M, float* loss, float* dist1, float* dist2, int32_t* idx1,
-                           int32_t* idx2, float* own_x, float* scat_x, float* own_y, float* scat_y,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+int rma_chamfer_cd_forward_weighted(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                                    const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
+                                    int B, int N, int M, const float* batch_weight, float coef, float* loss,
+                                    float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* own_x,
+                                    float* scat_x, float* own_y, float* scat_y, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
   if (!loss) return RMA_E_BADARG;
   if ((own_x == nullptr) != (scat_x == nullptr) || (own_y == nullptr) != (scat_y == nullptr)) return RMA_E_BADARG;
   if ((((uintptr_t)scat_x) | ((uintptr_t)scat_y)) & 15u) return RMA_E_BADARG;
@@ -793,9 +798,20 @@ int rma_chamfer_cd_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc
                           (float4*)scat_x, (float4*)scat_y, stream))
     return e;
   if (int e = rma_chamfer_search(B, N, M, workspace, workspace_bytes, stream)) return e;
-  FinalizeArgs f = {dist1, dist2, idx1, idx2, loss, own_x, own_y, (float4*)scat_x, (float4*)scat_y,
-                    0.5f / (float)B};
+  FinalizeArgs f = {dist1, dist2, idx1, idx2, loss, own_x, own_y, (float4*)scat_x, (float4*)scat_y, coef,
+                    batch_weight};
   return launch_finalize(B, N, M, f, workspace, workspace_bytes, stream);
+}
+
+int rma_chamfer_cd_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
+                           const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
+                           int B, int N, int M, float* loss, float* dist1, float* dist2, int32_t* idx1,
+                           int32_t* idx2, float* own_x, float* scat_x, float* own_y, float* scat_y,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0) return RMA_E_BADARG;
+  return rma_chamfer_cd_forward_weighted(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, nullptr, 0.5f / (float)B, loss,
+                                         dist1, dist2, idx1, idx2, own_x, scat_x, own_y, scat_y, workspace,
+                                         workspace_bytes, stream);
 }
 
 // out[p, c] = scalar * (own[p, c] + scat[p].c): combines the two gradient halves of the fused forward and applies

@@ -59,6 +59,7 @@ struct FinalizeArgs {
   float* own_x; float* own_y;      // null or [B,N,3] / [B,M,3]
   float4* scat_x; float4* scat_y;  // null or [B,N] / [B,M]
   float coef_loss;   // 0.5 / B for loss_on_cd
+  const float* batch_weight;   // null, or [B]: batch element b counts with weight batch_weight[b] (stage weights)
 };
 
 constexpr int kFinWarps = 8;

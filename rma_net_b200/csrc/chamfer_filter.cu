@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
   const float coef_grad = 2.f * f.coef_loss;
   const unsigned full = 0xffffffffu;
   const float inf = __int_as_float(0x7f800000);
-  float myd = 0.f;
+  float myd = 0.f, wb = 1.f;
   bool valid = false;
   pdl_wait();
   pdl_launch_dependents();   // the backward combine may queue behind us (it waits for our completion itself)
@@ -548,6 +548,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
     }
 
     myd = __uint_as_float(best_d);
+    wb = (valid && f.batch_weight) ? f.batch_weight[b] : 1.f;
     const int j = (int)best_j;
     if (valid) {
       if (f.dist1) f.dist1[t] = myd;
@@ -557,9 +558,10 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       float vx = 0.f, vy = 0.f, vz = 0.f;
       if (valid) {
         const float4 q = w.colpack[(size_t)b * g.Mp + j];
-        vx = coef_grad * __fmaf_rn(0.5f, q.x, rp.x);
-        vy = coef_grad * __fmaf_rn(0.5f, q.y, rp.y);
-        vz = coef_grad * __fmaf_rn(0.5f, q.z, rp.z);
+        const float cg = coef_grad * wb;
+        vx = cg * __fmaf_rn(0.5f, q.x, rp.x);
+        vy = cg * __fmaf_rn(0.5f, q.y, rp.y);
+        vz = cg * __fmaf_rn(0.5f, q.z, rp.z);
         if (f.own_x) { float* o = f.own_x + t * 3; o[0] = vx; o[1] = vy; o[2] = vz; }
       }
       if (f.scat_y) scatter_add4(f.scat_y + ((long long)b * g.M + j), (long long)b * g.M + j, valid, -vx, -vy, -vz);
@@ -661,6 +663,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
     }
 
     myd = __uint_as_float(best_d);
+    wb = (valid && f.batch_weight) ? f.batch_weight[b] : 1.f;
     const int i = (int)best_i;
     if (valid) {
       if (f.dist2) f.dist2[t] = myd;
@@ -671,9 +674,10 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       if (valid) {
         const float4 p = w.rowpack[(size_t)b * g.Npad + i];
         // d/dy_j |y_j - x_i|^2 = 2 (y_j - x_i) = -2 (x_i - y_j)
-        vx = -coef_grad * __fmaf_rn(0.5f, cq.x, p.x);
-        vy = -coef_grad * __fmaf_rn(0.5f, cq.y, p.y);
-        vz = -coef_grad * __fmaf_rn(0.5f, cq.z, p.z);
+        const float cg = coef_grad * wb;
+        vx = -cg * __fmaf_rn(0.5f, cq.x, p.x);
+        vy = -cg * __fmaf_rn(0.5f, cq.y, p.y);
+        vz = -cg * __fmaf_rn(0.5f, cq.z, p.z);
         if (f.own_y) { float* o = f.own_y + t * 3; o[0] = vx; o[1] = vy; o[2] = vz; }
       }
       if (f.scat_x) scatter_add4(f.scat_x + ((long long)b * g.N + i), (long long)b * g.N + i, valid, -vx, -vy, -vz);
@@ -681,7 +685,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
   }
 
   if (f.loss) {
-    double sd = valid ? (double)myd : 0.0;
+    double sd = valid ? (double)myd * (double)wb : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
     if (lane == 0) lsum[warp] = sd;

@@ -100,9 +100,11 @@ def chamfer_backward(points_x, points_y, idx1, idx2, g1, g2, need_x: bool = True
     return gx, gy
 
 
-def chamfer_cd_forward(points_x: torch.Tensor, points_y: torch.Tensor, need_x: bool, need_y: bool):
+def chamfer_cd_forward(points_x: torch.Tensor, points_y: torch.Tensor, need_x: bool, need_y: bool,
+                       batch_weight: Optional[torch.Tensor] = None, coef: Optional[float] = None):
     """Fused loss_on_cd: returns (loss 0-dim, gx_parts, gy_parts); g*_parts = (own [.,.,3], scat [.,.,4]) or None,
-    with d loss/d cloud = own + scat[..., :3] (combined and scaled by chamfer_cd_backward)."""
+    with d loss/d cloud = own + scat[..., :3] (combined and scaled by chamfer_cd_backward).
+    loss = coef * sum_b batch_weight[b] * (sum dist1[b] + sum dist2[b]); defaults: weights 1, coef 0.5 / B."""
     _check_points("points_x", points_x)
     _check_points("points_y", points_y)
     _same_device(points_x, points_y)
@@ -123,12 +125,17 @@ def chamfer_cd_forward(points_x: torch.Tensor, points_y: torch.Tensor, need_x: b
         gx = (torch.empty((B, N, 3), **f32), torch.empty((B, N, 4), **f32)) if need_x else None
         gy = (torch.empty((B, M, 3), **f32), torch.empty((B, M, 4), **f32)) if need_y else None
         xs, ys = points_x.stride(), points_y.stride()
-        rc = lib.rma_chamfer_cd_forward(_ptr(points_x), xs[0], xs[1], xs[2], _ptr(points_y), ys[0], ys[1], ys[2],
-                                        B, N, M, _ptr(loss), None, None, None, None,
+        if batch_weight is not None:
+            if batch_weight.numel() != B or not batch_weight.is_cuda:
+                raise RuntimeError(f"batch_weight must be a CUDA tensor with {B} elements")
+            batch_weight = batch_weight.to(torch.float32).contiguous()
+        rc = lib.rma_chamfer_cd_forward_weighted(_ptr(points_x), xs[0], xs[1], xs[2], _ptr(points_y), ys[0], ys[1], ys[2],
+                                        B, N, M, _ptr(batch_weight), float(0.5 / B if coef is None else coef),
+                                        _ptr(loss), None, None, None, None,
                                         _ptr(gx[0] if gx else None), _ptr(gx[1] if gx else None),
                                         _ptr(gy[0] if gy else None), _ptr(gy[1] if gy else None),
                                         _ptr(ws), wsb, _stream())
-        _lib.check(rc, "rma_chamfer_cd_forward")
+        _lib.check(rc, "rma_chamfer_cd_forward_weighted")
     return loss, gx, gy
 
 

@@ -31,9 +31,9 @@ class ChamferCDFunction(torch.autograd.Function):
     w.r.t. both clouds come out of the forward's three launches; backward is one combine-and-scale launch."""
 
     @staticmethod
-    def forward(ctx, deformation_p, p1):
+    def forward(ctx, deformation_p, p1, batch_weight=None, coef=None):
         need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        loss, gx, gy = ext.chamfer_cd_forward(deformation_p, p1, need_x, need_y)
+        loss, gx, gy = ext.chamfer_cd_forward(deformation_p, p1, need_x, need_y, batch_weight, coef)
         ctx.has = (gx is not None, gy is not None)
         ctx.save_for_backward(*[t for pair in (gx, gy) if pair is not None for t in pair])
         return loss
@@ -44,8 +44,8 @@ class ChamferCDFunction(torch.autograd.Function):
         gx = (saved.pop(0), saved.pop(0)) if ctx.has[0] else None
         gy = (saved.pop(0), saved.pop(0)) if ctx.has[1] else None
         if gx is None and gy is None:
-            return None, None
-        return ext.chamfer_cd_backward(gx, gy, grad_loss)
+            return None, None, None, None
+        return ext.chamfer_cd_backward(gx, gy, grad_loss) + (None, None)
 
 
 class Chamfer(torch.nn.Module):

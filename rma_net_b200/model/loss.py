@@ -4,6 +4,7 @@
     chamfer_dist         loss.py:60-70     -> (dist1 [B,M], dist2 [B,N])
     loss_on_cd           loss.py:200-205   (a method of Loss in the reference; a function here)
     loss_cd_stages       loss.py:260-267   (the gamma-weighted stage loop of Loss.forward)
+    loss_cd_stages_fused the same loop as ONE batched call
     get_neighbor_index   loss.py:99-110    ARAP neighbour graph: the n nearest OTHER vertices -> [B,V,n] (int64)
     indexing_neighbor    loss.py:113-120   gather by that index (torch)
 
@@ -56,6 +57,35 @@ def loss_cd_stages(deformation_points_list, target_points, gamma=0.8, weight_cd=
         loss_cd = loss_cd + gamma ** (iter_time - i - 1) * loss_on_cd(
             deformation_points_list[i].transpose(1, 2), target_points)
     return loss_cd * weight_cd
+
+
+def loss_cd_stages_fused(deformation_points_list, target_points, gamma=0.8, weight_cd=1.0):
+    """The same value and gradients as loss_cd_stages, with all T stages in ONE chamfer call: the stage outputs are
+    stacked into a [T*B,N,3] batch, the target is repeated, and the stage weights gamma^(T-i-1) * weight_cd enter the
+    fused kernel as per-batch-element weights (rma_chamfer_cd_forward_weighted).  4 launches instead of 4*T."""
+    iter_time = len(deformation_points_list)
+    B = target_points.shape[0]
+    x_all = torch.stack([d.transpose(1, 2) for d in deformation_points_list], 0)
+    x_all = x_all.reshape(iter_time * B, x_all.shape[2], 3)
+    y_all = target_points.unsqueeze(0).expand(iter_time, -1, -1, -1).reshape(iter_time * B, target_points.shape[1], 3)
+    return ChamferCDFunction.apply(x_all, y_all, _stage_weights(iter_time, B, float(gamma), float(weight_cd),
+                                                              target_points.device), 0.5 / B)
+
+
+_STAGE_WEIGHTS = {}
+
+
+def _stage_weights(iter_time, B, gamma, weight_cd, device):
+    """[T*B] device vector weight_cd * gamma^(T-i-1), cached: building it costs a synchronous H2D copy."""
+    key = (iter_time, B, gamma, weight_cd, str(device))
+    w = _STAGE_WEIGHTS.get(key)
+    if w is None:
+        w = torch.tensor([weight_cd * gamma ** (iter_time - i - 1) for i in range(iter_time)],
+                         dtype=torch.float32).repeat_interleave(B).to(device)
+        if len(_STAGE_WEIGHTS) > 64:
+            _STAGE_WEIGHTS.clear()
+        _STAGE_WEIGHTS[key] = w
+    return w
 
 
 def get_neighbor_index(vertices, neighbor_num):

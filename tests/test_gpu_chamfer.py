@@ -391,3 +391,25 @@ def test_paths_agree_and_auto_dispatch(cuda):
     for o in outs[1:]:
         for a, b_ in zip(outs[0], o):
             assert torch.equal(a, b_)
+
+
+def test_stage_loop_fused_equals_loop(cuda, chamfer_path):
+    """loss.py:260-267 as one batched call (loss_cd_stages_fused) == the per-stage loop, value and gradients."""
+    from rma_net_b200.model.loss import loss_cd_stages, loss_cd_stages_fused
+    g = torch.Generator().manual_seed(31)
+    T, B, N, M = 5, 3, 700, 650
+    stages = [(torch.rand(B, 3, N, generator=g) * 2 - 1).to(cuda).requires_grad_(True) for _ in range(T)]
+    target = (torch.rand(B, M, 3, generator=g) * 2 - 1).to(cuda).requires_grad_(True)
+    ref = loss_cd_stages(stages, target, gamma=0.8, weight_cd=1.3)
+    ref.backward()
+    gs = [s.grad.clone() for s in stages]
+    gt = target.grad.clone()
+    for s in stages:
+        s.grad = None
+    target.grad = None
+    got = loss_cd_stages_fused(stages, target, gamma=0.8, weight_cd=1.3)
+    got.backward()
+    assert abs(got.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    for s, r in zip(stages, gs):
+        assert (s.grad - r).abs().max() <= 2e-6 * r.abs().max()
+    assert (target.grad - gt).abs().max() <= 4e-6 * gt.abs().max()
