@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(256) chamfer_fprep_kernel(
   const long long nrow = (long long)g.B * g.Npad;
   const long long ncol = (long long)g.B * g.Mp;
   pdl_wait();
+  pdl_launch_dependents();   // let the search grid's launch overlap this kernel; its CTAs wait for our completion
   if (blockIdx.x == 0 && threadIdx.x < 4) w.stats[threadIdx.x] = 0u;
   if (zero_loss && blockIdx.x == 0 && threadIdx.x == 0) *zero_loss = 0.f;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nrow + ncol;
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
   long long unit = (long long)blockIdx.x * a.U;
   const long long unit_end = min(unit + a.U, a.units);
   pdl_wait();
+  pdl_launch_dependents();   // the resolve grid may be launched (it blocks in its own pdl_wait until we are done)
 
   while (unit < unit_end) {
     // ---- one segment: a run of `ntile` 64-column tiles of one CTA row block ----
@@ -493,13 +495,17 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
     const bool fast = valid && M2 > thr;
     unsigned best_d = 0xffffffffu, best_j = 0;
 
-    // Fast path (one candidate tile): 8 lanes per row, 8 columns per lane, 4 rows per round.
+    // Fast path (one candidate tile): 8 lanes per row, 8 columns per lane, 4 rows per round.  Inside the tile the
+    // same guard applies per COLUMN: every exact minimiser has f_j <= thr, so each column is first re-filtered with
+    // the search's own 3-FFMA chain (bit-identical f; padded columns carry |y|^2 = 1e30 and never pass) and only the
+    // survivors - typically one per row - are evaluated in the exact difference form.
 #pragma unroll 1
     for (int round = 0; round < 8; ++round) {
       const int src = round * 4 + grp;
       const int sb = __shfl_sync(full, b, src), st = __shfl_sync(full, T1, src);
       const bool sf = __shfl_sync(full, (int)fast, src) != 0;
       const float x = __shfl_sync(full, rp.x, src), y = __shfl_sync(full, rp.y, src), z = __shfl_sync(full, rp.z, src);
+      const float sthr = __shfl_sync(full, thr, src);
       unsigned d = 0xffffffffu, dj = 0xffffffffu;
       if (sf) {
         const int j0 = st * kFRowTile + sub;
@@ -509,8 +515,11 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
         for (int c = 0; c < 8; ++c) q[c] = cq[8 * c];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const unsigned dc = j0 + 8 * c < g.M ? __float_as_uint(sqdist_q(x, y, z, q[c])) : 0xffffffffu;
-          if (dc < d) { d = dc; dj = (unsigned)(j0 + 8 * c); }     // ascending columns: strict '<' keeps the first
+          const float fj = __fmaf_rn(x, q[c].x, __fmaf_rn(y, q[c].y, __fmaf_rn(z, q[c].z, q[c].w)));
+          if (fj <= sthr) {
+            const unsigned dc = __float_as_uint(sqdist_q(x, y, z, q[c]));
+            if (dc < d) { d = dc; dj = (unsigned)(j0 + 8 * c); }   // ascending columns: strict '<' keeps the first
+          }
         }
       }
       group8_min(d, dj);
