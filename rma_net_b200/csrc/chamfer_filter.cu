@@ -442,13 +442,36 @@ __device__ __forceinline__ void group8_min(unsigned& d, unsigned& idx) {
   }
 }
 
+// Result of one fast-path round for owner lane (round*4 + k): the (distance, index) minimum of 8-lane group k.
+// Usually exactly one lane of a group holds a survivor, then a ballot finds it and two SHFL fetch it; otherwise the
+// 3-step butterfly runs.  Warp-uniform control flow.
+__device__ __forceinline__ void round_result(unsigned d, unsigned idx, unsigned& rd, unsigned& ri) {
+  const unsigned full = 0xffffffffu, lane = lane_id();
+  const unsigned hit = __ballot_sync(full, d != 0xffffffffu);
+  const unsigned gb = (hit >> (lane & 24u)) & 0xffu;                 // my own group's survivors
+  if (__all_sync(full, (gb & (gb - 1u)) == 0u)) {                    // every group has at most one
+    const unsigned k = lane & 3u, gk = (hit >> (k * 8u)) & 0xffu;
+    const int src = (int)(k * 8u) + (gk ? __ffs(gk) - 1 : 0);
+    rd = __shfl_sync(full, d, src); ri = __shfl_sync(full, idx, src);
+  } else {
+    group8_min(d, idx);
+    rd = __shfl_sync(full, d, (lane & 3) * 8); ri = __shfl_sync(full, idx, (lane & 3) * 8);
+  }
+}
+
 __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGeometry g, FWorkspace w, FinalizeArgs f) {
   __shared__ double lsum[kFinWarps];
-  const long long nrow = (long long)g.B * g.N, ncol = (long long)g.B * g.M;
-  const long long row_warps = (nrow + 31) / 32;
+  // per-warp staging of the 32 items' broadcast data: a round reads its 4 items with two LDS.128 (one address per
+  // 8-lane group, conflict-free) instead of seven SHFL
+  __shared__ float4 sA[kFinWarps][32];
+  __shared__ int4 sB[kFinWarps][32];
+  // 32-bit index math throughout: B*Npad, B*Mp and the unit count are < 2^31 (f_sizes_ok); a 64-bit division
+  // costs ~80 emulated instructions per lane and there were five of them
+  const unsigned nrow = (unsigned)g.B * (unsigned)g.N, ncol = (unsigned)g.B * (unsigned)g.M;
+  const unsigned row_warps = (nrow + 31u) / 32u;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const int grp = lane >> 3, sub = lane & 7;
-  const long long wi = (long long)blockIdx.x * kFinWarps + warp;
+  const unsigned wi = blockIdx.x * kFinWarps + warp;
   const float coef_grad = 2.f * f.coef_loss;
   const unsigned full = 0xffffffffu;
   const float inf = __int_as_float(0x7f800000);
@@ -459,18 +482,18 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
 
   if (wi < row_warps) {
     // ---------------------------------------------------------------- rows: lane <-> row, candidates = 64-column tiles
-    const long long t = wi * 32 + lane;
+    const unsigned t = wi * 32u + lane;
     valid = t < nrow;
     int b = 0, i = 0;
     float4 rp = make_float4(0.f, 0.f, 0.f, 0.f);
     float M1 = inf, M2 = inf;
     int T1 = 0;
     if (valid) {
-      b = (int)(t / g.N); i = (int)(t % g.N);
+      b = (int)(t / (unsigned)g.N); i = (int)(t - (unsigned)b * (unsigned)g.N);
       rp = w.rowpack[(size_t)b * g.Npad + i];
       const int rbc = i / kFRowsPerCta, brb = b * g.nRBC + rbc;
-      const int kfirst = (int)(((long long)brb * g.nT) / g.U);
-      const int klast = (int)(((long long)(brb + 1) * g.nT - 1) / g.U);
+      const int kfirst = (int)(((unsigned)brb * (unsigned)g.nT) / (unsigned)g.U);
+      const int klast = (int)((((unsigned)brb + 1u) * (unsigned)g.nT - 1u) / (unsigned)g.U);
       const float* top = w.rowtop + ((size_t)brb * g.Smax * 3) * kFRowsPerCta + (i - rbc * kFRowsPerCta);
       const int nseg = klast - kfirst + 1;
       for (int s0 = 0; s0 < nseg; s0 += 4) {      // four segments' records in flight
@@ -499,17 +522,19 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
     // same guard applies per COLUMN: every exact minimiser has f_j <= thr, so each column is first re-filtered with
     // the search's own 3-FFMA chain (bit-identical f; padded columns carry |y|^2 = 1e30 and never pass) and only the
     // survivors - typically one per row - are evaluated in the exact difference form.
+    sA[warp][lane] = make_float4(rp.x, rp.y, rp.z, thr);
+    sB[warp][lane] = make_int4(b, T1, fast ? 1 : 0, 0);
+    __syncwarp();
 #pragma unroll 1
     for (int round = 0; round < 8; ++round) {
       const int src = round * 4 + grp;
-      const int sb = __shfl_sync(full, b, src), st = __shfl_sync(full, T1, src);
-      const bool sf = __shfl_sync(full, (int)fast, src) != 0;
-      const float x = __shfl_sync(full, rp.x, src), y = __shfl_sync(full, rp.y, src), z = __shfl_sync(full, rp.z, src);
-      const float sthr = __shfl_sync(full, thr, src);
+      const float4 sa = sA[warp][src];
+      const int4 sb4 = sB[warp][src];
+      const float x = sa.x, y = sa.y, z = sa.z, sthr = sa.w;
       unsigned d = 0xffffffffu, dj = 0xffffffffu;
-      if (sf) {
-        const int j0 = st * kFRowTile + sub;
-        const float4* cq = w.colpack + (size_t)sb * g.Mp + j0;
+      if (sb4.z) {
+        const int j0 = sb4.y * kFRowTile + sub;
+        const float4* cq = w.colpack + (size_t)sb4.x * g.Mp + j0;
         float4 q[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) q[c] = cq[8 * c];
@@ -522,8 +547,8 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
           }
         }
       }
-      group8_min(d, dj);
-      const unsigned rd = __shfl_sync(full, d, (lane & 3) * 8), rj = __shfl_sync(full, dj, (lane & 3) * 8);
+      unsigned rd, rj;
+      round_result(d, dj, rd, rj);
       if ((lane >> 2) == round) { best_d = rd; best_j = rj; }
     }
 
@@ -571,20 +596,20 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
         vx = cg * __fmaf_rn(0.5f, q.x, rp.x);
         vy = cg * __fmaf_rn(0.5f, q.y, rp.y);
         vz = cg * __fmaf_rn(0.5f, q.z, rp.z);
-        if (f.own_x) { float* o = f.own_x + t * 3; o[0] = vx; o[1] = vy; o[2] = vz; }
+        if (f.own_x) { float* o = f.own_x + (size_t)t * 3; o[0] = vx; o[1] = vy; o[2] = vz; }
       }
       if (f.scat_y) scatter_add4(f.scat_y + ((long long)b * g.M + j), (long long)b * g.M + j, valid, -vx, -vy, -vz);
     }
   } else {
     // ------------------------------------------------------------- columns: lane <-> column, candidates = 16-row groups
-    const long long t = (wi - row_warps) * 32 + lane;
+    const unsigned t = (wi - row_warps) * 32u + lane;
     valid = t < ncol;
     int b = 0, j = 0;
     float4 cq = make_float4(0.f, 0.f, 0.f, 0.f);
     float M1 = inf, M2 = inf;
     int R1 = 0;
     if (valid) {
-      b = (int)(t / g.M); j = (int)(t % g.M);
+      b = (int)(t / (unsigned)g.M); j = (int)(t - (unsigned)b * (unsigned)g.M);
       cq = w.colpack[(size_t)b * g.Mp + j];
       const float* rec = w.colrec + (size_t)b * g.nRB * 3 * g.Mp + j;
       for (int r0 = 0; r0 < g.nRB; r0 += 4) {     // four row blocks' records in flight
@@ -609,17 +634,18 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
     unsigned best_d = 0xffffffffu, best_i = 0;
 
     // Fast path (one candidate group of 16 rows): 8 lanes per column, 2 rows per lane, 4 columns per round.
+    sA[warp][lane] = make_float4(cq.x, cq.y, cq.z, 0.f);
+    sB[warp][lane] = make_int4(b, G1, fast ? 1 : 0, 0);
+    __syncwarp();
 #pragma unroll 2
     for (int round = 0; round < 8; ++round) {
       const int src = round * 4 + grp;
-      const int sb = __shfl_sync(full, b, src), sg = __shfl_sync(full, G1, src);
-      const bool sf = __shfl_sync(full, (int)fast, src) != 0;
-      const float4 q = make_float4(__shfl_sync(full, cq.x, src), __shfl_sync(full, cq.y, src),
-                                   __shfl_sync(full, cq.z, src), 0.f);
+      const float4 q = sA[warp][src];
+      const int4 sb4 = sB[warp][src];
       unsigned d = 0xffffffffu, di = 0xffffffffu;
-      if (sf) {
-        const int r0 = sg + sub, r1 = r0 + 8;
-        const float4 pa = w.rowpack[(size_t)sb * g.Npad + r0], pb = w.rowpack[(size_t)sb * g.Npad + r1];
+      if (sb4.z) {
+        const int r0 = sb4.y + sub, r1 = r0 + 8;
+        const float4 pa = w.rowpack[(size_t)sb4.x * g.Npad + r0], pb = w.rowpack[(size_t)sb4.x * g.Npad + r1];
         const unsigned d0 = r0 < g.N ? __float_as_uint(sqdist_q(pa.x, pa.y, pa.z, q)) : 0xffffffffu;
         const unsigned d1 = r1 < g.N ? __float_as_uint(sqdist_q(pb.x, pb.y, pb.z, q)) : 0xffffffffu;
         d = d0; di = (unsigned)r0;
@@ -687,7 +713,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
         vx = -cg * __fmaf_rn(0.5f, cq.x, p.x);
         vy = -cg * __fmaf_rn(0.5f, cq.y, p.y);
         vz = -cg * __fmaf_rn(0.5f, cq.z, p.z);
-        if (f.own_y) { float* o = f.own_y + t * 3; o[0] = vx; o[1] = vy; o[2] = vz; }
+        if (f.own_y) { float* o = f.own_y + (size_t)t * 3; o[0] = vx; o[1] = vy; o[2] = vz; }
       }
       if (f.scat_x) scatter_add4(f.scat_x + ((long long)b * g.N + i), (long long)b * g.N + i, valid, -vx, -vy, -vz);
     }
@@ -720,6 +746,7 @@ bool f_sizes_ok(int B, int N, int M) {
   const FGeometry g = f_make_geometry(B, N, M, 296, 1);
   if ((long long)B * g.Npad >= (1LL << 31) || (long long)B * g.Mp >= (1LL << 31)) return false;
   if ((long long)B * g.nRBC >= (1LL << 24)) return false;
+  if ((long long)B * g.nRBC * g.nT >= (1LL << 31)) return false;   // unit indices are 32-bit in the resolve
   return true;
 }
 
