@@ -413,3 +413,56 @@ def test_stage_loop_fused_equals_loop(cuda, chamfer_path):
     for s, r in zip(stages, gs):
         assert (s.grad - r).abs().max() <= 2e-6 * r.abs().max()
     assert (target.grad - gt).abs().max() <= 4e-6 * gt.abs().max()
+
+
+def test_filter_path_fuzz_against_exact_path(cuda):
+    """Randomised stress of the filter + exact-resolve search: 60 seeded configurations across coordinate scales
+    (1e-6 .. 1e6), offsets of up to 1000 cloud diameters, anisotropy, clusters, lattices (many exactly equal
+    distances), duplicated points and ragged sizes must reproduce the exact difference-form search bit for bit
+    (distances AND indices; the exact path itself is pinned to the fp32 C oracle by the tests above)."""
+    from rma_net_b200 import _lib
+    from rma_net_b200.model.loss import chamfer_dist_with_idx
+    lib = _lib.load()
+    rng = np.random.default_rng(20260101)
+    kinds = ["uniform", "normal", "offset", "aniso", "clusters", "lattice", "dups", "surface"]
+    try:
+        for trial in range(60):
+            kind = kinds[trial % len(kinds)]
+            B = int(rng.integers(1, 4))
+            N = int(rng.integers(1, 2600))
+            M = int(rng.integers(1, 2600))
+            scale = float(10.0 ** rng.uniform(-6, 6))
+
+            def cloud(n):
+                if kind == "uniform":
+                    p = rng.uniform(-1, 1, (B, n, 3))
+                elif kind == "normal":
+                    p = rng.normal(size=(B, n, 3)) * 0.3
+                elif kind == "offset":
+                    p = rng.uniform(-1, 1, (B, n, 3)) + rng.uniform(-1000, 1000, (B, 1, 3))
+                elif kind == "aniso":
+                    p = rng.normal(size=(B, n, 3)) * np.array([1.0, 1e-3, 30.0])
+                elif kind == "clusters":
+                    c = rng.uniform(-5, 5, (B, 6, 3))
+                    p = c[:, rng.integers(0, 6, n)] + rng.normal(size=(B, n, 3)) * 1e-4
+                elif kind == "lattice":
+                    p = rng.integers(-6, 7, (B, n, 3)).astype(np.float64) * 0.25
+                elif kind == "dups":
+                    base = rng.uniform(-1, 1, (B, max(1, n // 7), 3))
+                    p = base[:, rng.integers(0, base.shape[1], n)]
+                else:                                            # points on a sphere: 2-D manifold, near-equal norms
+                    v = rng.normal(size=(B, n, 3))
+                    p = v / np.linalg.norm(v, axis=-1, keepdims=True)
+                return (p * scale).astype(np.float32)
+            x, y = cloud(N), cloud(M)
+            if kind == "offset":                                 # both clouds around the SAME far-away centre
+                y = (y - y.mean(1, keepdims=True) + x.mean(1, keepdims=True)).astype(np.float32)
+            xt, yt = torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda)
+            outs = []
+            for path in (2, 1):
+                lib.rma_exp_set_chamfer_path(path, 0)
+                outs.append([t.cpu() for t in chamfer_dist_with_idx(xt, yt)])
+            for a, b_ in zip(*outs):
+                assert torch.equal(a, b_), (trial, kind, B, N, M, scale)
+    finally:
+        lib.rma_exp_set_chamfer_path(0, 0)
