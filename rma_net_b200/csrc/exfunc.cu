@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256) render_raster_kernel(const float* __restr
     const long long c = img + (long long)id_y * W + id_x;
     const float f = front[c], bk = back[c];
     // :110-111 — hidden if behind the middle of the local depth range and more than `threshold` behind the front
-    const bool visible = !(z > ((f + bk) * 0.5) && z > (f + threshold));
+    // (the reference's `* 0.5` promotes to double; halving is exact in fp32 too, so the comparison is the same)
+    const bool visible = !(z > ((f + bk) * 0.5f) && z > (f + threshold));
     if (k == 0) {
       pixel_index[pt * 2] = id_x; pixel_index[pt * 2 + 1] = id_y;
       is_visible[pt] = visible ? 1 : 0;
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(256) render_raster_kernel(const float* __restr
     const int current_x = id_x - (cpw - 1) / 2 + i, current_y = id_y - (cpw - 1) / 2 + j;
     float g = 0.f;
     if (visible && current_x >= 0 && current_x < W && current_y >= 0 && current_y < H) {
-      const float center_x = float(2 * current_x + 1) / 2.0, center_y = float(2 * current_y + 1) / 2.0;   // :159-160
+      const float center_x = float(2 * current_x + 1) * 0.5f, center_y = float(2 * current_y + 1) * 0.5f;   // :159-160 (exact)
       const float distance = (project_x - center_x) * (project_x - center_x) +
                              (project_y - center_y) * (project_y - center_y);                            // :161
       g = expf(-distance / distance_divisor);                                                             // :162
@@ -137,19 +138,23 @@ __global__ void __launch_bounds__(128) render_backward_kernel(const float* __res
       for (int j = 0; j < cpw; ++j) {
         const int current_y = init_y + j;
         if (current_y < 0 || current_y >= H) continue;
-        const float center_y = float(2 * current_y + 1) / 2.0;
+        const float center_y = float(2 * current_y + 1) * 0.5f;
         for (int i = 0; i < cpw; ++i) {
           const int current_x = init_x + i;
           if (current_x < 0 || current_x >= W) continue;
           const long long o = img + (long long)current_y * W + current_x;
-          const float center_x = float(2 * current_x + 1) / 2.0;
+          const float center_x = float(2 * current_x + 1) * 0.5f;
           const float distance = (project_x - center_x) * (project_x - center_x) +
                                  (project_y - center_y) * (project_y - center_y);
           const float wgt = expf(-distance / distance_divisor);            // == forward's weight_points entry
           const float gd = grad_depth[o];
           const float grad_depth_z = gd * z;                               // :262
           const float gwp = grad_depth_z + grad_weight[o];                 // :264 (added into a zero-filled slot)
-          const float grad_xy = -(gwp * wgt * 2.0 / distance_divisor);     // :318 — through double, as written
+          // :318 is -(gwp * wgt * 2.0 / divisor) through DOUBLE (the 2.0 literal).  With t = fl(gwp*wgt) and an integer
+          // divisor d < 2^15, q = 2t/d is never within 2^-40 relative of a float rounding midpoint unless it sits on
+          // it, so RN24(RN53(q)) == RN24(q): one IEEE float division gives the same bits as the reference's 39
+          // FP64 instructions per patch pixel (checked bit for bit against its output, tests/golden/exfunc_*.npz)
+          const float grad_xy = -__fdiv_rn(__fmul_rn(__fmul_rn(gwp, wgt), 2.f), distance_divisor);
           gx = __fadd_rn(gx, __fmul_rn(grad_xy, project_x - center_x));    // :319, :322 (atomicAdd: separate rounding)
           gy = __fadd_rn(gy, __fmul_rn(grad_xy, project_y - center_y));
           gz = __fadd_rn(gz, __fmul_rn(gd, wgt));                          // :321, :324
@@ -191,23 +196,54 @@ __device__ __forceinline__ float mask_gauss(float distance) {
 
 struct MaskEntry { float cx, cy, g, s; };   // pixel centre, upstream gradient (g / s after stage 2), epsilon + sum_i e_i
 
-// Stage 1: one CTA per batch element compacts the pixels with |g| > threshold, in pixel order (deterministic).
-__global__ void __launch_bounds__(1024) mask_compact_kernel(const float* __restrict__ grad_mask, int H, int W,
-                                                            float threshold, MaskEntry* __restrict__ entries,
-                                                            int* __restrict__ counts) {
-  __shared__ int warp_tot[32];
-  __shared__ int base;
+// Stage 1: compaction of the pixels with |g| > threshold, in pixel order (deterministic), in two passes over
+// kMaskSegs segments per batch element: a count pass, then every segment writes behind the sum of the counts before it.
+constexpr int kMaskSegs = 16;
+
+__global__ void __launch_bounds__(256) mask_count_kernel(const float* __restrict__ grad_mask, int npix,
+                                                         float threshold, int* __restrict__ segcount) {
+  __shared__ int wsum[8];
   pdl_wait();
-  const int b = blockIdx.x, npix = H * W;
+  const int b = blockIdx.y, seg = blockIdx.x;
+  const int per = (npix + kMaskSegs - 1) / kMaskSegs;
+  const int begin = min(seg * per, npix), end = min(begin + per, npix);
+  int c = 0;
+  for (int pix = begin + threadIdx.x; pix < end; pix += 256)
+    c += fabsf(grad_mask[(long long)b * npix + pix]) > threshold ? 1 : 0;                       // :46
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += wsum[k];
+    segcount[b * kMaskSegs + seg] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) mask_compact_kernel(const float* __restrict__ grad_mask, int H, int W,
+                                                           float threshold, const int* __restrict__ segcount,
+                                                           MaskEntry* __restrict__ entries, int* __restrict__ counts) {
+  __shared__ int warp_tot[8];
+  __shared__ int base;
+  const int b = blockIdx.y, seg = blockIdx.x, npix = H * W;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) base = 0;
+  const int per = (npix + kMaskSegs - 1) / kMaskSegs;
+  const int begin = min(seg * per, npix), end = min(begin + per, npix);
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < seg; ++k) t += segcount[b * kMaskSegs + k];
+    base = t;
+    if (seg == kMaskSegs - 1) counts[b] = t + segcount[b * kMaskSegs + seg];
+  }
   __syncthreads();
   MaskEntry* out = entries + (long long)b * npix;
-  for (int start = 0; start < npix; start += 1024) {
+  for (int start = begin; start < end; start += 256) {
     const int pix = start + threadIdx.x;
     float g = 0.f;
     bool on = false;
-    if (pix < npix) { g = grad_mask[(long long)b * npix + pix]; on = fabsf(g) > threshold; }   // :46
+    if (pix < end) { g = grad_mask[(long long)b * npix + pix]; on = fabsf(g) > threshold; }
     const unsigned bal = __ballot_sync(0xffffffffu, on);
     if (lane == 0) warp_tot[warp] = __popc(bal);
     __syncthreads();
@@ -216,14 +252,13 @@ __global__ void __launch_bounds__(1024) mask_compact_kernel(const float* __restr
     if (on) {
       const int x = pix % W, y = pix / W;
       MaskEntry e;
-      e.cx = float(2 * x + 1) / 2.0; e.cy = float(2 * y + 1) / 2.0; e.g = g; e.s = 0.f;      // :59-60
+      e.cx = float(2 * x + 1) * 0.5f; e.cy = float(2 * y + 1) * 0.5f; e.g = g; e.s = 0.f;     // :59-60
       out[before + __popc(bal & ((1u << lane) - 1u))] = e;
     }
     __syncthreads();
-    if (threadIdx.x == 0) { int tot = 0; for (int k = 0; k < 32; ++k) tot += warp_tot[k]; base += tot; }
+    if (threadIdx.x == 0) { int tot = 0; for (int k = 0; k < 8; ++k) tot += warp_tot[k]; base += tot; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) counts[b] = base;
 }
 
 // Stage 2: one thread per active pixel: s = epsilon + sum_i expf(-d_i / 1000), points in order (:70-78), staged
@@ -375,7 +410,7 @@ static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 
 size_t rma_point_masker_backward_scratch_bytes(int B, int N, int H, int W) {
   if (B <= 0 || N <= 0 || H <= 0 || W <= 0) return 0;
-  return up256((size_t)B * H * W * sizeof(MaskEntry)) + up256((size_t)B * sizeof(int)) +
+  return up256((size_t)B * H * W * sizeof(MaskEntry)) + up256((size_t)B * (1 + kMaskSegs) * sizeof(int)) +
          up256((size_t)B * kMaskSlices * N * sizeof(float));
 }
 
@@ -390,9 +425,19 @@ int rma_point_masker_backward(const float* grad_mask_image, const float* proj_po
   const int npix = H * W;
   MaskEntry* entries = (MaskEntry*)scratch;
   int* counts = (int*)((char*)scratch + up256((size_t)B * npix * sizeof(MaskEntry)));
-  float* partial = (float*)((char*)counts + up256((size_t)B * sizeof(int)));
-  RMA_CUDA_TRY(launch_pdl(mask_compact_kernel, (unsigned)B, 1024u, 0, st, grad_mask_image, H, W, threshold, entries,
-                          counts));
+  int* segcount = counts + B;
+  float* partial = (float*)((char*)counts + up256((size_t)B * (1 + kMaskSegs) * sizeof(int)));
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kMaskSegs, (unsigned)B, 1); cfg.blockDim = dim3(256, 1, 1); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    RMA_CUDA_TRY(cudaLaunchKernelEx(&cfg, mask_count_kernel, grad_mask_image, npix, threshold, segcount));
+  }
+  mask_compact_kernel<<<dim3(kMaskSegs, B), 256, 0, st>>>(grad_mask_image, H, W, threshold, segcount, entries, counts);
+  RMA_LAUNCH_CHECK();
   // the grids cover the worst case (every pixel active); blocks beyond the batch element's count exit at once
   mask_norm_kernel<<<dim3((npix + kMaskThreads - 1) / kMaskThreads, B), kMaskThreads, 0, st>>>(
       proj_points, N, npix, epsilon, entries, counts);
