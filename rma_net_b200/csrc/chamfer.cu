@@ -24,7 +24,6 @@ constexpr int kRowsPerThread = 16;                      // R: source points held
 constexpr int kRowsPerWarp = 32 * kRowsPerThread;       // 512: one "row block"
 constexpr int kSearchWarps = 4;                         // warps per CTA (one per SM sub-partition)
 constexpr int kSearchThreads = 32 * kSearchWarps;
-constexpr int kRowsPerCta = kRowsPerWarp * kSearchWarps;  // 2048
 constexpr int kTile = 32;                               // columns per tile (= lanes, for the column transpose)
 constexpr int kChunk = 1024;                            // columns staged in shared memory at a time
 constexpr int kCbStride = 36;                           // row stride (floats) of the per-warp column-min transpose
@@ -153,8 +152,6 @@ struct SearchArgs {
   u64* rowbest;
   u64* colbest;
   int N, M, nRB, Npad, nRBC, Mp, S;
-  long long* trace;   // experiments: per-CTA (start, after prologue, end, smid) clock64 stamps, or null
-  int stagger_ns;     // experiments: delay of the second-wave CTAs (desynchronise co-resident warps)
 };
 
 __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(SearchArgs a) {
@@ -164,9 +161,6 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_wait();
-  long long tr0 = 0, tr1 = 0;
-  if (a.trace) tr0 = clock64();
-  if (a.stagger_ns > 0 && blockIdx.x >= 148) __nanosleep(a.stagger_ns);
   const int s = blockIdx.x % a.S;
   const int rbc = (blockIdx.x / a.S) % a.nRBC;
   const int b = blockIdx.x / (a.S * a.nRBC);
@@ -209,7 +203,6 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
     __syncthreads();   // previous chunk fully consumed
     for (int idx = tid; idx < nc; idx += kSearchThreads) scol[idx] = cp[(size_t)cs + idx];
     __syncthreads();
-    if (a.trace && cs == 0) tr1 = clock64();
     if (!has_rows) continue;
 
 #pragma unroll 1
@@ -300,14 +293,6 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
     for (int r = 0; r < kRowsPerThread; ++r) {
       if (i0 + r < a.N) atomicMin(rbest + r, ((u64)__float_as_uint(m[r]) << 32) | (unsigned)mt[r]);
     }
-  }
-  if (a.trace && tid == 0) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-    long long gt;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-    long long* t = a.trace + (size_t)blockIdx.x * 5;
-    t[0] = tr0; t[1] = tr1; t[2] = clock64(); t[3] = smid; t[4] = gt;
   }
 }
 
@@ -656,9 +641,7 @@ size_t rma_chamfer_workspace_bytes(int B, int N, int M) {
   return bytes;
 }
 
-static long long* g_trace = nullptr;   // experiment hooks, see rma_exp_set_search_debug
-static int g_force_splits = 0;
-static int g_stagger_ns = 0;
+static int g_force_splits = 0;   // experiment hook, see rma_exp_set_search_debug
 
 static int forward_setup(const float* x, const float* y, int B, int N, int M, void* workspace,
                          size_t workspace_bytes, Geometry* g, Workspace* w) {
@@ -708,8 +691,6 @@ int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_by
   a.colbest = w.colbest;
   a.N = N; a.M = M; a.nRB = g.nRB; a.Npad = g.Npad; a.nRBC = g.nRBC; a.Mp = g.Mp;
   a.S = g_force_splits > 0 ? g_force_splits : choose_splits(g, caps);
-  a.trace = g_trace;
-  a.stagger_ns = g_stagger_ns;
   const long long ctas = (long long)B * g.nRBC * a.S;
   if (ctas > 0x7fffffffLL) return RMA_E_BADARG;
   RMA_CUDA_TRY(launch_pdl(chamfer_search_kernel, (unsigned)ctas, (unsigned)kSearchThreads, kSearchSmem,
@@ -717,12 +698,12 @@ int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_by
   return RMA_OK;
 }
 
-// Experiment hooks (tools/search_variants.py only; not part of include/rma_b200.h, not used by the product path).
-int rma_exp_set_search_debug(long long* trace, int force_splits, int stagger_ns) {
-  g_trace = trace;
+// Experiment hook (tools/fsearch_variants.py only; not part of include/rma_b200.h, not used by the product path):
+// forces the column splits of the exact search / the unit run (64-column tiles per CTA) of the filter search.
+// The first and third arguments are ignored (kept for the tools' call signature).
+int rma_exp_set_search_debug(long long* /*unused*/, int force_splits, int /*unused*/) {
   g_force_splits = force_splits;
-  f_set_force_unit_run(force_splits);   // filter path: tiles per CTA
-  g_stagger_ns = stagger_ns;
+  f_set_force_unit_run(force_splits);
   return RMA_OK;
 }
 

@@ -87,12 +87,14 @@ int rma_knn(const float* queries, int64_t qsb, int64_t qsn, int64_t qsc,
   if ((long long)N > (1LL << 30) || (long long)M > (1LL << 30)) return RMA_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream_;
   const dim3 grid((unsigned)((N + kKnnThreads - 1) / kKnnThreads), (unsigned)B);
-  // k sorted slots are compile-time (registers): 8 covers the reference's k = 5 in both call sites
+  // k sorted slots are compile-time (registers); 5 is the reference's k in both call sites (network.py:63 default,
+  // loss.py:253 with neighbour_num = 4): fewer slots = a tighter threshold and a shorter insert
 #define RMA_KNN_LAUNCH(KK)                                                                                       \
   knn_kernel<KK><<<grid, kKnnThreads, 0, st>>>(queries, (long long)qsb, (long long)qsn, (long long)qsc, candidates, \
                                                (long long)csb, (long long)csn, (long long)csc, N, M, k, skip_first, \
                                                (int*)idx, dist)
-  if (k <= 8) RMA_KNN_LAUNCH(8);
+  if (k <= 5) RMA_KNN_LAUNCH(5);
+  else if (k <= 8) RMA_KNN_LAUNCH(8);
   else if (k <= 16) RMA_KNN_LAUNCH(16);
   else RMA_KNN_LAUNCH(32);
 #undef RMA_KNN_LAUNCH
