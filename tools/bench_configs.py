@@ -75,6 +75,24 @@ def main():
             return loss
 
         ms = timed(step, dev, 10, world)
+
+        # the same step the way the reference structures it (network forward produces all stage outputs, then
+        # Loss.forward loops over them, loss.py:260-267): 8 warps, then ONE batched chamfer call over the T stages
+        from rma_net_b200.model.loss import loss_cd_stages_fused
+
+        def step_fused():
+            for p in phis + ws:
+                p.grad = None
+            outs, prev = [], None
+            for k in range(T):
+                out_k, _, _ = warp(phis[k], src, None if k == 0 else ws[k], prev)
+                outs.append(out_k.transpose(1, 2))          # [B,3,N] as the network holds the stage outputs
+                prev = out_k
+            loss = loss_cd_stages_fused(outs, tgt, gamma=gamma)
+            loss.backward()
+            return loss
+
+        ms_fused = timed(step_fused, dev, 10, world)
         pairs = T * B * N * N
         # warp kernels alone (HBM-bound): fwd 40 B/point, bwd reads src+prev+w+go, writes grad_w
         prev = src.clone()
@@ -87,6 +105,8 @@ def main():
         out.append({"config": "C3", "what": "8 x (se3 warp + chamfer) fwd+bwd, B=16 per GPU, N=M=8192", "n_gpus": world,
                     "ms_per_step": ms, "G_pairs_per_s": world * pairs / ms / 1e6,
                     "fp32_fma_peak_frac": 6 * pairs / (ms * 1e-3) / PEAK_FMA,
+                    "ms_per_step_stage_fused": ms_fused,
+                    "fp32_fma_peak_frac_stage_fused": 6 * pairs / (ms_fused * 1e-3) / PEAK_FMA,
                     "warp_fwd_bwd_pair_ms": wms,
                     "warp_fwd_bwd_algorithmic_GBps": B * N * (40 + 44) / (wms * 1e-3) / 1e9})
     if "C4" in cfgs:
