@@ -634,25 +634,32 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
     unsigned best_d = 0xffffffffu, best_i = 0;
 
     // Fast path (one candidate group of 16 rows): 8 lanes per column, 2 rows per lane, 4 columns per round.
-    sA[warp][lane] = make_float4(cq.x, cq.y, cq.z, 0.f);
-    sB[warp][lane] = make_int4(b, G1, fast ? 1 : 0, 0);
+    sA[warp][lane] = make_float4(cq.x, cq.y, cq.z, cq.w);
+    sB[warp][lane] = make_int4(b, G1, fast ? 1 : 0, __float_as_int(thr));
     __syncwarp();
+    // As for the rows: inside the candidate group the guard applies per ROW (g_i = fl(f + |x_i|^2) <= thr for every
+    // exact minimiser; padded rows carry |x|^2 = 1e30), so the 16 rows are re-filtered with the search's chain and
+    // only the survivors are evaluated exactly.
 #pragma unroll 2
     for (int round = 0; round < 8; ++round) {
       const int src = round * 4 + grp;
       const float4 q = sA[warp][src];
       const int4 sb4 = sB[warp][src];
+      const float sthr = __int_as_float(sb4.w);
       unsigned d = 0xffffffffu, di = 0xffffffffu;
       if (sb4.z) {
-        const int r0 = sb4.y + sub, r1 = r0 + 8;
-        const float4 pa = w.rowpack[(size_t)sb4.x * g.Npad + r0], pb = w.rowpack[(size_t)sb4.x * g.Npad + r1];
-        const unsigned d0 = r0 < g.N ? __float_as_uint(sqdist_q(pa.x, pa.y, pa.z, q)) : 0xffffffffu;
-        const unsigned d1 = r1 < g.N ? __float_as_uint(sqdist_q(pb.x, pb.y, pb.z, q)) : 0xffffffffu;
-        d = d0; di = (unsigned)r0;
-        if (d1 < d0) { d = d1; di = (unsigned)r1; }
+        const int r0 = sb4.y + sub;
+        const float4 pa = w.rowpack[(size_t)sb4.x * g.Npad + r0], pb = w.rowpack[(size_t)sb4.x * g.Npad + r0 + 8];
+        const float ga = __fadd_rn(__fmaf_rn(pa.x, q.x, __fmaf_rn(pa.y, q.y, __fmaf_rn(pa.z, q.z, q.w))), pa.w);
+        const float gb = __fadd_rn(__fmaf_rn(pb.x, q.x, __fmaf_rn(pb.y, q.y, __fmaf_rn(pb.z, q.z, q.w))), pb.w);
+        if (ga <= sthr) { d = __float_as_uint(sqdist_q(pa.x, pa.y, pa.z, q)); di = (unsigned)r0; }
+        if (gb <= sthr) {
+          const unsigned d1 = __float_as_uint(sqdist_q(pb.x, pb.y, pb.z, q));
+          if (d1 < d) { d = d1; di = (unsigned)(r0 + 8); }
+        }
       }
-      group8_min(d, di);
-      const unsigned rd = __shfl_sync(full, d, (lane & 3) * 8), ri = __shfl_sync(full, di, (lane & 3) * 8);
+      unsigned rd, ri;
+      round_result(d, di, rd, ri);
       if ((lane >> 2) == round) { best_d = rd; best_i = ri; }
     }
 
