@@ -496,11 +496,12 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       const int klast = (int)((((unsigned)brb + 1u) * (unsigned)g.nT - 1u) / (unsigned)g.U);
       const float* top = w.rowtop + ((size_t)brb * g.Smax * 3) * kFRowsPerCta + (i - rbc * kFRowsPerCta);
       const int nseg = klast - kfirst + 1;
-      for (int s0 = 0; s0 < nseg; s0 += 4) {      // four segments' records in flight
-        float a1[4], a2[4];
-        int at[4];
+      constexpr int kSegBatch = 12;                 // records of up to 12 segments in flight: one latency for C2 (10)
+      for (int s0 = 0; s0 < nseg; s0 += kSegBatch) {
+        float a1[kSegBatch], a2[kSegBatch];
+        int at[kSegBatch];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kSegBatch; ++k) {
           const bool on = s0 + k < nseg;
           const float* tp = top + (size_t)(on ? s0 + k : s0) * (3 * kFRowsPerCta);
           a1[k] = on ? tp[0] : inf;
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
           a2[k] = on ? tp[2 * kFRowsPerCta] : inf;
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kSegBatch; ++k) {
           M2 = fminf(fminf(M2, a2[k]), fmaxf(M1, a1[k]));
           if (a1[k] < M1) { M1 = a1[k]; T1 = at[k]; }
         }
@@ -612,17 +613,18 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       b = (int)(t / (unsigned)g.M); j = (int)(t - (unsigned)b * (unsigned)g.M);
       cq = w.colpack[(size_t)b * g.Mp + j];
       const float* rec = w.colrec + (size_t)b * g.nRB * 3 * g.Mp + j;
-      for (int r0 = 0; r0 < g.nRB; r0 += 4) {     // four row blocks' records in flight
-        float a1[4], a2[4];
+      constexpr int kRbBatch = 8;                   // records of 8 row blocks in flight (C2: all of them)
+      for (int r0 = 0; r0 < g.nRB; r0 += kRbBatch) {
+        float a1[kRbBatch], a2[kRbBatch];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kRbBatch; ++k) {
           const bool on = r0 + k < g.nRB;
           const float* rp_ = rec + (size_t)(on ? r0 + k : r0) * 3 * g.Mp;
           a1[k] = on ? rp_[0] : inf;
           a2[k] = on ? rp_[g.Mp] : inf;
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kRbBatch; ++k) {
           M2 = fminf(fminf(M2, a2[k]), fmaxf(M1, a1[k]));
           if (a1[k] < M1) { M1 = a1[k]; R1 = r0 + k; }
         }
