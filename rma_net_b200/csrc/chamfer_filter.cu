@@ -7,7 +7,7 @@
 //              f_ij = |y_j|^2 - 2 x_i.y_j   (3 FFMA, chain seeded with |y_j|^2)         -> row direction  min_j f_ij
 //              g_ij = f_ij + |x_i|^2        (1 FADD)                                    -> column direction min_i g_ij
 //            The expanded form cancels, so f/g are only a FILTER.  Per row the minimum of f over every 64-column tile
-//            is written to a record; per column and 512-row block the three smallest 16-row-group minima are written
+//            is written to a record; per column and 512-row block the two smallest 16-row-group minima are written
 //            (group id packed into the 5 low mantissa bits).  No atomics, no index bookkeeping in the inner loop.
 //   resolve  per row: every tile whose filter minimum lies within a rigorous rounding-error guard G of the smallest
 //            one is a candidate; its 64 columns are re-evaluated in the exact difference form and the (distance,
@@ -34,6 +34,7 @@ constexpr int kFWarps = 4;
 constexpr int kFThreads = 32 * kFWarps;
 constexpr int kFRowsPerCta = kFRowsPerWarp * kFWarps;   // 2048
 constexpr int kFColTile = 32;                           // columns per column-direction tile (= lanes)
+constexpr int kFColTop = 2;                             // packed group minima recorded per column and row block
 constexpr int kFRowTile = 64;                           // columns per row-direction record
 #ifndef RMA_F_CHUNK
 #define RMA_F_CHUNK 1024
@@ -96,7 +97,7 @@ struct FWorkspace {
   float4* colpack;   // [B][Mp]                 (-2x, -2y, -2z, |y|^2); padded columns (0,0,0,1e30)
   float* rowrec;     // [B][nT][Npad]           min over the tile's 64 columns of f (read only when a guard fails)
   float* rowtop;     // [B*nRBC][Smax][3][2048] per segment: smallest tile minimum, its tile, second smallest
-  float* colrec;     // [B][nRB][3][Mp]         three smallest packed group minima of g over the row block
+  float* colrec;     // [B][nRB][2][Mp]         two smallest packed group minima of g over the row block
   unsigned* stats;   // [4] rows on the slow path, columns on the slow path, row-block rescans, unused
   size_t bytes;
 };
@@ -110,7 +111,7 @@ static FWorkspace f_carve(const FGeometry& g, void* base) {
   w.colpack = (float4*)(p + off); off += align256((size_t)g.B * g.Mp * sizeof(float4));
   w.rowrec = (float*)(p + off);   off += align256((size_t)g.B * g.nT * g.Npad * sizeof(float));
   w.rowtop = (float*)(p + off);   off += align256((size_t)g.B * g.nRBC * g.Smax * 3 * kFRowsPerCta * sizeof(float));
-  w.colrec = (float*)(p + off);   off += align256((size_t)g.B * g.nRB * 3 * g.Mp * sizeof(float));
+  w.colrec = (float*)(p + off);   off += align256((size_t)g.B * g.nRB * kFColTop * g.Mp * sizeof(float));
   w.stats = (unsigned*)(p + off); off += 256;
   w.bytes = off;
   return w;
@@ -171,9 +172,9 @@ __global__ void __launch_bounds__(256) chamfer_fprep_kernel(
 // ---------------------------------------------------------------------------------------------------------------
 // search
 // ---------------------------------------------------------------------------------------------------------------
-// Insert v into the ascending triple (p1 <= p2 <= p3): 5 FMNMX, no predicates.
-__device__ __forceinline__ void top3_insert(float& p1, float& p2, float& p3, float v) {
-  p3 = fminf(p3, fmaxf(p2, v));
+// Insert v into the ascending pair (p1 <= p2): 3 FMNMX, no predicates.  (Two entries per row block suffice: a second
+// group within the guard - ~5e-5 of the columns at C2 - makes the resolve re-evaluate the whole 512-row block.)
+__device__ __forceinline__ void top2_insert(float& p1, float& p2, float v) {
   p2 = fminf(p2, fmaxf(p1, v));
   p1 = fminf(p1, v);
 }
@@ -204,6 +205,8 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
   float* cb = cball + warp * (2 * kFColTile * kFCbStride);
   const float inf = __int_as_float(0x7f800000);
   const unsigned lane_tag = (unsigned)lane;
+  unsigned tag_mask = ~31u;                                    // kept in a register: (bits & mask) | tag is then ONE LOP3
+  asm volatile("" : "+r"(tag_mask));
 
   long long unit = (long long)blockIdx.x * a.U;
   const long long unit_end = min(unit + a.U, a.units);
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
 
     const float4* cp = a.colpack + ((size_t)b * a.Mp + c0);
     float* rrec = a.rowrec + ((size_t)b * a.nT + tile0) * a.Npad + (size_t)rb * kFRowsPerWarp + lane * kFRowsPerThread;
-    float* crec = a.colrec + ((size_t)(b * a.nRB + rb) * 3) * a.Mp + c0 + lane;
+    float* crec = a.colrec + ((size_t)(b * a.nRB + rb) * kFColTop) * a.Mp + c0 + lane;
 
     // Column direction, software-pipelined: while tile t is computed, lane l folds column l of tile t-1 (32 per-lane
     // packed partial minima in the other half of the double buffer) into its running top-3, four values per body.
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
           float* cbw = cb + parity * (kFColTile * kFCbStride) + lane;
           const float4* cbr = reinterpret_cast<const float4*>(cb + (parity ^ 1) * (kFColTile * kFCbStride) +
                                                               lane * kFCbStride);
-          float p1 = inf, p2 = inf, p3 = inf;
+          float p1 = inf, p2 = inf;
 
           // Four columns against the 16 rows, plus four pending values of the previous tile's column reduce.
           auto body = [&](const float4& q0, const float4& q1, const float4& q2, const float4& q3, int jj) {
@@ -326,11 +329,11 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              cbw[(jj + c) * kFCbStride] = __uint_as_float((__float_as_uint(cm[c]) & ~31u) | lane_tag);
-            top3_insert(p1, p2, p3, pv.x);
-            top3_insert(p1, p2, p3, pv.y);
-            top3_insert(p1, p2, p3, pv.z);
-            top3_insert(p1, p2, p3, pv.w);
+              cbw[(jj + c) * kFCbStride] = __uint_as_float((__float_as_uint(cm[c]) & tag_mask) | lane_tag);
+            top2_insert(p1, p2, pv.x);
+            top2_insert(p1, p2, pv.y);
+            top2_insert(p1, p2, pv.z);
+            top2_insert(p1, p2, pv.w);
           };
 
           // Operands are prefetched one body ahead into the OTHER register set (ping-pong, unrolled by two) so that no
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
 
           if (pend_col >= 0) {
             float* o = crec + pend_col;
-            o[0] = p1; o[a.Mp] = p2; o[2 * (size_t)a.Mp] = p3;
+            o[0] = p1; o[a.Mp] = p2;
           }
           pend_col = cs + t0 + h;
           parity ^= 1;
@@ -380,11 +383,11 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
     if (has_rows) {
       if (pend_col >= 0) {   // drain: column reduce of the segment's last tile
         const float* col = cb + (parity ^ 1) * (kFColTile * kFCbStride) + lane * kFCbStride;
-        float p1 = inf, p2 = inf, p3 = inf;
+        float p1 = inf, p2 = inf;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) top3_insert(p1, p2, p3, col[k]);
+        for (int k = 0; k < 32; ++k) top2_insert(p1, p2, col[k]);
         float* o = crec + pend_col;
-        o[0] = p1; o[a.Mp] = p2; o[2 * (size_t)a.Mp] = p3;
+        o[0] = p1; o[a.Mp] = p2;
       }
       float* top = a.rowtop + ((size_t)(brb * a.Smax + seg) * 3) * kFRowsPerCta + warp * kFRowsPerWarp +
                    lane * kFRowsPerThread;
@@ -612,14 +615,14 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
     if (valid) {
       b = (int)(t / (unsigned)g.M); j = (int)(t - (unsigned)b * (unsigned)g.M);
       cq = w.colpack[(size_t)b * g.Mp + j];
-      const float* rec = w.colrec + (size_t)b * g.nRB * 3 * g.Mp + j;
+      const float* rec = w.colrec + (size_t)b * g.nRB * kFColTop * g.Mp + j;
       constexpr int kRbBatch = 8;                   // records of 8 row blocks in flight (C2: all of them)
       for (int r0 = 0; r0 < g.nRB; r0 += kRbBatch) {
         float a1[kRbBatch], a2[kRbBatch];
 #pragma unroll
         for (int k = 0; k < kRbBatch; ++k) {
           const bool on = r0 + k < g.nRB;
-          const float* rp_ = rec + (size_t)(on ? r0 + k : r0) * 3 * g.Mp;
+          const float* rp_ = rec + (size_t)(on ? r0 + k : r0) * kFColTop * g.Mp;
           a1[k] = on ? rp_[0] : inf;
           a2[k] = on ? rp_[g.Mp] : inf;
         }
@@ -665,8 +668,8 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       if ((lane >> 2) == round) { best_d = rd; best_i = ri; }
     }
 
-    // Slow path: every (row block, k) entry within the guard is a candidate group; a third-smallest entry within
-    // the guard means the row block may hold more than the recorded three, so all of its 512 rows are re-evaluated.
+    // Slow path: every row block's smallest entry within the guard is a candidate group; a second-smallest entry
+    // within the guard means the row block may hold more than the recorded two, so all of its 512 rows are re-evaluated.
     unsigned slow = __ballot_sync(full, valid && !fast);
     if (slow && lane == 0) atomicAdd(w.stats + 1, (unsigned)__popc(slow));
     while (slow) {
@@ -675,19 +678,19 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       const float sthr = __shfl_sync(full, thr, src);
       const float4 q = make_float4(__shfl_sync(full, cq.x, src), __shfl_sync(full, cq.y, src),
                                    __shfl_sync(full, cq.z, src), 0.f);
-      const float* rec = w.colrec + (size_t)sb * g.nRB * 3 * g.Mp + sj;
+      const float* rec = w.colrec + (size_t)sb * g.nRB * kFColTop * g.Mp + sj;
       unsigned bd = 0xffffffffu, bi = 0xffffffffu;
-      const int nE = g.nRB * 3;
+      const int nE = g.nRB * kFColTop;
       for (int base = 0; base < nE; base += 32) {
         const int e = base + lane;
         const float p = e < nE ? rec[(size_t)e * g.Mp] : inf;
         unsigned hits = __ballot_sync(full, p <= sthr);
         while (hits) {
           const int hl = __ffs(hits) - 1; hits &= hits - 1;
-          const int he = base + hl, hrb = he / 3, hk = he - hrb * 3;
+          const int he = base + hl, hrb = he / kFColTop, hk = he - hrb * kFColTop;
           const unsigned pbits = __float_as_uint(__shfl_sync(full, p, hl));
           int first, n;
-          if (hk < 2) { first = (hrb * 32 + (int)(pbits & 31u)) * kFRowsPerThread; n = kFRowsPerThread; }
+          if (hk < kFColTop - 1) { first = (hrb * 32 + (int)(pbits & 31u)) * kFRowsPerThread; n = kFRowsPerThread; }
           else { first = hrb * kFRowsPerWarp; n = kFRowsPerWarp; if (lane == 0) atomicAdd(w.stats + 2, 1u); }
           unsigned dm = 0xffffffffu, im = 0xffffffffu;
           for (int o = lane; o < n; o += 32) {
@@ -762,7 +765,7 @@ bool f_sizes_ok(int B, int N, int M) {
 // Bytes of the filter's tile records alone (the dispatcher's size criterion; device independent).
 size_t f_record_bytes(int B, int N, int M) {
   const FGeometry g = f_make_geometry(B, N, M, 296, 1);
-  return ((size_t)g.B * g.nT * g.Npad + (size_t)g.B * g.nRB * 3 * g.Mp) * sizeof(float);
+  return ((size_t)g.B * g.nT * g.Npad + (size_t)g.B * g.nRB * kFColTop * g.Mp) * sizeof(float);
 }
 
 // SM count and resident search CTAs per SM of the current device.  Immutable device properties, cached per device
