@@ -188,3 +188,31 @@ def test_numpy_oracle_agrees_on_gpu_case(cuda):
     gm = np.where(rng.random((1, 48, 48, 1)) < 0.2, rng.normal(size=(1, 48, 48, 1)), 0).astype(np.float32)
     ours = ext.point_masker_backward(torch.from_numpy(gm).to(cuda), proj.to(cuda), 1e-5, 1e-10)[0].cpu().numpy()
     _close_sum(ours, eo.masker_backward(gm, proj.numpy(), 1e-5, 1e-10), "mask backward vs numpy", rel=1e-5)
+
+
+def test_multi_view_losses_batched_equals_per_view_loop(cuda):
+    """loss_on_depth / loss_on_mask (loss.py:147-196): the views folded into the batch (2 kernel calls) against the
+    reference's literal per-view loop (2V calls) on the same kernels, and euler2rot against the reference formula."""
+    from rma_net_b200.model.loss import euler2rot, loss_on_depth, loss_on_mask, view_rotations
+    g = torch.Generator().manual_seed(5)
+    B, N, vd = 2, 1200, 3
+    src = (torch.randn(B, N, 3, generator=g) * 0.3).clamp(-0.9, 0.9).to(cuda).requires_grad_(True)
+    tgt = (torch.randn(B, N, 3, generator=g) * 0.3).clamp(-0.9, 0.9).to(cuda)
+    rot = view_rotations(vd, cuda, jitter=torch.rand(vd * vd, 2, generator=g))
+    assert rot.shape == (3 * vd * vd, 3)
+    r0 = rot[:3]
+    assert torch.allclose(r0 @ r0.T, torch.eye(3, device=cuda), atol=1e-6)
+    e = euler2rot(torch.tensor([[0.3, -0.2, 0.1]], device=cuda))[0]
+    assert torch.allclose(e @ e.T, torch.eye(3, device=cuda), atol=1e-6) and abs(torch.det(e).item() - 1) < 1e-5
+    for fn, rel in ((loss_on_depth, 2e-5), (loss_on_mask, 1e-5)):
+        src.grad = None
+        a = fn(src, tgt, rot, resolution=128, batched=True)
+        a.backward()
+        ga = src.grad.clone()
+        src.grad = None
+        b = fn(src, tgt, rot, resolution=128, batched=False)
+        b.backward()
+        gb = src.grad.clone()
+        assert abs(a.item() - b.item()) <= rel * abs(b.item()) + 1e-12, (fn.__name__, a.item(), b.item())
+        assert (ga - gb).abs().max() <= 2e-5 * gb.abs().max() + 1e-12, fn.__name__
+        assert gb.abs().max() > 0
