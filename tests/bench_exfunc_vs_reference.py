@@ -4,7 +4,7 @@ loss.py:33-37 configuration (256x256, Render(7, 9), Masker(5)), forward + backwa
 The reference leg is timed twice: `kernels` = its launchers alone on pre-filled buffers, and `wrapper` = with what
 point_render.cpp / point_masker.cpp do around them on every call (6 torch fills and 3 cudaDeviceSynchronize for the
 render forward, point_render.cpp:54-96), which is what a user of the reference actually pays.
-    python tools/bench_exfunc.py [B] [N]"""
+    python tests/bench_exfunc_vs_reference.py [B] [N]   (lives under tests/: it runs the reference kernels of oracle/_ref)"""
 import json
 import os
 import sys
