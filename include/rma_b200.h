@@ -230,6 +230,28 @@ int rma_knn(const float* queries, int64_t qsb, int64_t qsn, int64_t qsc,
             int B, int N, int M, int k, int skip_first, int32_t* idx, float* dist, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * As-rigid-as-possible edge-length loss, all stages of a step in one launch.
+ * Replaces Loss.loss_on_arap (model/loss.py:233-243) and its stage loop (model/loss.py:334-345):
+ *   loss += coef * sum_g group_weight[g] * sum_{v,k} (sqrt(|d_j-d_v|^2 + 1e-5) - sqrt(|s_j-s_v|^2 + 1e-5))^2,
+ *   j = neighbour_idx[b,v,k], b = g % B.
+ * deformation [G,V,3] (G = stages * B) and source [B,V,3] with element strides; neighbour_idx [B,V,n] contiguous
+ * (entries outside [0,V) are skipped); group_weight NULL (all 1) or [G]; loss [1] and grad_deformation (NULL or
+ * [G,V,3] contiguous) must be ZEROED by the caller: the kernel accumulates d loss / d deformation into it. */
+int rma_arap_forward(const float* deformation, int64_t dsb, int64_t dsn, int64_t dsc,
+                     const float* source, int64_t ssb, int64_t ssn, int64_t ssc,
+                     const int32_t* neighbour_idx, int G, int B, int V, int n,
+                     const float* group_weight, float coef, float* loss, float* grad_deformation, void* stream);
+
+/* Per-view depth comparison of loss_on_depth (model/loss.py:169-181) over n pixels (all views and batch elements):
+ *   ori = ori_depth / ori_weight, tar = tar_depth / tar_weight, dis = |ori - tar|,
+ *   mask = sign(ori * tar) * [dis <= dis_threshold],   *loss += coef * sum mask * dis^2,
+ * and (when non-NULL) grad_ori_depth / grad_ori_weight [n] = d loss / d ori_depth, d loss / d ori_weight.
+ * All arrays contiguous and 16-byte aligned; loss [1] must be zeroed by the caller. */
+int rma_depth_view_term(const float* ori_depth, const float* ori_weight, const float* tar_depth,
+                        const float* tar_weight, int64_t n, float dis_threshold, float coef, float* loss,
+                        float* grad_ori_depth, float* grad_ori_weight, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Host-buffer convenience entry (what a non-torch FFI binding would call): pageable or pinned HOST pointers,
  * contiguous [B,N,3] / [B,M,3]; allocates device memory, copies in, runs forward (+ backward of
  * loss_on_cd = 0.5 (sum dist1 + sum dist2) / B, loss.py:200-205, when grad pointers are non-NULL), copies out and

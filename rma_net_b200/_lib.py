@@ -49,6 +49,9 @@ SIGNATURES = {
     "rma_point_masker_backward_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "rma_point_masker_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, c_size_t, _P]),
     "rma_knn": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "rma_arap_forward": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _P, c_int, c_int, c_int, c_int,
+                                 _P, c_float, _P, _P, _P]),
+    "rma_depth_view_term": (c_int, [_P, _P, _P, _P, _I64, c_float, c_float, _P, _P, _P, _P]),
     "rma_chamfer_loss_host": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
 }
 

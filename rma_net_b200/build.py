@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "librma_b200.so")
-SOURCES = ["chamfer.cu", "chamfer_filter.cu", "se3.cu", "exfunc.cu", "knn.cu"]
+SOURCES = ["chamfer.cu", "chamfer_filter.cu", "se3.cu", "exfunc.cu", "knn.cu", "loss_terms.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "--cudart", "static", "-shared", "-Xcompiler", "-fPIC", "-std=c++17",

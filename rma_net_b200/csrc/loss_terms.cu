@@ -1,0 +1,200 @@
+// As-rigid-as-possible edge-length term of the reference's Loss.forward for B200 (sm_100a) — SURVEY.md §8f rank 3.
+//
+// Replaces, for all T stages of a training step at once, the torch composition of
+//   Loss.loss_on_arap(neighbour_indexes, deformation_p, source_points)      model/loss.py:233-243
+//   and its stage loop with the 10000 / 1000 / 100 stage factors             model/loss.py:334-345
+// which per stage launches two advanced-indexing gathers to [B,V,n,3], ~12 elementwise / reduction kernels and their
+// ~20 autograd kernels.  Here: ONE launch computes
+//     loss = coef * sum_g weight[g] * sum_{v,k} ( sqrt(|d_j - d_v|^2 + 1e-5) - sqrt(|s_j - s_v|^2 + 1e-5) )^2,
+//     j = idx[b,v,k],  g = stage * B + b
+// and, fused, its gradient w.r.t. every deformation point (own part accumulated in registers, neighbour part
+// scattered with red.global.add).  HBM-bound gather work: per (g, v) it reads 12 B own + 12 n B neighbours of the
+// deformation, the same of the source, 4 n B of indices, and updates 12 (n + 1) B of gradient; the neighbour reads
+// hit L2 (the graph is local).  fp32 throughout, sums in the reference's order ((x^2 + y^2) + z^2) + 1e-5.
+#include "common.cuh"
+#include "../../include/rma_b200.h"
+
+namespace rma {
+
+constexpr int kArapThreads = 256;
+
+struct ArapArgs {
+  const float* d; long long dsb, dsn, dsc;     // deformation [G,V,3], element strides
+  const float* s; long long ssb, ssn, ssc;     // source      [B,V,3], element strides
+  const int* idx;                              // [B,V,n] contiguous; entries outside [0,V) are skipped
+  const float* weight;                         // null or [G]
+  float coef;
+  int G, B, V, n;
+  float* loss;                                 // [1], zeroed by the caller; += coef * weight[g] * (block sum)
+  float* grad;                                 // null or [G,V,3] contiguous, zeroed by the caller
+};
+
+__device__ __forceinline__ float edge_len(float ax, float ay, float az, float bx, float by, float bz,
+                                          float& ex, float& ey, float& ez) {
+  ex = ax - bx; ey = ay - by; ez = az - bz;     // neighbour - centre, as the reference subtracts (loss.py:237-238)
+  return sqrtf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)), 0.00001f));
+}
+
+__global__ void __launch_bounds__(kArapThreads) arap_kernel(ArapArgs a) {
+  __shared__ float swarp[kArapThreads / 32];
+  pdl_wait();
+  const int g = blockIdx.y;
+  const int b = g % a.B;
+  const int v = blockIdx.x * kArapThreads + threadIdx.x;
+  const float wg = a.coef * (a.weight ? a.weight[g] : 1.f);
+  float part = 0.f;
+  if (v < a.V) {
+    const float* dp = a.d + g * a.dsb;
+    const float* sp = a.s + b * a.ssb;
+    const float* pd = dp + v * a.dsn;
+    const float* ps = sp + v * a.ssn;
+    const float dvx = pd[0], dvy = pd[a.dsc], dvz = pd[2 * a.dsc];
+    const float svx = ps[0], svy = ps[a.ssc], svz = ps[2 * a.ssc];
+    const int* ip = a.idx + ((long long)b * a.V + v) * a.n;
+    float* gp = a.grad ? a.grad + (long long)g * a.V * 3 : nullptr;
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    for (int k = 0; k < a.n; ++k) {
+      const int j = ip[k];
+      if ((unsigned)j >= (unsigned)a.V) continue;
+      const float* qd = dp + j * a.dsn;
+      const float* qs = sp + j * a.ssn;
+      float ex, ey, ez, fx, fy, fz;
+      const float ld = edge_len(qd[0], qd[a.dsc], qd[2 * a.dsc], dvx, dvy, dvz, ex, ey, ez);
+      const float ls = edge_len(qs[0], qs[a.ssc], qs[2 * a.ssc], svx, svy, svz, fx, fy, fz);
+      const float diff = ld - ls;
+      part = fmaf(diff, diff, part);
+      if (gp) {
+        // d/d(d_j) of wg * diff^2 = 2 wg diff (d_j - d_v) / ld; the centre gets the opposite
+        const float f = 2.f * wg * diff / ld;
+        const float gx = f * ex, gy = f * ey, gz = f * ez;
+        ox -= gx; oy -= gy; oz -= gz;
+        float* t = gp + (long long)j * 3;
+        atomicAdd(t, gx); atomicAdd(t + 1, gy); atomicAdd(t + 2, gz);
+      }
+    }
+    if (gp) {
+      float* t = gp + (long long)v * 3;
+      atomicAdd(t, ox); atomicAdd(t + 1, oy); atomicAdd(t + 2, oz);
+    }
+  }
+  pdl_launch_dependents();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) swarp[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < kArapThreads / 32; ++w) tot += (double)swarp[w];
+    atomicAdd(a.loss, (float)(tot * (double)wg));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-view depth comparison of loss_on_depth (model/loss.py:169-181) as one pass over the four rendered images:
+//   ori = ori_depth / ori_weight, tar = tar_depth / tar_weight, dis = |ori - tar|,
+//   mask = sign(ori * tar) * [dis <= 0.05]  (the reference builds the second factor as
+//          (sign(sign(-1.0 * (dis - 0.05)) + 0.5) + 1.0) * 0.5, which is 1 at dis == 0.05 too),
+//   loss += coef * sum mask * dis^2,   and the gradients w.r.t. ori_depth / ori_weight (mask is detached there).
+// Replaces ~14 elementwise torch kernels forward and as many backward over [views*B, H, W] images: 24 B read + 8 B
+// written per pixel instead of ~200 B.  HBM-bound streaming kernel, 4 pixels per thread (LDG.128 / STG.128).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kDepthThreads = 256;
+
+__device__ __forceinline__ float sign_of(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+
+__device__ __forceinline__ float depth_pixel(float od, float ow, float td, float tw, float thr, float coef,
+                                             float& g_od, float& g_ow) {
+  const float ori = __fdiv_rn(od, ow), tar = __fdiv_rn(td, tw);
+  const float m1 = sign_of(__fmul_rn(ori, tar));
+  const float diff = ori - tar;
+  const float dis = fabsf(diff);
+  const float thres = -1.0f * (dis - thr);
+  const float m2 = (sign_of(sign_of(thres) + 0.5f) + 1.0f) * 0.5f;
+  const float mask = m2 * m1;
+  const float g_ori = coef * mask * 2.f * dis * sign_of(diff);
+  g_od = __fdiv_rn(g_ori, ow);
+  g_ow = __fdiv_rn(-g_ori * od, ow * ow);
+  return mask * (dis * dis);
+}
+
+__global__ void __launch_bounds__(kDepthThreads) depth_view_term_kernel(
+    const float* __restrict__ od, const float* __restrict__ ow, const float* __restrict__ td,
+    const float* __restrict__ tw, long long n, float thr, float coef, float* __restrict__ loss,
+    float* __restrict__ g_od, float* __restrict__ g_ow) {
+  __shared__ float swarp[kDepthThreads / 32];
+  pdl_wait();
+  float part = 0.f;
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * kDepthThreads;
+  for (long long t = (long long)blockIdx.x * kDepthThreads + threadIdx.x; t < n4; t += stride) {
+    const float4 a = reinterpret_cast<const float4*>(od)[t], b = reinterpret_cast<const float4*>(ow)[t];
+    const float4 c = reinterpret_cast<const float4*>(td)[t], d = reinterpret_cast<const float4*>(tw)[t];
+    float4 ga, gb;
+    part += depth_pixel(a.x, b.x, c.x, d.x, thr, coef, ga.x, gb.x);
+    part += depth_pixel(a.y, b.y, c.y, d.y, thr, coef, ga.y, gb.y);
+    part += depth_pixel(a.z, b.z, c.z, d.z, thr, coef, ga.z, gb.z);
+    part += depth_pixel(a.w, b.w, c.w, d.w, thr, coef, ga.w, gb.w);
+    if (g_od) { reinterpret_cast<float4*>(g_od)[t] = ga; reinterpret_cast<float4*>(g_ow)[t] = gb; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) {      // tail pixels
+    const long long t = (n4 << 2) + threadIdx.x;
+    float ga, gb;
+    part += depth_pixel(od[t], ow[t], td[t], tw[t], thr, coef, ga, gb);
+    if (g_od) { g_od[t] = ga; g_ow[t] = gb; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) swarp[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < kDepthThreads / 32; ++w) tot += (double)swarp[w];
+    atomicAdd(loss, (float)(tot * (double)coef));
+  }
+}
+
+}  // namespace rma
+
+using namespace rma;
+
+extern "C" {
+
+int rma_arap_forward(const float* deformation, int64_t dsb, int64_t dsn, int64_t dsc,
+                     const float* source, int64_t ssb, int64_t ssn, int64_t ssc,
+                     const int32_t* neighbour_idx, int G, int B, int V, int n,
+                     const float* group_weight, float coef, float* loss, float* grad_deformation, void* stream_) {
+  if (!deformation || !source || !neighbour_idx || !loss) return RMA_E_BADARG;
+  if (G <= 0 || B <= 0 || V <= 0 || n <= 0 || G % B != 0 || G > 65535) return RMA_E_BADARG;
+  if ((long long)V > (1LL << 30) || (long long)G * V * 3 >= (1LL << 40)) return RMA_E_BADARG;
+  ArapArgs a;
+  a.d = deformation; a.dsb = dsb; a.dsn = dsn; a.dsc = dsc;
+  a.s = source; a.ssb = ssb; a.ssn = ssn; a.ssc = ssc;
+  a.idx = (const int*)neighbour_idx; a.weight = group_weight; a.coef = coef;
+  a.G = G; a.B = B; a.V = V; a.n = n; a.loss = loss; a.grad = grad_deformation;
+  const dim3 grid((unsigned)((V + kArapThreads - 1) / kArapThreads), (unsigned)G);
+  arap_kernel<<<grid, kArapThreads, 0, (cudaStream_t)stream_>>>(a);
+  RMA_LAUNCH_CHECK();
+  return RMA_OK;
+}
+
+int rma_depth_view_term(const float* ori_depth, const float* ori_weight, const float* tar_depth,
+                        const float* tar_weight, int64_t n, float dis_threshold, float coef, float* loss,
+                        float* grad_ori_depth, float* grad_ori_weight, void* stream_) {
+  if (!ori_depth || !ori_weight || !tar_depth || !tar_weight || !loss || n <= 0) return RMA_E_BADARG;
+  if ((grad_ori_depth == nullptr) != (grad_ori_weight == nullptr)) return RMA_E_BADARG;
+  const uintptr_t al = (uintptr_t)ori_depth | (uintptr_t)ori_weight | (uintptr_t)tar_depth | (uintptr_t)tar_weight |
+                       (uintptr_t)grad_ori_depth | (uintptr_t)grad_ori_weight;
+  if (al & 15u) return RMA_E_BADARG;                        // LDG.128 / STG.128
+  long long blocks = ((n >> 2) + kDepthThreads - 1) / kDepthThreads;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  depth_view_term_kernel<<<(unsigned)blocks, kDepthThreads, 0, (cudaStream_t)stream_>>>(
+      ori_depth, ori_weight, tar_depth, tar_weight, (long long)n, dis_threshold, coef, loss, grad_ori_depth,
+      grad_ori_weight);
+  RMA_LAUNCH_CHECK();
+  return RMA_OK;
+}
+
+}  // extern "C"

@@ -101,10 +101,13 @@ def chamfer_backward(points_x, points_y, idx1, idx2, g1, g2, need_x: bool = True
 
 
 def chamfer_cd_forward(points_x: torch.Tensor, points_y: torch.Tensor, need_x: bool, need_y: bool,
-                       batch_weight: Optional[torch.Tensor] = None, coef: Optional[float] = None):
+                       batch_weight: Optional[torch.Tensor] = None, coef: Optional[float] = None,
+                       want_dist: bool = False):
     """Fused loss_on_cd: returns (loss 0-dim, gx_parts, gy_parts); g*_parts = (own [.,.,3], scat [.,.,4]) or None,
     with d loss/d cloud = own + scat[..., :3] (combined and scaled by chamfer_cd_backward).
-    loss = coef * sum_b batch_weight[b] * (sum dist1[b] + sum dist2[b]); defaults: weights 1, coef 0.5 / B."""
+    loss = coef * sum_b batch_weight[b] * (sum dist1[b] + sum dist2[b]); defaults: weights 1, coef 0.5 / B.
+    want_dist=True appends (dist1 [B,N], dist2 [B,M]) — the unweighted distances, for the metric callers
+    (train_view.py:376-380) that would otherwise repeat the forward."""
     _check_points("points_x", points_x)
     _check_points("points_y", points_y)
     _same_device(points_x, points_y)
@@ -124,6 +127,8 @@ def chamfer_cd_forward(points_x: torch.Tensor, points_y: torch.Tensor, need_x: b
         f32 = dict(dtype=torch.float32, device=dev)
         gx = (torch.empty((B, N, 3), **f32), torch.empty((B, N, 4), **f32)) if need_x else None
         gy = (torch.empty((B, M, 3), **f32), torch.empty((B, M, 4), **f32)) if need_y else None
+        d1 = torch.empty((B, N), **f32) if want_dist else None
+        d2 = torch.empty((B, M), **f32) if want_dist else None
         xs, ys = points_x.stride(), points_y.stride()
         if batch_weight is not None:
             if batch_weight.numel() != B or not batch_weight.is_cuda:
@@ -131,11 +136,13 @@ def chamfer_cd_forward(points_x: torch.Tensor, points_y: torch.Tensor, need_x: b
             batch_weight = batch_weight.to(torch.float32).contiguous()
         rc = lib.rma_chamfer_cd_forward_weighted(_ptr(points_x), xs[0], xs[1], xs[2], _ptr(points_y), ys[0], ys[1], ys[2],
                                         B, N, M, _ptr(batch_weight), float(0.5 / B if coef is None else coef),
-                                        _ptr(loss), None, None, None, None,
+                                        _ptr(loss), _ptr(d1), _ptr(d2), None, None,
                                         _ptr(gx[0] if gx else None), _ptr(gx[1] if gx else None),
                                         _ptr(gy[0] if gy else None), _ptr(gy[1] if gy else None),
                                         _ptr(ws), wsb, _stream())
         _lib.check(rc, "rma_chamfer_cd_forward_weighted")
+    if want_dist:
+        return loss, gx, gy, d1, d2
     return loss, gx, gy
 
 
@@ -534,3 +541,60 @@ def knn_indices(queries: torch.Tensor, candidates: torch.Tensor, k: int, skip_fi
                                      B, N, M, k, int(skip_first), _ptr(idx), _ptr(dist), _stream())
             _lib.check(rc, "rma_knn")
     return (idx, dist) if want_dist else idx
+
+
+def arap_forward(deformation: torch.Tensor, source: torch.Tensor, neighbour_idx: torch.Tensor,
+                 group_weight: Optional[torch.Tensor], coef: float, need_grad: bool):
+    """deformation [G,V,3] (G a multiple of B), source [B,V,3] (any strides), neighbour_idx [B,V,n] int32 ->
+    (loss 0-dim, d loss / d deformation [G,V,3] or None); see rma_arap_forward in include/rma_b200.h."""
+    _check_points("deformation", deformation)
+    _check_points("source", source)
+    _same_device(deformation, source)
+    G, V = deformation.shape[0], deformation.shape[1]
+    B = source.shape[0]
+    if B == 0 or G % B != 0 or source.shape[1] != V:
+        raise RuntimeError(f"deformation {tuple(deformation.shape)} does not stack over source {tuple(source.shape)}")
+    if neighbour_idx.dim() != 3 or neighbour_idx.shape[0] != B or neighbour_idx.shape[1] != V:
+        raise RuntimeError(f"neighbour_idx must be [B,V,n], got {tuple(neighbour_idx.shape)}")
+    if not neighbour_idx.is_cuda or neighbour_idx.device != deformation.device:
+        raise RuntimeError("neighbour_idx must be on the same CUDA device as the points")
+    idx = neighbour_idx.to(torch.int32).contiguous()
+    n = idx.shape[2]
+    dev = deformation.device
+    if group_weight is not None:
+        if group_weight.numel() != G or not group_weight.is_cuda:
+            raise RuntimeError(f"group_weight must be a CUDA tensor with {G} elements")
+        group_weight = group_weight.to(torch.float32).contiguous()
+    loss = torch.zeros((), dtype=torch.float32, device=dev)
+    grad = torch.zeros((G, V, 3), dtype=torch.float32, device=dev) if need_grad else None
+    if n and V:
+        ds, ss = deformation.stride(), source.stride()
+        with torch.cuda.device(dev):
+            rc = _lib.load().rma_arap_forward(_ptr(deformation), ds[0], ds[1], ds[2], _ptr(source), ss[0], ss[1], ss[2],
+                                              _ptr(idx), G, B, V, n, _ptr(group_weight), float(coef), _ptr(loss),
+                                              _ptr(grad), _stream())
+            _lib.check(rc, "rma_arap_forward")
+    return loss, grad
+
+
+def depth_view_term(ori_depth: torch.Tensor, ori_weight: torch.Tensor, tar_depth: torch.Tensor,
+                    tar_weight: torch.Tensor, dis_threshold: float, coef: float, need_grad: bool):
+    """Rendered images [*,H,W,1] x 4 -> (loss 0-dim, (d loss / d ori_depth, d loss / d ori_weight) or None);
+    see rma_depth_view_term in include/rma_b200.h."""
+    imgs = [ori_depth, ori_weight, tar_depth, tar_weight]
+    for t in imgs:
+        if not t.is_cuda or t.dtype != torch.float32 or t.shape != ori_depth.shape:
+            raise RuntimeError("depth_view_term: four float32 CUDA images of one shape expected")
+    imgs = [t.contiguous() for t in imgs]
+    dev = ori_depth.device
+    n = ori_depth.numel()
+    loss = torch.zeros((), dtype=torch.float32, device=dev)
+    grads = (torch.empty_like(imgs[0]), torch.empty_like(imgs[1])) if need_grad else None
+    if n:
+        with torch.cuda.device(dev):
+            rc = _lib.load().rma_depth_view_term(_ptr(imgs[0]), _ptr(imgs[1]), _ptr(imgs[2]), _ptr(imgs[3]), n,
+                                                 float(dis_threshold), float(coef), _ptr(loss),
+                                                 _ptr(grads[0] if grads else None), _ptr(grads[1] if grads else None),
+                                                 _stream())
+            _lib.check(rc, "rma_depth_view_term")
+    return loss, grads

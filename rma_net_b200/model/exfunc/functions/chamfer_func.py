@@ -48,6 +48,67 @@ class ChamferCDFunction(torch.autograd.Function):
         return ext.chamfer_cd_backward(gx, gy, grad_loss) + (None, None)
 
 
+class ChamferCDMetricsFunction(torch.autograd.Function):
+    """ChamferCDFunction that also hands back the unweighted dist1 [B,N] / dist2 [B,M] of the same forward
+    (non-differentiable), so that the metric callers (reference train_view.py:376-380) do not repeat the search."""
+
+    @staticmethod
+    def forward(ctx, deformation_p, p1, batch_weight=None, coef=None):
+        need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        loss, gx, gy, d1, d2 = ext.chamfer_cd_forward(deformation_p, p1, need_x, need_y, batch_weight, coef,
+                                                      want_dist=True)
+        ctx.has = (gx is not None, gy is not None)
+        ctx.save_for_backward(*[t for pair in (gx, gy) if pair is not None for t in pair])
+        ctx.mark_non_differentiable(d1, d2)
+        return loss, d1, d2
+
+    @staticmethod
+    def backward(ctx, grad_loss, _d1, _d2):
+        return ChamferCDFunction.backward(ctx, grad_loss)
+
+
+class ArapFunction(torch.autograd.Function):
+    """Edge-length (ARAP) term of Loss.forward for any number of stacked stages (reference model/loss.py:233-243,
+    334-345): forward(deformation [G,V,3], source [B,V,3], neighbour_idx [B,V,n] int32, group_weight [G] | None,
+    coef) -> scalar; the gradient w.r.t. the deformation comes out of the same launch."""
+
+    @staticmethod
+    def forward(ctx, deformation, source_points, neighbour_idx, group_weight=None, coef=1.0):
+        if ctx.needs_input_grad[1]:
+            raise RuntimeError("ArapFunction: no gradient w.r.t. source_points (it is input data in the reference)")
+        loss, grad = ext.arap_forward(deformation, source_points, neighbour_idx, group_weight, float(coef),
+                                      ctx.needs_input_grad[0])
+        ctx.save_for_backward(*([grad] if grad is not None else []))
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        if not ctx.saved_tensors:
+            return None, None, None, None, None
+        return ctx.saved_tensors[0] * grad_loss, None, None, None, None
+
+
+class DepthViewTermFunction(torch.autograd.Function):
+    """sum(mask * dis^2) of loss_on_depth (reference model/loss.py:169-181) from the four rendered images, with the
+    gradients w.r.t. the deformation's depth / weight images out of the same pass; the target images get none."""
+
+    @staticmethod
+    def forward(ctx, ori_depth, ori_weight, tar_depth, tar_weight, coef=1.0, dis_threshold=0.05):
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            raise RuntimeError("DepthViewTermFunction: no gradient w.r.t. the target images")
+        loss, grads = ext.depth_view_term(ori_depth, ori_weight, tar_depth, tar_weight, dis_threshold, coef,
+                                          ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        ctx.save_for_backward(*(grads or ()))
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        if not ctx.saved_tensors:
+            return None, None, None, None, None, None
+        g_od, g_ow = ctx.saved_tensors
+        return g_od * grad_loss, g_ow * grad_loss, None, None, None, None
+
+
 class Chamfer(torch.nn.Module):
     """forward(points_x [B,M,3], points_y [B,N,3]) -> (dist1 [B,M], dist2 [B,N], idx1, idx2)."""
 

@@ -9,15 +9,25 @@
                          loss.py:73-95, 135-141, 147-196  the multi-view depth / mask losses on top of Render / Masker
     get_neighbor_index   loss.py:99-110    ARAP neighbour graph: the n nearest OTHER vertices -> [B,V,n] (int64)
     indexing_neighbor    loss.py:113-120   gather by that index (torch)
+    loss_on_pd / loss_on_sparse / loss_on_tran / loss_on_arap
+                         loss.py:207-243   the other terms (arap = one fused CUDA launch, the rest torch one-liners)
+    Loss                 loss.py:122-355   the module: same constructor argument (args), same forward signature and
+                                           return value (loss, loss_stages); fused=True runs every term once over
+                                           the stacked [T*B,N,3] stage outputs instead of T times
+    stage_chamfer_errors train_view.py:376-380  per-stage metric from the dists of the training forward
 
 Differences from the reference that a caller can observe: distances are evaluated in fp32
 difference form (accurate to ~2e-7 relative) instead of the expanded |x|^2+|y|^2-2x.y form (1e-2..1e-5), so they
 are never negative; CPU tensors raise instead of running.
 """
+import math
+import random
+
 import torch
 
 from .. import ext
-from .exfunc.functions.chamfer_func import ChamferCDFunction, ChamferFunction
+from .exfunc.functions.chamfer_func import (ArapFunction, ChamferCDFunction, ChamferCDMetricsFunction,
+                                            ChamferFunction)
 
 
 def compute_sqrdis_map(points_x, points_y):
@@ -61,29 +71,47 @@ def loss_cd_stages(deformation_points_list, target_points, gamma=0.8, weight_cd=
     return loss_cd * weight_cd
 
 
-def loss_cd_stages_fused(deformation_points_list, target_points, gamma=0.8, weight_cd=1.0):
+def stack_stages(deformation_points_list):
+    """T stage outputs [B,3,N] (as the network returns them) -> one contiguous [T,B,N,3] tensor."""
+    return torch.stack([d.transpose(1, 2) for d in deformation_points_list], 0)
+
+
+def loss_cd_stages_fused(deformation_points_list, target_points, gamma=0.8, weight_cd=1.0, return_dist=False,
+                         stacked=None):
     """The same value and gradients as loss_cd_stages, with all T stages in ONE chamfer call: the stage outputs are
     stacked into a [T*B,N,3] batch, the target is repeated, and the stage weights gamma^(T-i-1) * weight_cd enter the
-    fused kernel as per-batch-element weights (rma_chamfer_cd_forward_weighted).  4 launches instead of 4*T."""
-    iter_time = len(deformation_points_list)
+    fused kernel as per-batch-element weights (rma_chamfer_cd_forward_weighted).  4 launches instead of 4*T.
+    return_dist=True -> (loss, dist1 [T,B,N], dist2 [T,B,M]): the unweighted distances of the same forward, for
+    stage_chamfer_errors.  stacked: the [T,B,N,3] tensor of stack_stages, if the caller already has it."""
+    iter_time = len(deformation_points_list) if stacked is None else stacked.shape[0]
     B = target_points.shape[0]
-    x_all = torch.stack([d.transpose(1, 2) for d in deformation_points_list], 0)
+    x_all = stack_stages(deformation_points_list) if stacked is None else stacked
     x_all = x_all.reshape(iter_time * B, x_all.shape[2], 3)
     y_all = target_points.unsqueeze(0).expand(iter_time, -1, -1, -1).reshape(iter_time * B, target_points.shape[1], 3)
-    return ChamferCDFunction.apply(x_all, y_all, _stage_weights(iter_time, B, float(gamma), float(weight_cd),
-                                                              target_points.device), 0.5 / B)
+    w = _stage_weights(iter_time, B, float(gamma), float(weight_cd), target_points.device)
+    if not return_dist:
+        return ChamferCDFunction.apply(x_all, y_all, w, 0.5 / B)
+    loss, d1, d2 = ChamferCDMetricsFunction.apply(x_all, y_all, w, 0.5 / B)
+    return loss, d1.view(iter_time, B, -1), d2.view(iter_time, B, -1)
+
+
+def stage_chamfer_errors(dist1, dist2):
+    """[T,B,N], [T,B,N] -> [T] device tensor: mean(dist1 + dist2) * 0.5 per stage — the `cd_list` metric of
+    train_view.py:376-380 (which calls chamfer_dist(target, deformation_i) again under no_grad; the sum is symmetric
+    in the two directions, so the dists of the training forward give the same numbers).  One .tolist() reads all T."""
+    return (dist1 + dist2).mean(dim=(1, 2)) * 0.5
 
 
 _STAGE_WEIGHTS = {}
 
 
-def _stage_weights(iter_time, B, gamma, weight_cd, device):
-    """[T*B] device vector weight_cd * gamma^(T-i-1), cached: building it costs a synchronous H2D copy."""
-    key = (iter_time, B, gamma, weight_cd, str(device))
+def _stage_weights(iter_time, B, gamma, weight_cd, device, factors=None):
+    """[T*B] device vector weight_cd * gamma^(T-i-1) (* factors[i]), cached: building it costs a synchronous H2D copy."""
+    key = (iter_time, B, gamma, weight_cd, str(device), factors)
     w = _STAGE_WEIGHTS.get(key)
     if w is None:
-        w = torch.tensor([weight_cd * gamma ** (iter_time - i - 1) for i in range(iter_time)],
-                         dtype=torch.float32).repeat_interleave(B).to(device)
+        w = torch.tensor([weight_cd * gamma ** (iter_time - i - 1) * (factors[i] if factors else 1.0)
+                          for i in range(iter_time)], dtype=torch.float32).repeat_interleave(B).to(device)
         if len(_STAGE_WEIGHTS) > 64:
             _STAGE_WEIGHTS.clear()
         _STAGE_WEIGHTS[key] = w
@@ -103,6 +131,54 @@ def indexing_neighbor(tensor, index):
     bs = index.size(0)
     id_0 = torch.arange(bs, device=tensor.device).view(-1, 1, 1)
     return tensor[id_0, index]
+
+
+def loss_on_pd(deformation_p, p1):
+    """point-to-point L2 term, sum((deformation - target)^2) / B   (loss.py:207-212)"""
+    dist = deformation_p - p1
+    return torch.sum(torch.mul(dist, dist)) / deformation_p.size()[0]
+
+
+def loss_on_sparse(point_weight):
+    """mean |point_weight|   (loss.py:217-220)"""
+    return torch.mean(torch.abs(point_weight))
+
+
+def loss_on_tran(rigid_matrix, trans_mask=None):
+    """sum of the squared translation column of the [B,4,4] matrices / B   (loss.py:224-230, mask of loss.py:134-135)"""
+    t = rigid_matrix[:, 0:3, 3] if trans_mask is None else torch.mul(trans_mask.expand(rigid_matrix.size()[0], -1, -1),
+                                                                     rigid_matrix)
+    return torch.sum(torch.mul(t, t)) / rigid_matrix.size()[0]
+
+
+def loss_on_arap(neighbour_indexes, deformation_p, source_points):
+    """sum over vertices and neighbours of (|edge| after - |edge| before)^2 / B, |e| = sqrt(e.e + 1e-5)
+    (loss.py:233-243) as one fused launch (ArapFunction); neighbour_indexes [B,V,n] int32 or int64."""
+    return ArapFunction.apply(deformation_p, source_points, neighbour_indexes, None,
+                              1.0 / deformation_p.size()[0])
+
+
+def arap_stage_factor(i):
+    """the hard-wired stage factors of loss.py:337-343"""
+    return 10000.0 if i <= 1 else (1000.0 if i <= 3 else 100.0)
+
+
+def loss_arap_stages(neighbour_indexes, deformation_points_list, source_points, gamma=0.8):
+    """the stage loop of loss.py:334-345, one loss_on_arap per stage"""
+    iter_time = len(deformation_points_list)
+    out = 0
+    for i in range(iter_time):
+        out = out + arap_stage_factor(i) * gamma ** (iter_time - i - 1) * loss_on_arap(
+            neighbour_indexes, deformation_points_list[i].transpose(1, 2), source_points)
+    return out
+
+
+def loss_arap_stages_fused(neighbour_indexes, deformation_points_list, source_points, gamma=0.8, stacked=None):
+    """the same value and gradients as loss_arap_stages in ONE launch over the stacked [T*B,V,3] stage outputs"""
+    x_all = stack_stages(deformation_points_list) if stacked is None else stacked
+    T, B = x_all.shape[0], x_all.shape[1]
+    w = _stage_weights(T, B, float(gamma), 1.0, x_all.device, tuple(arap_stage_factor(i) for i in range(T)))
+    return ArapFunction.apply(x_all.reshape(T * B, x_all.shape[2], 3), source_points, neighbour_indexes, w, 1.0 / B)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -154,11 +230,12 @@ def _views_to_batch(points, all_rot):
 
 
 def loss_on_depth(deformation_p, p1, all_rot, renderer=None, threshold=threshold_, resolution=resolution_,
-                  batched=True):
+                  batched=True, fused_compare=True):
     """loss.py:147-183 without the in-place re-sampling of the views (pass them in: view_rotations(..., jitter)).
     batched=True folds the V views into the batch dimension: 2 Render calls instead of 2V, same value and gradient
-    (up to fp32 summation order); batched=False is the reference's literal per-view loop."""
-    from .exfunc.functions import Render
+    (up to fp32 summation order); batched=False is the reference's literal per-view loop.  fused_compare=True runs
+    the image comparison (loss.py:169-181) as one kernel (DepthViewTermFunction) instead of ~14 torch kernels."""
+    from .exfunc.functions import DepthViewTermFunction, Render
     renderer = renderer or Render(resolution, resolution, 7, 9, 1e-5)            # loss.py:34
 
     def project(pv):           # loss.py:166: xy -> pixels, z - 1
@@ -167,6 +244,8 @@ def loss_on_depth(deformation_p, p1, all_rot, renderer=None, threshold=threshold
     def view_term(ori_proj, tar_proj):                                           # loss.py:169-181
         od, ow, _ = renderer(ori_proj, threshold)
         td, tw, _ = renderer(tar_proj, threshold)
+        if fused_compare and not ((td.requires_grad or tw.requires_grad) and torch.is_grad_enabled()):
+            return DepthViewTermFunction.apply(od, ow, td, tw, 1.0, 0.05)
         ori_img, tar_img = od / ow, td / tw
         mask = torch.sign(ori_img * tar_img).detach()
         dis = torch.abs(ori_img - tar_img)
@@ -213,3 +292,180 @@ def loss_on_mask(deformation_p, p1, all_rot, masker=None, threshold=threshold_2_
         out = out + torch.mean(torch.abs(masker(project(dv[:, :, 3 * v:3 * v + 3]), threshold)
                                          - masker(project(tv[:, :, 3 * v:3 * v + 3]), threshold))) / V
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the Loss module (loss.py:122-355): same constructor argument, forward signature and return value
+# ------------------------------------------------------------------------------------------------------------
+def sample_view_angles(view_divide, jitter=True, rng=random):
+    """The view_divide^2 Euler angle triples in host double precision, exactly as the reference computes them:
+    the regular grid of Loss.__init__ (loss.py:137-140) or, with jitter, the re-sampled grid of loss_on_depth
+    (loss.py:152-158), drawing rng.random() twice per view in the reference's order (x, then y)."""
+    out = []
+    for view_id in range(view_divide ** 2):
+        euler_x = view_id // view_divide
+        euler_y = view_id - euler_x * view_divide
+        rx = rng.random() if jitter else 0.0
+        ry = rng.random() if jitter else 0.0
+        out.append([-math.pi + 2 * math.pi * (euler_x + rx) / view_divide,
+                    -math.pi + 2 * math.pi * (euler_y + ry) / view_divide, 0.0])
+    return out
+
+
+def rotations_from_angles(angles, device):
+    """[V][3] host angles -> [3V,3] stacked rotations on the device (one H2D copy, one batched euler2rot)."""
+    return euler2rot(torch.tensor(angles, dtype=torch.float32).to(device)).reshape(-1, 3)
+
+
+class Loss(torch.nn.Module):
+    """Drop-in for the reference's `Loss(args)` (model/loss.py:122-355).  args needs weight_cd, weight_pd,
+    weight_sparse, weight_depth, weight_tran, weight_mask, weight_arap, gamma, neighbour_num, view_divide
+    (utils/config.py:41-92, 128).  forward(phi_list, point_weight_list, deform_rigid_points_list,
+    deformation_points_list, rigid_matrix_list, source_points, target_points) -> (loss, loss_stages) with
+    loss_stages = [cd, pd, sparse, depth, tran, mask, arap] (a zero tensor where the weight is not positive).
+
+    fused=True (default): the T stage outputs are stacked once into [T,B,N,3]; cd and arap each run as ONE weighted
+    call over the T*B batch, pd / sparse / tran as one stacked torch expression, depth / mask per stage with the V
+    views folded into the batch.  fused=False is the reference's literal per-stage loop on the same kernels.
+    After forward, `self.last_stage_dists` holds (dist1 [T,B,N], dist2 [T,B,M]) of the cd term (fused path, cd on) for
+    stage_chamfer_errors.  Unlike the reference the module does not pin itself to cuda:0 (loss.py:134-141): buffers
+    follow `device` (default: the current CUDA device)."""
+
+    def __init__(self, args, device=None, fused=True, rng=random):
+        super().__init__()
+        self.args = args
+        self.fused = fused
+        self.rng = rng
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        trans_mask = torch.zeros([1, 4, 4], dtype=torch.float32, device=device)
+        trans_mask[:, 0:3, 3] += 1.0
+        self.register_buffer("trans_mask", trans_mask, persistent=False)
+        self.all_rot_matrix_for_lfd = rotations_from_angles(sample_view_angles(args.view_divide, jitter=False), device)
+        self.last_stage_dists = None
+        self._renderer = None
+        self._masker = None
+
+    # ---- per-term methods, reference names ------------------------------------------------------------------
+    def loss_on_cd(self, deformation_p, p1):
+        return loss_on_cd(deformation_p, p1)
+
+    def loss_on_pd(self, deformation_p, p1):
+        return loss_on_pd(deformation_p, p1)
+
+    def loss_on_sparse(self, point_weight):
+        return loss_on_sparse(point_weight)
+
+    def loss_on_tran(self, rigid_matrix):
+        return loss_on_tran(rigid_matrix, self.trans_mask)
+
+    def loss_on_arap(self, neighbour_indexes, deformation_p, source_points):
+        return loss_on_arap(neighbour_indexes, deformation_p, source_points)
+
+    def loss_on_depth(self, deformation_p, p1):
+        """re-samples the views (loss.py:151-159), then the batched-view depth term"""
+        from .exfunc.functions import Render
+        self.all_rot_matrix_for_lfd = rotations_from_angles(
+            sample_view_angles(self.args.view_divide, jitter=True, rng=self.rng), deformation_p.device)
+        if self._renderer is None:
+            self._renderer = Render(resolution_, resolution_, 7, 9, 1e-5)
+        return loss_on_depth(deformation_p, p1, self.all_rot_matrix_for_lfd, self._renderer)
+
+    def loss_on_mask(self, deformation_p, p1):
+        from .exfunc.functions import Masker
+        if self._masker is None:
+            self._masker = Masker(resolution_, resolution_, 5, 1e-5)
+        return loss_on_mask(deformation_p, p1, self.all_rot_matrix_for_lfd.to(deformation_p.device), self._masker)
+
+    # ---- forward ---------------------------------------------------------------------------------------------
+    def forward(self, phi_list, point_weight_list, deform_rigid_points_list, deformation_points_list,
+                rigid_matrix_list, source_points, target_points):
+        a = self.args
+        iter_time = len(phi_list)
+        dev = phi_list[0].device
+        B = phi_list[0].size()[0]
+        gam = [a.gamma ** (iter_time - i - 1) for i in range(iter_time)]
+        zero_tensor = torch.zeros((), dtype=torch.float, device=dev)
+        loss = torch.zeros((), dtype=torch.float, device=dev)
+        loss_stages = []
+        fused = self.fused
+        stacked = stack_stages(deformation_points_list) if fused else None          # [T,B,N,3]
+        stage = [d.transpose(1, 2) for d in deformation_points_list]
+        self.last_stage_dists = None
+
+        def stage_vec():
+            return _stage_weights(iter_time, 1, float(a.gamma), 1.0, dev)              # [T]
+
+        neighbour_indexes_ = None
+        if a.weight_arap > 0:                                                        # loss.py:253 (always, there)
+            neighbour_indexes_ = ext.knn_indices(source_points.detach(), source_points.detach(),
+                                                 a.neighbour_num + 1, skip_first=1)
+
+        if a.weight_cd > 0:                                                          # loss.py:260-268
+            if fused:
+                loss_cd, d1, d2 = loss_cd_stages_fused(None, target_points, a.gamma, 1.0, return_dist=True,
+                                                       stacked=stacked)
+                self.last_stage_dists = (d1, d2)
+            else:
+                loss_cd = sum(gam[i] * self.loss_on_cd(stage[i], target_points) for i in range(iter_time))
+            loss = loss + loss_cd * a.weight_cd
+            loss_stages.append(loss_cd)
+        else:
+            loss_stages.append(zero_tensor)
+
+        if a.weight_pd > 0:                                                          # loss.py:272-284
+            if fused:
+                diff = stacked - target_points.unsqueeze(0)
+                loss_pd = torch.mul(diff, diff).sum(dim=(1, 2, 3)).dot(stage_vec()) / B
+            else:
+                loss_pd = sum(gam[i] * self.loss_on_pd(stage[i], target_points) for i in range(iter_time))
+            loss = loss + loss_pd * a.weight_pd
+            loss_stages.append(loss_pd)
+        else:
+            loss_stages.append(zero_tensor)
+
+        if a.weight_sparse > 0:                                                      # loss.py:289-298
+            if fused:
+                loss_sparse = torch.stack(list(point_weight_list), 0).abs().flatten(1).mean(dim=1).dot(stage_vec())
+            else:
+                loss_sparse = sum(gam[i] * self.loss_on_sparse(point_weight_list[i]) for i in range(iter_time))
+            loss = loss + loss_sparse * a.weight_sparse
+            loss_stages.append(loss_sparse)
+        else:
+            loss_stages.append(zero_tensor)
+
+        if a.weight_depth > 0:                                                       # loss.py:300-308
+            loss_depth = sum(gam[i] * self.loss_on_depth(stage[i], target_points) for i in range(iter_time))
+            loss = loss + loss_depth * a.weight_depth
+            loss_stages.append(loss_depth)
+        else:
+            loss_stages.append(zero_tensor)
+
+        if a.weight_tran > 0:                                                        # loss.py:311-319
+            if fused:
+                t = torch.stack(list(rigid_matrix_list), 0)[:, :, 0:3, 3]
+                loss_tran = torch.mul(t, t).sum(dim=(1, 2)).dot(stage_vec()) / B
+            else:
+                loss_tran = sum(gam[i] * self.loss_on_tran(rigid_matrix_list[i]) for i in range(iter_time))
+            loss = loss + loss_tran * a.weight_tran
+            loss_stages.append(loss_tran)
+        else:
+            loss_stages.append(zero_tensor)
+
+        if a.weight_mask > 0:                                                        # loss.py:321-330
+            loss_mask = sum(gam[i] * self.loss_on_mask(stage[i], target_points) for i in range(iter_time))
+            loss = loss + loss_mask * a.weight_mask
+            loss_stages.append(loss_mask)
+        else:
+            loss_stages.append(zero_tensor)
+
+        if a.weight_arap > 0:                                                        # loss.py:333-347
+            if fused:
+                loss_arap = loss_arap_stages_fused(neighbour_indexes_, None, source_points, a.gamma, stacked=stacked)
+            else:
+                loss_arap = loss_arap_stages(neighbour_indexes_, deformation_points_list, source_points, a.gamma)
+            loss = loss + loss_arap * a.weight_arap
+            loss_stages.append(loss_arap)
+        else:
+            loss_stages.append(zero_tensor)
+
+        return loss, loss_stages
