@@ -46,69 +46,93 @@ __global__ void __launch_bounds__(256) render_init_kernel(float* __restrict__ fr
   }
 }
 
+// The three splatting kernels below run one thread per (point, patch pixel): lanes hit consecutive pixels, so the L2
+// reductions of a patch row share sectors.  Index arithmetic is 32-bit inside a batch element (blockIdx.y walks the
+// batch) and the patch width is a compile-time constant for the widths the reference uses (5, 7, 9; PW = 0 = any):
+// a 64-bit `t / patch_area` is an emulated ~100-instruction division, which alone made these kernels twice as slow as
+// their reduction traffic (tools/red_v2_microbench.cu).
+template <int PW>
+__device__ __forceinline__ void patch_split(unsigned t, int pw_runtime, unsigned& pt, int& j, int& i) {
+  const unsigned pw = PW ? (unsigned)PW : (unsigned)pw_runtime;
+  pt = t / (pw * pw);
+  const unsigned k = t - pt * (pw * pw);
+  j = (int)(k / pw);
+  i = (int)(k - (unsigned)j * pw);
+}
+
 // visibility_kernel1 (point_render_cuda.cu:30-84): nearest / farthest z over every point whose visible patch covers
-// the pixel.  One thread per (point, patch pixel).
+// the pixel.
+template <int PW>
 __global__ void __launch_bounds__(256) render_visibility_kernel(const float* __restrict__ proj, float* __restrict__ front,
-                                                                float* __restrict__ back, long long npoints,
-                                                                int N, int H, int W, int vpw) {
+                                                                float* __restrict__ back, int B, int N, int H, int W,
+                                                                int vpw_runtime) {
   pdl_wait();
-  const int vp2 = vpw * vpw;
-  const long long total = npoints * vp2;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const long long pt = t / vp2;
-    const int k = (int)(t - pt * vp2), j = k / vpw, i = k - j * vpw;
-    const float* p = proj + pt * 3;
-    const int x = pixel_of(p[0], W) - (vpw - 1) / 2 + i, y = pixel_of(p[1], H) - (vpw - 1) / 2 + j;
-    if (x >= 0 && x < W && y >= 0 && y < H) {
-      const long long o = (pt / N) * (long long)H * W + (long long)y * W + x;
-      const float z = p[2];
-      atomic_min_float(front + o, z);
-      atomic_max_float(back + o, z);
+  const int vpw = PW ? PW : vpw_runtime;
+  const unsigned total = (unsigned)N * (unsigned)(vpw * vpw);
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    const float* pb = proj + (size_t)b * N * 3;
+    float* fb = front + (size_t)b * H * W;
+    float* bb = back + (size_t)b * H * W;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+      unsigned pt; int j, i;
+      patch_split<PW>(t, vpw, pt, j, i);
+      const float* p = pb + pt * 3u;
+      const int x = pixel_of(p[0], W) - (vpw - 1) / 2 + i, y = pixel_of(p[1], H) - (vpw - 1) / 2 + j;
+      if (x >= 0 && x < W && y >= 0 && y < H) {
+        const int o = y * W + x;
+        const float z = p[2];
+        atomic_min_float(fb + o, z);
+        atomic_max_float(bb + o, z);
+      }
     }
   }
 }
 
 // visibility_kernel2 + Rasterize_kernel1 + Rasterize_kernel2 (point_render_cuda.cu:86-227) in one pass.
-// One thread per (point, colour patch pixel); the point's visibility test is evaluated by each of its threads
-// (two cached loads) instead of in a separate launch.
+// The point's visibility test is evaluated by each of its threads (two cached loads) instead of in a separate launch.
+template <int PW>
 __global__ void __launch_bounds__(256) render_raster_kernel(const float* __restrict__ proj, const float* __restrict__ front,
                                                             const float* __restrict__ back, int* __restrict__ pixel_index,
                                                             int* __restrict__ is_visible, float* __restrict__ weight_points,
                                                             float* __restrict__ depth, float* __restrict__ weight,
-                                                            long long npoints, int N, int H, int W, int cpw,
+                                                            int B, int N, int H, int W, int cpw_runtime,
                                                             float threshold) {
   pdl_wait();
-  const int cp2 = cpw * cpw;
-  const long long total = npoints * cp2;
+  const int cpw = PW ? PW : cpw_runtime;
+  const unsigned cp2 = (unsigned)(cpw * cpw);
+  const unsigned total = (unsigned)N * cp2;
   const float distance_divisor = float(((cpw + 1) / 2) * ((cpw + 1) / 2));
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const long long pt = t / cp2;
-    const int k = (int)(t - pt * cp2), j = k / cpw, i = k - j * cpw;
-    const float* p = proj + pt * 3;
-    const float project_x = p[0], project_y = p[1], z = p[2];
-    const int id_x = pixel_of(project_x, W), id_y = pixel_of(project_y, H);
-    const long long img = (pt / N) * (long long)H * W;
-    const long long c = img + (long long)id_y * W + id_x;
-    const float f = front[c], bk = back[c];
-    // :110-111 — hidden if behind the middle of the local depth range and more than `threshold` behind the front
-    // (the reference's `* 0.5` promotes to double; halving is exact in fp32 too, so the comparison is the same)
-    const bool visible = !(z > ((f + bk) * 0.5f) && z > (f + threshold));
-    if (k == 0) {
-      pixel_index[pt * 2] = id_x; pixel_index[pt * 2 + 1] = id_y;
-      is_visible[pt] = visible ? 1 : 0;
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    const size_t img = (size_t)b * H * W, pts = (size_t)b * N;
+    const float* pb = proj + pts * 3;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+      unsigned pt; int j, i;
+      patch_split<PW>(t, cpw, pt, j, i);
+      const float* p = pb + pt * 3u;
+      const float project_x = p[0], project_y = p[1], z = p[2];
+      const int id_x = pixel_of(project_x, W), id_y = pixel_of(project_y, H);
+      const int c = id_y * W + id_x;
+      const float f = front[img + c], bk = back[img + c];
+      // :110-111 — hidden if behind the middle of the local depth range and more than `threshold` behind the front
+      // (the reference's `* 0.5` promotes to double; halving is exact in fp32 too, so the comparison is the same)
+      const bool visible = !(z > ((f + bk) * 0.5f) && z > (f + threshold));
+      if (i == 0 && j == 0) {
+        pixel_index[(pts + pt) * 2] = id_x; pixel_index[(pts + pt) * 2 + 1] = id_y;
+        is_visible[pts + pt] = visible ? 1 : 0;
+      }
+      const int current_x = id_x - (cpw - 1) / 2 + i, current_y = id_y - (cpw - 1) / 2 + j;
+      float g = 0.f;
+      if (visible && current_x >= 0 && current_x < W && current_y >= 0 && current_y < H) {
+        const float center_x = float(2 * current_x + 1) * 0.5f, center_y = float(2 * current_y + 1) * 0.5f;   // :159-160 (exact)
+        const float distance = (project_x - center_x) * (project_x - center_x) +
+                               (project_y - center_y) * (project_y - center_y);                            // :161
+        g = expf(-distance / distance_divisor);                                                             // :162
+        const size_t o = img + (size_t)(current_y * W + current_x);
+        atomicAdd(weight + o, g);                                                                           // :164
+        atomicAdd(depth + o, g * z);                                                                        // :222
+      }
+      if (weight_points) weight_points[pts * cp2 + t] = g;   // zero outside the image / for hidden points (point_render.cpp:86)
     }
-    const int current_x = id_x - (cpw - 1) / 2 + i, current_y = id_y - (cpw - 1) / 2 + j;
-    float g = 0.f;
-    if (visible && current_x >= 0 && current_x < W && current_y >= 0 && current_y < H) {
-      const float center_x = float(2 * current_x + 1) * 0.5f, center_y = float(2 * current_y + 1) * 0.5f;   // :159-160 (exact)
-      const float distance = (project_x - center_x) * (project_x - center_x) +
-                             (project_y - center_y) * (project_y - center_y);                            // :161
-      g = expf(-distance / distance_divisor);                                                             // :162
-      const long long o = img + (long long)current_y * W + current_x;
-      atomicAdd(weight + o, g);                                                                           // :164
-      atomicAdd(depth + o, g * z);                                                                        // :222
-    }
-    if (weight_points) weight_points[t] = g;     // zero outside the image / for hidden points (point_render.cpp:86)
   }
 }
 
@@ -169,32 +193,45 @@ __global__ void __launch_bounds__(128) render_backward_kernel(const float* __res
 // point_masker
 // ---------------------------------------------------------------------------------------------------------------
 // mask_kernel (point_masker_cuda.cu:4-37): -1 inside every point's patch (the image is zeroed by the caller).
+template <int PW>
 __global__ void __launch_bounds__(256) mask_forward_kernel(const float* __restrict__ proj, float* __restrict__ mask,
-                                                           long long npoints, int N, int H, int W, int mpw) {
+                                                           int B, int N, int H, int W, int mpw_runtime) {
   pdl_wait();
-  const int mp2 = mpw * mpw;
-  const long long total = npoints * mp2;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const long long pt = t / mp2;
-    const int k = (int)(t - pt * mp2), j = k / mpw, i = k - j * mpw;
-    const float* p = proj + pt * 3;
-    const int x = pixel_of(p[0], W) - (mpw - 1) / 2 + i, y = pixel_of(p[1], H) - (mpw - 1) / 2 + j;
-    if (x >= 0 && x < W && y >= 0 && y < H) mask[(pt / N) * (long long)H * W + (long long)y * W + x] = -1.0f;
+  const int mpw = PW ? PW : mpw_runtime;
+  const unsigned total = (unsigned)N * (unsigned)(mpw * mpw);
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    const float* pb = proj + (size_t)b * N * 3;
+    float* mb = mask + (size_t)b * H * W;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+      unsigned pt; int j, i;
+      patch_split<PW>(t, mpw, pt, j, i);
+      const float* p = pb + pt * 3u;
+      const int x = pixel_of(p[0], W) - (mpw - 1) / 2 + i, y = pixel_of(p[1], H) - (mpw - 1) / 2 + j;
+      if (x >= 0 && x < W && y >= 0 && y < H) mb[y * W + x] = -1.0f;
+    }
   }
 }
 
 // mask_backward_kernel (point_masker_cuda.cu:39-88) in three atomic-free stages.
 constexpr int kMaskThreads = 256;
 
-// exp(-d / 1000) for the O(pixels x points) loops of the mask backward: one FMUL + MUFU.EX2 instead of an IEEE divide
-// and the ~10-instruction expf.  Relative error <= |d/1000| * log2(e) * 2^-23 + 2 ulp: below 1e-6 for every term
-// larger than 1e-4 of the largest one - the sums are compared at 1e-5 and the reference accumulates them with atomics
-// in arbitrary order.  (The render kernels keep the exact expf: their outputs are compared bit for bit.)
-__device__ __forceinline__ float mask_gauss(float distance) {
-  return exp2f(distance * (-1.4426950408889634f / 1000.f));   // exp2f lowers to MUFU.EX2 (+ denormal scaling)
+// exp(-d / 1000) for the O(pixels x points) loops of the mask backward.  Both kernels are bound by the MUFU unit
+// (16 ex2 / clk / SM), so everything around the MUFU.EX2 is kept below its 8 issue cycles per warp: coordinates are
+// pre-scaled by k = sqrt(log2(e) / 1000), so that exp(-d / 1000) = ex2(-(dx'^2 + dy'^2)) needs no multiply, and
+// ex2.approx.ftz is issued directly (exp2f adds a range test and two multiplies for results below 2^-126, which are
+// irrelevant next to a sum >= epsilon = 1e-5).  Relative error of a term: 2 ulp (ex2.approx) + 2^-22 |x'| |dx'|
+// (rounding of the scaled coordinates; |x'| <= 9.8 for a 256-pixel image): below 3e-6 for every term larger than
+// e^-4 of the largest one.  The sums are compared at 1e-5 and the reference accumulates them with atomics in
+// arbitrary order.  (The render kernels keep the exact expf: their outputs are compared bit for bit.)
+constexpr float kMaskScale = 0.03798282566f;      // sqrt(1.4426950408889634 / 1000)
+
+__device__ __forceinline__ float ex2_neg(float d) {         // 2^(-d)
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-d));
+  return r;
 }
 
-struct MaskEntry { float cx, cy, g, s; };   // pixel centre, upstream gradient (g / s after stage 2), epsilon + sum_i e_i
+struct MaskEntry { float cx, cy, g, pad; };   // pixel centre * kMaskScale, upstream gradient
 
 // Stage 1: compaction of the pixels with |g| > threshold, in pixel order (deterministic), in two passes over
 // kMaskSegs segments per batch element: a count pass, then every segment writes behind the sum of the counts before it.
@@ -252,7 +289,8 @@ __global__ void __launch_bounds__(256) mask_compact_kernel(const float* __restri
     if (on) {
       const int x = pix % W, y = pix / W;
       MaskEntry e;
-      e.cx = float(2 * x + 1) * 0.5f; e.cy = float(2 * y + 1) * 0.5f; e.g = g; e.s = 0.f;     // :59-60
+      e.cx = float(2 * x + 1) * 0.5f * kMaskScale; e.cy = float(2 * y + 1) * 0.5f * kMaskScale;   // :59-60
+      e.g = g; e.pad = 0.f;
       out[before + __popc(bal & ((1u << lane) - 1u))] = e;
     }
     __syncthreads();
@@ -261,81 +299,110 @@ __global__ void __launch_bounds__(256) mask_compact_kernel(const float* __restri
   }
 }
 
-// Stage 2: one thread per active pixel: s = epsilon + sum_i expf(-d_i / 1000), points in order (:70-78), staged
-// through shared memory.
+// Stage 2: thread = active pixel, split = a contiguous chunk of the points: partial sums of e over the chunk, points
+// staged through shared memory; spart[pixel][split].  (Split over the points because a batch element has only a few
+// thousand active pixels: pixels alone do not fill the machine evenly.)  Each CTA walks the pixel tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ... of its batch element.
+constexpr int kMaskMaxSplits = 8;
+constexpr int kMaskTileCtas = 8;
+
 __global__ void __launch_bounds__(kMaskThreads) mask_norm_kernel(const float* __restrict__ proj, int N, int npix,
-                                                                 float epsilon, MaskEntry* __restrict__ entries,
-                                                                 const int* __restrict__ counts) {
+                                                                 int splits, const MaskEntry* __restrict__ entries,
+                                                                 const int* __restrict__ counts,
+                                                                 float* __restrict__ spart) {
   __shared__ float2 sp[kMaskThreads];
-  const int b = blockIdx.y;
+  const int b = blockIdx.y, split = blockIdx.z;
   const int count = counts[b];
-  if ((int)(blockIdx.x * kMaskThreads) >= count) return;      // block-uniform
-  const int e = blockIdx.x * kMaskThreads + threadIdx.x;
-  MaskEntry* ent = entries + (long long)b * npix + e;
-  const bool on = e < count;
-  const float cx = on ? ent->cx : 0.f, cy = on ? ent->cy : 0.f;
-  float s = epsilon;
+  const int per = (N + splits - 1) / splits;
+  const int ibeg = min(split * per, N), iend = min(ibeg + per, N);
   const float* p = proj + (long long)b * N * 3;
-  for (int i0 = 0; i0 < N; i0 += kMaskThreads) {
-    __syncthreads();
-    if (i0 + (int)threadIdx.x < N) sp[threadIdx.x] = make_float2(p[(i0 + threadIdx.x) * 3], p[(i0 + threadIdx.x) * 3 + 1]);
-    __syncthreads();
-    const int n = min(kMaskThreads, N - i0);
-    for (int i = 0; i < n; ++i) {
-      const float proj_x = sp[i].x, proj_y = sp[i].y;
-      const float distance = (proj_x - cx) * (proj_x - cx) + (proj_y - cy) * (proj_y - cy);
-      s += mask_gauss(distance);
+  for (int tile = blockIdx.x * kMaskThreads; tile < count; tile += gridDim.x * kMaskThreads) {      // block-uniform
+    const int e = tile + threadIdx.x;
+    const bool on = e < count;
+    const MaskEntry* ent = entries + (long long)b * npix + e;
+    const float cx = on ? ent->cx : 0.f, cy = on ? ent->cy : 0.f;
+    float s0 = 0.f, s1 = 0.f;
+    for (int i0 = ibeg; i0 < iend; i0 += kMaskThreads) {
+      __syncthreads();
+      if (i0 + (int)threadIdx.x < iend)
+        sp[threadIdx.x] = make_float2(p[(i0 + threadIdx.x) * 3] * kMaskScale, p[(i0 + threadIdx.x) * 3 + 1] * kMaskScale);
+      __syncthreads();
+      const int n = min(kMaskThreads, iend - i0);
+      int i = 0;
+#pragma unroll 4
+      for (; i + 1 < n; i += 2) {
+        const float4 q = *reinterpret_cast<const float4*>(&sp[i]);
+        const float ax = q.x - cx, ay = q.y - cy, bx = q.z - cx, by = q.w - cy;
+        s0 += ex2_neg(fmaf(ax, ax, ay * ay));
+        s1 += ex2_neg(fmaf(bx, bx, by * by));
+      }
+      if (i < n) { const float ax = sp[i].x - cx, ay = sp[i].y - cy; s0 += ex2_neg(fmaf(ax, ax, ay * ay)); }
     }
+    if (on) spart[((long long)b * npix + e) * kMaskMaxSplits + split] = s0 + s1;
   }
-  if (on) { ent->s = s; ent->g = ent->g / s; }     // g / s once per pixel, for the gather
 }
 
 // Stage 3: gather.  Thread (point i, slice k) accumulates  sum g/s * e  over the k-th slice of the batch element's
 // active pixels, in pixel order; the slices' partial sums are then added in slice order (stage 4), so the result
-// is deterministic.  g/s is formed once per pixel (stage 2), which replaces the reference's per-pair division
-// `g * e / s` (:85) by one multiply-add; the two differ by an ulp per term.
+// is deterministic.  s = epsilon + the split sums of stage 2 (in split order) and g / s are formed once per staged
+// pixel, which replaces the reference's per-pair division `g * e / s` (:85) by one multiply-add; the two differ by an
+// ulp per term.
 constexpr int kMaskSlices = 16;
 
 __global__ void __launch_bounds__(kMaskThreads) mask_gather_kernel(const float* __restrict__ proj, int N, int npix,
+                                                                   int splits, int slices, float epsilon,
                                                                    const MaskEntry* __restrict__ entries,
                                                                    const int* __restrict__ counts,
+                                                                   const float* __restrict__ spart,
                                                                    float* __restrict__ partial) {
-  __shared__ MaskEntry se[kMaskThreads];
+  __shared__ float4 se[kMaskThreads];
   const int b = blockIdx.y, slice = blockIdx.z;
   const int i = blockIdx.x * kMaskThreads + threadIdx.x;
   const bool on = i < N;
   const float* p = proj + ((long long)b * N + (on ? i : 0)) * 3;
-  const float proj_x = p[0], proj_y = p[1];
+  const float proj_x = p[0] * kMaskScale, proj_y = p[1] * kMaskScale;
   const int count = counts[b];
-  const int per = (count + kMaskSlices - 1) / kMaskSlices;
+  const int per = (count + slices - 1) / slices;
   const int begin = min(slice * per, count), end = min(begin + per, count);
   const MaskEntry* ent = entries + (long long)b * npix;
-  float acc = 0.f;
+  float acc0 = 0.f, acc1 = 0.f;
   for (int e0 = begin; e0 < end; e0 += kMaskThreads) {
     __syncthreads();
-    if (e0 + (int)threadIdx.x < end) se[threadIdx.x] = ent[e0 + threadIdx.x];
+    if (e0 + (int)threadIdx.x < end) {
+      const MaskEntry m = ent[e0 + threadIdx.x];
+      const float* sq = spart + ((long long)b * npix + e0 + threadIdx.x) * kMaskMaxSplits;
+      float sum = epsilon;
+      for (int k = 0; k < splits; ++k) sum += sq[k];
+      se[threadIdx.x] = make_float4(m.cx, m.cy, m.g / sum, 0.f);
+    }
     __syncthreads();
     const int n = min(kMaskThreads, end - e0);
+    int k = 0;
 #pragma unroll 4
-    for (int k = 0; k < n; ++k) {
-      const MaskEntry m = se[k];
-      const float distance = (proj_x - m.cx) * (proj_x - m.cx) + (proj_y - m.cy) * (proj_y - m.cy);
-      acc = fmaf(m.g, mask_gauss(distance), acc);        // m.g holds g / s here
+    for (; k + 1 < n; k += 2) {
+      const float4 m0 = se[k], m1 = se[k + 1];
+      const float ax = proj_x - m0.x, ay = proj_y - m0.y, bx = proj_x - m1.x, by = proj_y - m1.y;
+      acc0 = fmaf(m0.z, ex2_neg(fmaf(ax, ax, ay * ay)), acc0);
+      acc1 = fmaf(m1.z, ex2_neg(fmaf(bx, bx, by * by)), acc1);
+    }
+    if (k < n) {
+      const float4 m0 = se[k];
+      const float ax = proj_x - m0.x, ay = proj_y - m0.y;
+      acc0 = fmaf(m0.z, ex2_neg(fmaf(ax, ax, ay * ay)), acc0);
     }
   }
-  if (on) partial[((long long)b * kMaskSlices + slice) * N + i] = acc;
+  if (on) partial[((long long)b * slices + slice) * N + i] = acc0 + acc1;
 }
 
 // Stage 4: grad_z[i] = sum over slices, in slice order; x and y get no gradient (:85 touches only 3*i + 2).
 __global__ void __launch_bounds__(256) mask_reduce_kernel(const float* __restrict__ partial, int N, long long npoints,
-                                                          float* __restrict__ grad_proj) {
+                                                          int slices, float* __restrict__ grad_proj) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= npoints) return;
   const long long b = t / N;
   const int i = (int)(t - b * N);
   float acc = 0.f;
-#pragma unroll
-  for (int k = 0; k < kMaskSlices; ++k) acc += partial[(b * kMaskSlices + k) * N + i];
+  for (int k = 0; k < slices; ++k) acc += partial[(b * slices + k) * N + i];
   grad_proj[t * 3] = 0.f; grad_proj[t * 3 + 1] = 0.f; grad_proj[t * 3 + 2] = acc;
 }
 
@@ -346,8 +413,42 @@ static unsigned capped_grid(long long n, int block, int cap) {
   return (unsigned)g;
 }
 
+// grid of a splatting kernel: x covers the N * pw^2 (point, patch pixel) threads of one batch element, y the batch,
+// about 32 CTAs per SM in total
+static dim3 splat_grid(int B, int N, int pw) {
+  const long long total = (long long)N * pw * pw;
+  const int by = B < 65535 ? B : 65535;
+  long long gx = (total + 255) / 256, cap = (148LL * 32 + by - 1) / by;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)by, 1);
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_grid(void (*kernel)(KArgs...), dim3 grid, unsigned block, cudaStream_t stream,
+                                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// PW-specialised launch of a splatting kernel template (5, 7, 9 are the reference's patch widths, loss.py:34-35)
+#define RMA_SPLAT_LAUNCH(KERNEL, pw, grid, st, ...)                                                       \
+  ((pw) == 5   ? launch_pdl_grid(KERNEL<5>, grid, 256u, st, __VA_ARGS__)                                  \
+   : (pw) == 7 ? launch_pdl_grid(KERNEL<7>, grid, 256u, st, __VA_ARGS__)                                  \
+   : (pw) == 9 ? launch_pdl_grid(KERNEL<9>, grid, 256u, st, __VA_ARGS__)                                  \
+               : launch_pdl_grid(KERNEL<0>, grid, 256u, st, __VA_ARGS__))
+
 static bool render_sizes_ok(int B, int N, int H, int W, int pw) {
   if (B <= 0 || N <= 0 || H <= 0 || W <= 0 || pw <= 0 || pw > 255) return false;
+  if ((long long)N * pw * pw >= (1LL << 31) - (1LL << 24)) return false;   // 32-bit thread index inside a batch element
   if ((long long)B * N >= (1LL << 31) / 3) return false;       // the reference indexes index*3 with int (cuda.cu:38)
   if ((long long)B * H * W >= (1LL << 31)) return false;
   return true;
@@ -368,17 +469,15 @@ int rma_point_render_forward(const float* proj_points, int B, int N, int H, int 
   if (!render_sizes_ok(B, N, H, W, visible_patch_width) || !render_sizes_ok(B, N, H, W, color_patch_width))
     return RMA_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream_;
-  const long long npix = (long long)B * H * W, npts = (long long)B * N;
+  const long long npix = (long long)B * H * W;
   RMA_CUDA_TRY(launch_pdl(render_init_kernel, capped_grid(npix, 256, 148 * 8), 256u, 0, st, front_image, back_image,
                           depth_image, weight_image, npix, epsilon));
-  RMA_CUDA_TRY(launch_pdl(render_visibility_kernel,
-                          capped_grid(npts * visible_patch_width * visible_patch_width, 256, 148 * 32), 256u, 0, st,
-                          proj_points, front_image, back_image, npts, N, H, W, visible_patch_width));
-  RMA_CUDA_TRY(launch_pdl(render_raster_kernel,
-                          capped_grid(npts * color_patch_width * color_patch_width, 256, 148 * 32), 256u, 0, st,
-                          proj_points, (const float*)front_image, (const float*)back_image, (int*)pixel_index,
-                          (int*)is_visible, weight_points, depth_image, weight_image, npts, N, H, W, color_patch_width,
-                          threshold));
+  RMA_CUDA_TRY(RMA_SPLAT_LAUNCH(render_visibility_kernel, visible_patch_width, splat_grid(B, N, visible_patch_width), st,
+                                proj_points, front_image, back_image, B, N, H, W, visible_patch_width));
+  RMA_CUDA_TRY(RMA_SPLAT_LAUNCH(render_raster_kernel, color_patch_width, splat_grid(B, N, color_patch_width), st,
+                                proj_points, (const float*)front_image, (const float*)back_image, (int*)pixel_index,
+                                (int*)is_visible, weight_points, depth_image, weight_image, B, N, H, W,
+                                color_patch_width, threshold));
   return RMA_OK;
 }
 
@@ -400,9 +499,8 @@ int rma_point_masker_forward(const float* proj_points, int B, int N, int H, int 
   if (!proj_points || !mask_image || !render_sizes_ok(B, N, H, W, mask_patch_width)) return RMA_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream_;
   RMA_CUDA_TRY(cudaMemsetAsync(mask_image, 0, (size_t)B * H * W * sizeof(float), st));
-  const long long npts = (long long)B * N;
-  RMA_CUDA_TRY(launch_pdl(mask_forward_kernel, capped_grid(npts * mask_patch_width * mask_patch_width, 256, 148 * 32),
-                          256u, 0, st, proj_points, mask_image, npts, N, H, W, mask_patch_width));
+  RMA_CUDA_TRY(RMA_SPLAT_LAUNCH(mask_forward_kernel, mask_patch_width, splat_grid(B, N, mask_patch_width), st,
+                                proj_points, mask_image, B, N, H, W, mask_patch_width));
   return RMA_OK;
 }
 
@@ -411,7 +509,7 @@ static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 size_t rma_point_masker_backward_scratch_bytes(int B, int N, int H, int W) {
   if (B <= 0 || N <= 0 || H <= 0 || W <= 0) return 0;
   return up256((size_t)B * H * W * sizeof(MaskEntry)) + up256((size_t)B * (1 + kMaskSegs) * sizeof(int)) +
-         up256((size_t)B * kMaskSlices * N * sizeof(float));
+         up256((size_t)B * kMaskSlices * N * sizeof(float)) + up256((size_t)B * H * W * kMaskMaxSplits * sizeof(float));
 }
 
 int rma_point_masker_backward(const float* grad_mask_image, const float* proj_points, int B, int N, int H, int W,
@@ -427,6 +525,17 @@ int rma_point_masker_backward(const float* grad_mask_image, const float* proj_po
   int* counts = (int*)((char*)scratch + up256((size_t)B * npix * sizeof(MaskEntry)));
   int* segcount = counts + B;
   float* partial = (float*)((char*)counts + up256((size_t)B * (1 + kMaskSegs) * sizeof(int)));
+  float* spart = (float*)((char*)partial + up256((size_t)B * kMaskSlices * N * sizeof(float)));
+  // The number of active pixels is only known on the device.  Size the grids for ~4 waves of 8 CTAs per SM assuming
+  // about four 256-pixel tiles per batch element (a silhouette boundary in a 256x256 image); more pixels only add
+  // iterations to the per-CTA loops.
+  const int target = 4 * 148 * 8;
+  int splits = (target + B * 4 - 1) / (B * 4);
+  splits = splits < 1 ? 1 : (splits > kMaskMaxSplits ? kMaskMaxSplits : splits);
+  if (splits > (N + kMaskThreads - 1) / kMaskThreads) splits = (N + kMaskThreads - 1) / kMaskThreads;
+  const int point_ctas = (N + kMaskThreads - 1) / kMaskThreads;
+  int slices = (target + B * point_ctas - 1) / (B * point_ctas);
+  slices = slices < 1 ? 1 : (slices > kMaskSlices ? kMaskSlices : slices);
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kMaskSegs, (unsigned)B, 1); cfg.blockDim = dim3(256, 1, 1); cfg.stream = st;
@@ -438,14 +547,14 @@ int rma_point_masker_backward(const float* grad_mask_image, const float* proj_po
   }
   mask_compact_kernel<<<dim3(kMaskSegs, B), 256, 0, st>>>(grad_mask_image, H, W, threshold, segcount, entries, counts);
   RMA_LAUNCH_CHECK();
-  // the grids cover the worst case (every pixel active); blocks beyond the batch element's count exit at once
-  mask_norm_kernel<<<dim3((npix + kMaskThreads - 1) / kMaskThreads, B), kMaskThreads, 0, st>>>(
-      proj_points, N, npix, epsilon, entries, counts);
+  const int tiles = (npix + kMaskThreads - 1) / kMaskThreads;
+  mask_norm_kernel<<<dim3(tiles < kMaskTileCtas ? tiles : kMaskTileCtas, B, splits), kMaskThreads, 0, st>>>(
+      proj_points, N, npix, splits, entries, counts, spart);
   RMA_LAUNCH_CHECK();
-  mask_gather_kernel<<<dim3((N + kMaskThreads - 1) / kMaskThreads, B, kMaskSlices), kMaskThreads, 0, st>>>(
-      proj_points, N, npix, entries, counts, partial);
+  mask_gather_kernel<<<dim3(point_ctas, B, slices), kMaskThreads, 0, st>>>(proj_points, N, npix, splits, slices,
+                                                                            epsilon, entries, counts, spart, partial);
   RMA_LAUNCH_CHECK();
-  mask_reduce_kernel<<<(unsigned)(((long long)B * N + 255) / 256), 256, 0, st>>>(partial, N, (long long)B * N,
+  mask_reduce_kernel<<<(unsigned)(((long long)B * N + 255) / 256), 256, 0, st>>>(partial, N, (long long)B * N, slices,
                                                                                  grad_proj_points);
   RMA_LAUNCH_CHECK();
   return RMA_OK;
