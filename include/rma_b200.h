@@ -251,6 +251,17 @@ int rma_depth_view_term(const float* ori_depth, const float* ori_weight, const f
                         const float* tar_weight, int64_t n, float dis_threshold, float coef, float* loss,
                         float* grad_ori_depth, float* grad_ori_weight, void* stream);
 
+/* Multi-view projection of loss_on_depth / loss_on_mask (model/loss.py:161-166, 187-191), views folded into the batch:
+ *   out[v,b,n,r] = (sum_c rotations[v][r][c] * points[b,n,c] + add3[r]) * mul3[r]        out [V*B, N, 3] contiguous.
+ * points [B,N,3] with element strides; rotations [V,3,3] contiguous on the device (the reference's stacked
+ * `all_rot_matrix_for_lfd` [3V,3]); add3 / mul3 are HOST arrays of 3 floats (depth: add (1,1,-1), mul ((res-1)/2,
+ * (res-1)/2, 1); mask: add (1,1,-1), mul res/2).  backward: grad_points [B,N,3] contiguous (overwritten)
+ *   = sum_v rotations[v]^T (mul3 * grad_out[v,b,n,:]). */
+int rma_view_project_forward(const float* points, int64_t sb, int64_t sn, int64_t sc, const float* rotations, int V,
+                             int B, int N, const float* add3, const float* mul3, float* out, void* stream);
+int rma_view_project_backward(const float* grad_out, const float* rotations, int V, int B, int N, const float* mul3,
+                              float* grad_points, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Host-buffer convenience entry (what a non-torch FFI binding would call): pageable or pinned HOST pointers,
  * contiguous [B,N,3] / [B,M,3]; allocates device memory, copies in, runs forward (+ backward of

@@ -52,6 +52,8 @@ SIGNATURES = {
     "rma_arap_forward": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _P, c_int, c_int, c_int, c_int,
                                  _P, c_float, _P, _P, _P]),
     "rma_depth_view_term": (c_int, [_P, _P, _P, _P, _I64, c_float, c_float, _P, _P, _P, _P]),
+    "rma_view_project_forward": (c_int, [_P, _I64, _I64, _I64, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "rma_view_project_backward": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "rma_chamfer_loss_host": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
 }
 

@@ -155,6 +155,65 @@ __global__ void __launch_bounds__(kDepthThreads) depth_view_term_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-view projection of loss_on_depth / loss_on_mask (model/loss.py:161-166, 187-191): every point is rotated by
+// each of the V view matrices and mapped to pixel coordinates,
+//     out[v, b, n, r] = (sum_c R[v][r][c] * p[b, n, c] + add[r]) * mul[r],
+// with the views folded into the batch dimension ([V*B, N, 3], ready for the renderer).  The reference does this with
+// one bmm against the stacked rotations, a transpose, V slices, and 3-5 elementwise kernels per view (add, mul, div,
+// cat, contiguous) plus their autograd mirror; here one launch forward and one backward
+//     grad_p[b, n, c] = sum_v sum_r R[v][r][c] * mul[r] * g[v, b, n, r].
+// `(x + 1) * (res - 1) / 2` of the reference is three roundings, the last one exact: (x + 1) * ((res - 1) / 2) gives
+// the same bits.  HBM-bound: 12 B read + 12 V B written per point (and the reverse).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kProjThreads = 256;
+
+__global__ void __launch_bounds__(kProjThreads) view_project_kernel(
+    const float* __restrict__ pts, long long sb, long long sn, long long sc, const float* __restrict__ rot, int V, int B,
+    int N, float ax, float ay, float az, float mx, float my, float mz, float* __restrict__ out) {
+  extern __shared__ float srot[];
+  pdl_wait();
+  for (int t = threadIdx.x; t < V * 9; t += kProjThreads) srot[t] = rot[t];
+  __syncthreads();
+  const long long total = (long long)B * N;
+  for (long long t = (long long)blockIdx.x * kProjThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kProjThreads) {
+    const int b = (int)(t / N), n = (int)(t - (long long)b * N);
+    const float* p = pts + b * sb + n * sn;
+    const float x = p[0], y = p[sc], z = p[2 * sc];
+    for (int v = 0; v < V; ++v) {
+      const float* r = srot + v * 9;
+      float* o = out + ((long long)v * total + t) * 3;
+      o[0] = (fmaf(r[2], z, fmaf(r[1], y, r[0] * x)) + ax) * mx;
+      o[1] = (fmaf(r[5], z, fmaf(r[4], y, r[3] * x)) + ay) * my;
+      o[2] = (fmaf(r[8], z, fmaf(r[7], y, r[6] * x)) + az) * mz;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kProjThreads) view_project_backward_kernel(
+    const float* __restrict__ gout, const float* __restrict__ rot, int V, long long total, float mx, float my, float mz,
+    float* __restrict__ gpts) {
+  extern __shared__ float srot[];
+  pdl_wait();
+  for (int t = threadIdx.x; t < V * 9; t += kProjThreads) {
+    const int r = (t % 9) / 3;
+    srot[t] = rot[t] * (r == 0 ? mx : (r == 1 ? my : mz));
+  }
+  __syncthreads();
+  for (long long t = (long long)blockIdx.x * kProjThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kProjThreads) {
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    for (int v = 0; v < V; ++v) {
+      const float* r = srot + v * 9;
+      const float* g = gout + ((long long)v * total + t) * 3;
+      const float g0 = g[0], g1 = g[1], g2 = g[2];
+      gx = fmaf(r[0], g0, fmaf(r[3], g1, fmaf(r[6], g2, gx)));
+      gy = fmaf(r[1], g0, fmaf(r[4], g1, fmaf(r[7], g2, gy)));
+      gz = fmaf(r[2], g0, fmaf(r[5], g1, fmaf(r[8], g2, gz)));
+    }
+    gpts[t * 3] = gx; gpts[t * 3 + 1] = gy; gpts[t * 3 + 2] = gz;
+  }
+}
+
 }  // namespace rma
 
 using namespace rma;
@@ -193,6 +252,31 @@ int rma_depth_view_term(const float* ori_depth, const float* ori_weight, const f
   depth_view_term_kernel<<<(unsigned)blocks, kDepthThreads, 0, (cudaStream_t)stream_>>>(
       ori_depth, ori_weight, tar_depth, tar_weight, (long long)n, dis_threshold, coef, loss, grad_ori_depth,
       grad_ori_weight);
+  RMA_LAUNCH_CHECK();
+  return RMA_OK;
+}
+
+static unsigned proj_grid(long long total) {
+  long long g = (total + kProjThreads - 1) / kProjThreads;
+  return (unsigned)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+int rma_view_project_forward(const float* points, int64_t sb, int64_t sn, int64_t sc, const float* rotations, int V,
+                             int B, int N, const float* add3, const float* mul3, float* out, void* stream_) {
+  if (!points || !rotations || !add3 || !mul3 || !out || V <= 0 || B <= 0 || N <= 0 || V > 4096) return RMA_E_BADARG;
+  view_project_kernel<<<proj_grid((long long)B * N), kProjThreads, (size_t)V * 9 * sizeof(float),
+                        (cudaStream_t)stream_>>>(points, (long long)sb, (long long)sn, (long long)sc, rotations, V, B, N,
+                                                 add3[0], add3[1], add3[2], mul3[0], mul3[1], mul3[2], out);
+  RMA_LAUNCH_CHECK();
+  return RMA_OK;
+}
+
+int rma_view_project_backward(const float* grad_out, const float* rotations, int V, int B, int N, const float* mul3,
+                              float* grad_points, void* stream_) {
+  if (!grad_out || !rotations || !mul3 || !grad_points || V <= 0 || B <= 0 || N <= 0 || V > 4096) return RMA_E_BADARG;
+  view_project_backward_kernel<<<proj_grid((long long)B * N), kProjThreads, (size_t)V * 9 * sizeof(float),
+                                 (cudaStream_t)stream_>>>(grad_out, rotations, V, (long long)B * N, mul3[0], mul3[1],
+                                                          mul3[2], grad_points);
   RMA_LAUNCH_CHECK();
   return RMA_OK;
 }

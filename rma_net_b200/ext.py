@@ -598,3 +598,39 @@ def depth_view_term(ori_depth: torch.Tensor, ori_weight: torch.Tensor, tar_depth
                                                  _stream())
             _lib.check(rc, "rma_depth_view_term")
     return loss, grads
+
+
+def _float3(v):
+    import ctypes
+    return (ctypes.c_float * 3)(*[float(a) for a in v])
+
+
+def view_project_forward(points: torch.Tensor, rotations: torch.Tensor, add3, mul3) -> torch.Tensor:
+    """points [B,N,3] (any strides), rotations [3V,3] or [V,3,3] -> [V*B, N, 3] = (R_v p + add3) * mul3."""
+    _check_points("points", points)
+    rot = rotations.to(torch.float32).contiguous()
+    if rot.numel() % 9 != 0 or rot.device != points.device:
+        raise RuntimeError("rotations must be [V,3,3] / [3V,3] on the points' device")
+    V = rot.numel() // 9
+    B, N = points.shape[0], points.shape[1]
+    out = torch.empty((V * B, N, 3), dtype=torch.float32, device=points.device)
+    if B * N:
+        st = points.stride()
+        a, m = _float3(add3), _float3(mul3)
+        with torch.cuda.device(points.device):
+            rc = _lib.load().rma_view_project_forward(_ptr(points), st[0], st[1], st[2], _ptr(rot), V, B, N, a, m,
+                                                      _ptr(out), _stream())
+            _lib.check(rc, "rma_view_project_forward")
+    return out
+
+
+def view_project_backward(grad_out: torch.Tensor, rotations: torch.Tensor, B: int, N: int, mul3) -> torch.Tensor:
+    rot = rotations.to(torch.float32).contiguous()
+    V = rot.numel() // 9
+    g = grad_out.to(torch.float32).contiguous()
+    out = torch.empty((B, N, 3), dtype=torch.float32, device=g.device)
+    if B * N:
+        with torch.cuda.device(g.device):
+            rc = _lib.load().rma_view_project_backward(_ptr(g), _ptr(rot), V, B, N, _float3(mul3), _ptr(out), _stream())
+            _lib.check(rc, "rma_view_project_backward")
+    return out

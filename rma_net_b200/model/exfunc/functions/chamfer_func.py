@@ -109,6 +109,24 @@ class DepthViewTermFunction(torch.autograd.Function):
         return g_od * grad_loss, g_ow * grad_loss, None, None, None, None
 
 
+class ViewProjectFunction(torch.autograd.Function):
+    """points [B,N,3], stacked view rotations [3V,3] -> [V*B,N,3] = (R_v p + add3) * mul3: the rotate-and-map-to-
+    pixels step of loss_on_depth / loss_on_mask (reference model/loss.py:161-166, 187-191) with the views folded into
+    the batch; one launch forward, one backward (gradient w.r.t. the points only)."""
+
+    @staticmethod
+    def forward(ctx, points, rotations, add3, mul3):
+        ctx.save_for_backward(rotations)
+        ctx.shape = (points.shape[0], points.shape[1])
+        ctx.mul3 = tuple(float(m) for m in mul3)
+        return ext.view_project_forward(points, rotations, add3, mul3)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (rotations,) = ctx.saved_tensors
+        return ext.view_project_backward(grad_out, rotations, ctx.shape[0], ctx.shape[1], ctx.mul3), None, None, None
+
+
 class Chamfer(torch.nn.Module):
     """forward(points_x [B,M,3], points_y [B,N,3]) -> (dist1 [B,M], dist2 [B,N], idx1, idx2)."""
 

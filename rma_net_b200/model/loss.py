@@ -230,11 +230,12 @@ def _views_to_batch(points, all_rot):
 
 
 def loss_on_depth(deformation_p, p1, all_rot, renderer=None, threshold=threshold_, resolution=resolution_,
-                  batched=True, fused_compare=True):
+                  batched=True, fused_compare=True, fused_project=True):
     """loss.py:147-183 without the in-place re-sampling of the views (pass them in: view_rotations(..., jitter)).
     batched=True folds the V views into the batch dimension: 2 Render calls instead of 2V, same value and gradient
     (up to fp32 summation order); batched=False is the reference's literal per-view loop.  fused_compare=True runs
-    the image comparison (loss.py:169-181) as one kernel (DepthViewTermFunction) instead of ~14 torch kernels."""
+    the image comparison (loss.py:169-181) as one kernel (DepthViewTermFunction) instead of ~14 torch kernels;
+    fused_project=True the rotate-and-map-to-pixels step (loss.py:161-166) as one kernel (ViewProjectFunction)."""
     from .exfunc.functions import DepthViewTermFunction, Render
     renderer = renderer or Render(resolution, resolution, 7, 9, 1e-5)            # loss.py:34
 
@@ -255,6 +256,12 @@ def loss_on_depth(deformation_p, p1, all_rot, renderer=None, threshold=threshold
         return torch.sum(torch.mul(mask, torch.mul(dis, dis)))
 
     if batched:
+        V = all_rot.shape[0] // 3
+        if fused_project:
+            from .exfunc.functions import ViewProjectFunction
+            add3, mul3 = (1., 1., -1.), ((resolution - 1) / 2, (resolution - 1) / 2, 1.)
+            return view_term(ViewProjectFunction.apply(deformation_p, all_rot, add3, mul3),
+                             ViewProjectFunction.apply(p1, all_rot, add3, mul3)) / V
         a, V = _views_to_batch(deformation_p, all_rot)
         b, _ = _views_to_batch(p1, all_rot)
         return view_term(project(a), project(b)) / V
@@ -269,7 +276,7 @@ def loss_on_depth(deformation_p, p1, all_rot, renderer=None, threshold=threshold
 
 
 def loss_on_mask(deformation_p, p1, all_rot, masker=None, threshold=threshold_2_, resolution=resolution_,
-                 batched=True):
+                 batched=True, fused_project=True):
     """loss.py:185-196: mean |mask(deformation) - mask(target)| averaged over the views; the projection scales all
     three coordinates by resolution/2 after adding (1, 1, -1), as the reference does (:190)."""
     from .exfunc.functions import Masker
@@ -279,6 +286,11 @@ def loss_on_mask(deformation_p, p1, all_rot, masker=None, threshold=threshold_2_
     def project(pv):
         return ((pv + shift) * resolution / 2.).contiguous()
 
+    if batched and fused_project:
+        from .exfunc.functions import ViewProjectFunction
+        add3, mul3 = (1., 1., -1.), (resolution / 2.,) * 3
+        return torch.mean(torch.abs(masker(ViewProjectFunction.apply(deformation_p, all_rot, add3, mul3), threshold)
+                                    - masker(ViewProjectFunction.apply(p1, all_rot, add3, mul3), threshold)))
     if batched:
         a, V = _views_to_batch(deformation_p, all_rot)
         b, _ = _views_to_batch(p1, all_rot)
