@@ -78,6 +78,33 @@ def main():
     near = (torch.arange(N, dtype=torch.int32)[None].expand(B, -1).contiguous()).to(dev)   # local partners: coalesced
     t = timed(lambda: ext.chamfer_backward(src, y, near, near, g1, g2))
     out["chamfer_backward_local_idx_GBps"] = 56 * 2 * B * N / t / 1e9
+    # ---- kernels of the Loss module (csrc/loss_terms.cu), algorithmic bytes as stated in DESIGN.md section 12 ----
+    # depth image comparison: 4 images read (16 B/pixel) + 2 gradient images written (8 B/pixel); 200 images 256x256
+    npx = 200 * 256 * 256
+    imgs = [torch.rand(npx, generator=g).to(dev) + 0.5 for _ in range(4)]
+    t = timed(lambda: ext.depth_view_term(imgs[0], imgs[1], imgs[2], imgs[3], 0.05, 1.0, True))
+    out["depth_view_term_GBps"] = 24 * npx / t / 1e9          # + two torch.empty and one 4-byte memset per call
+    # multi-view projection, V = 25: forward 12 B read + 12 V B written per point; backward the reverse
+    Bp, Np, V = 8, 1 << 15, 25
+    pts = (torch.rand(Bp, Np, 3, generator=g) - 0.5).to(dev)
+    rot = torch.linalg.qr(torch.randn(V, 3, 3, generator=g))[0].reshape(-1, 3).contiguous().to(dev)
+    add3, mul3 = (1., 1., -1.), (127.5, 127.5, 1.)
+    t = timed(lambda: ext.view_project_forward(pts, rot, add3, mul3))
+    out["view_project_fwd_GBps"] = 12 * (V + 1) * Bp * Np / t / 1e9
+    gproj = torch.randn(V * Bp, Np, 3, generator=g).to(dev)
+    t = timed(lambda: ext.view_project_backward(gproj, rot, Bp, Np, mul3))
+    out["view_project_bwd_GBps"] = 12 * (V + 1) * Bp * Np / t / 1e9
+    # ARAP, n = 4, T*B = 56 groups: per (group, vertex) 60 B deformation + 60 B source + 16 B indices + 60 B gradient
+    # updates = 196 B (the source and the indices are shared by the T stages and the neighbour reads hit L2: the
+    # figure is algorithmic, not DRAM traffic)
+    Ba, Va, T = 8, 1 << 15, 7
+    srca = (torch.rand(Ba, Va, 3, generator=g) - 0.5).to(dev)
+    defo = (srca.repeat(T, 1, 1) + 0.01 * torch.randn(T * Ba, Va, 3, generator=g).to(dev)).contiguous()
+    from rma_net_b200.model.loss import get_neighbor_index
+    nb = get_neighbor_index(srca, 4).int()
+    wa = torch.ones(T * Ba, device=dev)
+    t = timed(lambda: ext.arap_forward(defo, srca, nb, wa, 1.0 / Ba, True))
+    out["arap_fwd_with_grad_GBps"] = 196 * T * Ba * Va / t / 1e9     # includes the zero-fill of the gradient buffer
     for k in list(out):
         if k.endswith("GBps") and k != "hbm_peak_GBps":
             out[k.replace("GBps", "frac_of_peak")] = out[k] / peak
