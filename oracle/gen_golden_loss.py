@@ -76,6 +76,12 @@ def main():
                ref_grad_rigid=np.stack([r.grad.numpy() for r in rigid]))
     for k, v in single.items():
         out["ref_single_" + k] = np.float32(v.item())
+    # euler2rot (loss.py:73-95, exec'd verbatim) on seeded angles, incl. the view grid's range [-pi, pi)
+    ens = {"torch": torch}
+    exec(compile(_lines(73, 95), REF, "exec"), ens)
+    angles = (torch.rand(40, 3, generator=g) * 2 - 1) * float(np.pi)
+    out["euler_angles"] = angles.numpy()
+    out["ref_euler2rot"] = ens["euler2rot"](angles).numpy()
     np.savez_compressed(os.path.join(GOLD, "loss_forward.npz"), **out)
     print("loss", loss.item(), "stages", [float(s) for s in stages])
 

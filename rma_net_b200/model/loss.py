@@ -189,20 +189,25 @@ threshold_ = 0.1             # loss.py:36
 threshold_2_ = 1e-10         # loss.py:37
 
 
+def _plane_rotation(angle, i, j):
+    """[n] angles -> [n,3,3] rotations acting in the coordinate plane (i, j): m[i,i] = m[j,j] = cos, m[i,j] = -sin,
+    m[j,i] = sin, identity elsewhere."""
+    m = torch.eye(3, dtype=angle.dtype, device=angle.device).repeat(angle.shape[0], 1, 1)
+    c, s = angle.cos(), angle.sin()
+    m[:, i, i] = c
+    m[:, j, j] = c
+    m[:, i, j] = -s
+    m[:, j, i] = s
+    return m
+
+
 def euler2rot(euler_angle):
-    """[n,3] Euler angles -> [n,3,3] = Rz(psi) Ry(phi) Rx(theta)   (loss.py:73-95)"""
-    n = euler_angle.shape[0]
-    one = torch.ones(n, 1, 1, device=euler_angle.device)
-    zero = torch.zeros(n, 1, 1, device=euler_angle.device)
-    theta = euler_angle[:, 0].reshape(-1, 1, 1)
-    phi = euler_angle[:, 1].reshape(-1, 1, 1)
-    psi = euler_angle[:, 2].reshape(-1, 1, 1)
-    rot_x = torch.cat((torch.cat((one, zero, zero), 1), torch.cat((zero, theta.cos(), theta.sin()), 1),
-                       torch.cat((zero, -theta.sin(), theta.cos()), 1)), 2)
-    rot_y = torch.cat((torch.cat((phi.cos(), zero, -phi.sin()), 1), torch.cat((zero, one, zero), 1),
-                       torch.cat((phi.sin(), zero, phi.cos()), 1)), 2)
-    rot_z = torch.cat((torch.cat((psi.cos(), -psi.sin(), zero), 1), torch.cat((psi.sin(), psi.cos(), zero), 1),
-                       torch.cat((zero, zero, one), 1)), 2)
+    """[n,3] Euler angles (theta, phi, psi) -> [n,3,3] = Rz(psi) Ry(phi) Rx(theta) with the reference's sign
+    conventions (loss.py:73-95): Rx turns the (y,z) plane, Ry the (z,x) plane, Rz the (y,x) plane; the product is
+    formed by two bmm calls in the reference's order, so the fp32 entries are the same."""
+    rot_x = _plane_rotation(euler_angle[:, 0], 1, 2)
+    rot_y = _plane_rotation(euler_angle[:, 1], 2, 0)
+    rot_z = _plane_rotation(euler_angle[:, 2], 1, 0)
     return torch.bmm(rot_z, torch.bmm(rot_y, rot_x))
 
 
