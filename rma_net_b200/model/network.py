@@ -22,13 +22,11 @@ def knn(x, k):
 
 
 def get_graph_feature(x, k=5):
-    idx = knn(x, k=k)                                 # (batch_size, num_points, k)
-    batch_size, num_points, _ = idx.size()
-    idx_base = torch.arange(0, batch_size, device=x.device).view(-1, 1, 1) * num_points
-    idx = (idx + idx_base).view(-1)
-    _, num_dims, _ = x.size()
-    x = x.transpose(2, 1).contiguous()
-    feature = x.view(batch_size * num_points, -1)[idx, :]
-    feature = feature.view(batch_size, num_points, k, num_dims)
-    x = x.view(batch_size, num_points, 1, num_dims).repeat(1, 1, k, 1)
-    return torch.cat((feature, x), dim=3).permute(0, 3, 1, 2)
+    """x [B,C,N] -> [B,2C,N,k] DGCNN edge features: channels 0..C-1 hold the neighbour's coordinates, C..2C-1 the
+    point's own (the value and memory layout of network.py:61-83: a permuted view of a contiguous [B,N,k,2C] tensor)."""
+    neighbours = knn(x, k=k)                                             # [B,N,k]
+    batch = torch.arange(x.shape[0], device=x.device)[:, None, None]
+    points = x.transpose(2, 1)                                           # [B,N,C] view
+    theirs = points[batch, neighbours]                                   # [B,N,k,C]
+    own = points.unsqueeze(2).expand(-1, -1, neighbours.shape[2], -1)
+    return torch.cat((theirs, own), dim=3).permute(0, 3, 1, 2)
