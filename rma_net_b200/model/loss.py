@@ -280,10 +280,20 @@ def loss_on_depth(deformation_p, p1, all_rot, renderer=None, threshold=threshold
     return out
 
 
+def target_view_masks(p1, all_rot, masker=None, threshold=threshold_2_, resolution=resolution_):
+    """The target's masks for all views, [V*B,H,W,1] (no gradient): what loss_on_mask computes for `p1`.  The views of
+    the mask term do not change between the stages of one Loss.forward, so it can be computed once per step."""
+    from .exfunc.functions import Masker, ViewProjectFunction
+    masker = masker or Masker(resolution, resolution, 5, 1e-5)
+    with torch.no_grad():
+        return masker(ViewProjectFunction.apply(p1, all_rot, (1., 1., -1.), (resolution / 2.,) * 3), threshold)
+
+
 def loss_on_mask(deformation_p, p1, all_rot, masker=None, threshold=threshold_2_, resolution=resolution_,
-                 batched=True, fused_project=True):
+                 batched=True, fused_project=True, target_masks=None):
     """loss.py:185-196: mean |mask(deformation) - mask(target)| averaged over the views; the projection scales all
-    three coordinates by resolution/2 after adding (1, 1, -1), as the reference does (:190)."""
+    three coordinates by resolution/2 after adding (1, 1, -1), as the reference does (:190).  target_masks: the
+    result of target_view_masks(p1, all_rot, ...) if the caller already has it (batched + fused_project path)."""
     from .exfunc.functions import Masker
     masker = masker or Masker(resolution, resolution, 5, 1e-5)                   # loss.py:35
     shift = torch.tensor([[[1., 1., -1.]]], device=deformation_p.device)
@@ -294,8 +304,10 @@ def loss_on_mask(deformation_p, p1, all_rot, masker=None, threshold=threshold_2_
     if batched and fused_project:
         from .exfunc.functions import ViewProjectFunction
         add3, mul3 = (1., 1., -1.), (resolution / 2.,) * 3
+        if target_masks is None:
+            target_masks = masker(ViewProjectFunction.apply(p1, all_rot, add3, mul3), threshold)
         return torch.mean(torch.abs(masker(ViewProjectFunction.apply(deformation_p, all_rot, add3, mul3), threshold)
-                                    - masker(ViewProjectFunction.apply(p1, all_rot, add3, mul3), threshold)))
+                                    - target_masks))
     if batched:
         a, V = _views_to_batch(deformation_p, all_rot)
         b, _ = _views_to_batch(p1, all_rot)
@@ -387,11 +399,12 @@ class Loss(torch.nn.Module):
             self._renderer = Render(resolution_, resolution_, 7, 9, 1e-5)
         return loss_on_depth(deformation_p, p1, self.all_rot_matrix_for_lfd, self._renderer)
 
-    def loss_on_mask(self, deformation_p, p1):
+    def loss_on_mask(self, deformation_p, p1, target_masks=None):
         from .exfunc.functions import Masker
         if self._masker is None:
             self._masker = Masker(resolution_, resolution_, 5, 1e-5)
-        return loss_on_mask(deformation_p, p1, self.all_rot_matrix_for_lfd.to(deformation_p.device), self._masker)
+        return loss_on_mask(deformation_p, p1, self.all_rot_matrix_for_lfd.to(deformation_p.device), self._masker,
+                            target_masks=target_masks)
 
     # ---- forward ---------------------------------------------------------------------------------------------
     def forward(self, phi_list, point_weight_list, deform_rigid_points_list, deformation_points_list,
@@ -469,7 +482,14 @@ class Loss(torch.nn.Module):
             loss_stages.append(zero_tensor)
 
         if a.weight_mask > 0:                                                        # loss.py:321-330
-            loss_mask = sum(gam[i] * self.loss_on_mask(stage[i], target_points) for i in range(iter_time))
+            tmasks = None
+            if fused and not (target_points.requires_grad and torch.is_grad_enabled()):
+                # every stage of this term uses the views of the last depth call: one target render instead of T
+                from .exfunc.functions import Masker
+                if self._masker is None:
+                    self._masker = Masker(resolution_, resolution_, 5, 1e-5)
+                tmasks = target_view_masks(target_points, self.all_rot_matrix_for_lfd.to(dev), self._masker)
+            loss_mask = sum(gam[i] * self.loss_on_mask(stage[i], target_points, tmasks) for i in range(iter_time))
             loss = loss + loss_mask * a.weight_mask
             loss_stages.append(loss_mask)
         else:
