@@ -332,6 +332,7 @@ def run_ours(args):
     barrier()
     e2e_serial_ms = ev0.elapsed_time(ev1) / args.steps
     e2e_ms, e2e_mode = e2e_serial_ms, "serial: H2D copy, fwd+bwd, D2H loss, host sync, one after the other"
+    e2e_sync_ms = e2e_serial_ms
 
     if use_graph and pair_pin is not None:
         # The same K steps the way a training loop feeds them (rma_net_b200.data.PairBatchLoader, the replacement of
@@ -344,12 +345,14 @@ def run_ours(args):
         xs = [b_[:, :N].detach().requires_grad_(True) for b_ in bufs]
         ys = [b_[:, N:].detach().requires_grad_(True) for b_ in bufs]
 
+        loss_pins = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+
         def compute(i):
             xs[i].grad = None
             ys[i].grad = None
             loss = loss_on_cd(xs[i], ys[i])
             loss.backward()
-            loss_pin.copy_(loss.detach(), non_blocking=True)
+            loss_pins[i].copy_(loss.detach(), non_blocking=True)
 
         graphs = []
         for i in range(2):
@@ -370,42 +373,55 @@ def run_ours(args):
                 bufs[i].copy_(pair_pin, non_blocking=True)
             ev_copied[i].record(copy_stream)
 
-        def run_pipelined(steps, first_event=None):
+        def run_pipelined(steps, first_event=None, lag=0):
+            """lag=0: the host reads step k's loss before it launches step k+1.  lag=1: it launches step k+1 first and
+            reads step k's loss (own pinned slot, own event) while k+1 runs - the logging pattern of a training loop
+            that never stalls the device; still K copies in, K losses read, all inside the timed region."""
             for i in range(2):
                 ev_free[i].record(main_stream)
             if first_event is not None:
                 copy_stream.wait_event(first_event)          # the first copy starts inside the timed region
             issue_copy(0)
-            val = 0.0
+            vals = []
             for k in range(steps):
                 i = k & 1
                 main_stream.wait_event(ev_copied[i])
                 graphs[i].replay()
-                ev_free[i].record(main_stream)
+                ev_free[i].record(main_stream)               # also marks "loss of step k is in its pinned slot"
                 if k + 1 < steps:
                     issue_copy(1 - i)
-                main_stream.synchronize()                    # the host reads the loss every step
-                val = float(loss_pin)
-            return val
+                if lag == 0:
+                    main_stream.synchronize()                # the host reads the loss every step
+                    vals.append(float(loss_pins[i]))
+                elif k >= 1:
+                    ev_free[1 - i].synchronize()             # step k-1 done (step k is running)
+                    vals.append(float(loss_pins[1 - i]))
+            if lag:
+                main_stream.synchronize()
+                vals.append(float(loss_pins[(steps - 1) & 1]))
+            assert len(vals) == steps
+            return vals[-1]
 
-        run_pipelined(4)
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        pipelined_loss = run_pipelined(args.steps, ev0)
-        ev1.record()
-        barrier()
-        if abs(pipelined_loss - serial_loss) > 1e-6 * abs(serial_loss):
-            raise RuntimeError(f"pipelined e2e loss {pipelined_loss} != serial {serial_loss}")
-        e2e_ms = ev0.elapsed_time(ev1) / args.steps
-        e2e_mode = ("double-buffered: the H2D copy of step k+1 runs on a copy stream while step k computes "
-                    "(PairBatchLoader pattern); every step copies its inputs and the host reads every loss")
+        e2e_modes = {}
+        for lag in (0, 1):
+            run_pipelined(4, lag=lag)
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            pipelined_loss = run_pipelined(args.steps, ev0, lag=lag)
+            ev1.record()
+            barrier()
+            if abs(pipelined_loss - serial_loss) > 1e-6 * abs(serial_loss):
+                raise RuntimeError(f"pipelined e2e loss {pipelined_loss} != serial {serial_loss}")
+            e2e_modes[lag] = ev0.elapsed_time(ev1) / args.steps
+        e2e_sync_ms = e2e_modes[0]
+        e2e_ms = e2e_modes[1]
 
     # ---- aggregate over ranks (max time) ------------------------------------------------------------------------
-    t = torch.tensor([ms, e2e_ms, search_ms, e2e_serial_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_ms, search_ms, e2e_serial_ms, e2e_sync_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, search_ms, e2e_serial_ms = (float(v) for v in t.cpu())
+    ms, e2e_ms, search_ms, e2e_serial_ms, e2e_sync_ms = (float(v) for v in t.cpu())
     value = world * pairs / (ms * 1e-3) / 1e9
     e2e_value = world * pairs / (e2e_ms * 1e-3) / 1e9
 
@@ -452,7 +468,8 @@ def run_ours(args):
                                     f"reaches 97% of it (profiles/r01_fp32_microbench.jsonl)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
-                "mode": e2e_mode, "serial_ms_per_step": e2e_serial_ms,
+                "mode": e2e_mode, "sync_ms_per_step": e2e_sync_ms,
+                "sync_value": world * pairs / (e2e_sync_ms * 1e-3) / 1e9, "serial_ms_per_step": e2e_serial_ms,
                 "serial_value": world * pairs / (e2e_serial_ms * 1e-3) / 1e9,
                 "host_layout": "one pinned [B,2N,3] pair batch (train_view.py:369-370), one H2D copy, strided slices"
                                if pair_pin is not None else "two pinned clouds, two H2D copies"},

@@ -519,7 +519,11 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       }
     }
     const float thr = M1 + guard_row(rp.w, M1);
+#ifdef RMA_EXP_NO_SLOW   // timing experiment only (tools/resolve_variants.py): wrong results for the slow-path items
+    const bool fast = valid;
+#else
     const bool fast = valid && M2 > thr;
+#endif
     unsigned best_d = 0xffffffffu, best_j = 0;
 
     // Fast path (one candidate tile): 8 lanes per row, 8 columns per lane, 4 rows per round.  Inside the tile the
@@ -634,7 +638,11 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       }
     }
     const float thr = M1 + guard_col(cq.w, M1);
+#ifdef RMA_EXP_NO_SLOW   // timing experiment only (tools/resolve_variants.py): wrong results for the slow-path items
+    const bool fast = valid;
+#else
     const bool fast = valid && M2 > thr;
+#endif
     const int G1 = (R1 * 32 + (int)(__float_as_uint(M1) & 31u)) * kFRowsPerThread;   // first row of the candidate group
     unsigned best_d = 0xffffffffu, best_i = 0;
 
