@@ -76,11 +76,12 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("RMA_B200_LIB") or LIB_PATH     # override: A/B runs of two builds of this same library
+    if not os.path.exists(path):
         raise RmaB200Error(
-            f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+            f"{path} not found: the CUDA extension is required (no CPU fallback). "
             "Build it with `python -m rma_net_b200.build` (needs nvcc, sm_100a).")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here == header/library mismatch
         fn.restype = res

@@ -28,6 +28,9 @@ constexpr int kTile = 32;                               // columns per tile (= l
 constexpr int kChunk = 1024;                            // columns staged in shared memory at a time
 constexpr int kCbStride = 36;                           // row stride (floats) of the per-warp column-min transpose
                                                         // buffer: 16-B aligned rows, conflict-free LDS.128 / STS.32
+// dynamic shared memory of the search: column double buffer, per-warp transpose buffers, two mbarriers
+constexpr size_t kSearchSmem = (size_t)2 * (kChunk + 4) * sizeof(float4) +
+                               (size_t)kSearchWarps * 2 * kTile * kCbStride * sizeof(float) + 16;
 constexpr float kRowSentinel = 1e18f;                   // padded source rows:  d ~ 3e36 against real targets
 constexpr float kColSentinelNeg = 3e18f;                // padded target columns (stored negated): d ~ 2.7e37
 
@@ -156,10 +159,13 @@ struct SearchArgs {
 
 __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(SearchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* scol = reinterpret_cast<float4*>(smem_raw);                                       // [kChunk + 4]
-  float* cball = reinterpret_cast<float*>(smem_raw + (size_t)(kChunk + 4) * sizeof(float4));  // [warps][2][32][36]
+  float4* scol = reinterpret_cast<float4*>(smem_raw);                                           // [2][kChunk + 4]
+  float* cball = reinterpret_cast<float*>(smem_raw + (size_t)2 * (kChunk + 4) * sizeof(float4));  // [warps][2][32][36]
+  u64* mbar = reinterpret_cast<u64*>(smem_raw + kSearchSmem - 16);                              // [2]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
+  __syncthreads();
   pdl_wait();
   const int s = blockIdx.x % a.S;
   const int rbc = (blockIdx.x / a.S) % a.nRBC;
@@ -191,6 +197,11 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
   for (int r = 0; r < kRowsPerThread; ++r) { m[r] = __int_as_float(0x7f800000); mt[r] = 0; }
 
   const float4* cp = a.colpack + ((size_t)b * a.Mp + c0);
+  // Column chunks arrive by TMA bulk copy into a double buffer: chunk 0 is in flight while the rows above are
+  // loaded, chunk k+1 while chunk k is computed.
+  if (tid == 0 && ncols > 0) bulk_load(scol, cp, (unsigned)min(kChunk, ncols) * 16u, &mbar[0]);
+  int cur = 0;
+  unsigned phases = 0;   // bit s: parity the next wait on buffer s expects
 
   // Column direction, software-pipelined: while tile t is being computed, lane l reduces column l of tile t-1
   // (32 per-lane partial minima in the other half of the double buffer), four values per loop body, so the
@@ -200,17 +211,21 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
 
   for (int cs = 0; cs < ncols; cs += kChunk) {
     const int nc = min(kChunk, ncols - cs);
-    __syncthreads();   // previous chunk fully consumed
-    for (int idx = tid; idx < nc; idx += kSearchThreads) scol[idx] = cp[(size_t)cs + idx];
-    __syncthreads();
-    if (!has_rows) continue;
+    // the other buffer was last read in the previous iteration, which ended with a __syncthreads
+    if (tid == 0 && cs + kChunk < ncols)
+      bulk_load(scol + (cur ^ 1) * (kChunk + 4), cp + cs + kChunk, (unsigned)min(kChunk, ncols - cs - kChunk) * 16u,
+                &mbar[cur ^ 1]);
+    mbar_wait(&mbar[cur], (phases >> cur) & 1u);
+    phases ^= 1u << cur;
+    const float4* schunk = scol + cur * (kChunk + 4);
+    cur ^= 1;
 
 #pragma unroll 1
-    for (int t0 = 0; t0 < nc; t0 += kTile) {
+    for (int t0 = 0; has_rows && t0 < nc; t0 += kTile) {
       float tm[kRowsPerThread];
 #pragma unroll
       for (int r = 0; r < kRowsPerThread; ++r) tm[r] = __int_as_float(0x7f800000);
-      const float4* sp = scol + t0;
+      const float4* sp = schunk + t0;
       float* cbw = cb + parity * (kTile * kCbStride) + lane;                          // this tile: [col][lane]
       const float4* cbr = reinterpret_cast<const float4*>(cb + (parity ^ 1) * (kTile * kCbStride) +
                                                           lane * kCbStride);          // previous tile: my column
@@ -268,6 +283,7 @@ __global__ void __launch_bounds__(kSearchThreads, 2) chamfer_search_kernel(Searc
       parity ^= 1;
       __syncwarp();   // this tile's partial minima visible to all lanes; previous buffer free for reuse
     }
+    __syncthreads();   // chunk fully consumed: the next iteration's prefetch refills this buffer
   }
 
   if (has_rows) {
@@ -527,7 +543,6 @@ __global__ void unpack_keys_kernel(const u64* __restrict__ keys, long long n, fl
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-constexpr size_t kSearchSmem = (size_t)(kChunk + 4) * sizeof(float4) + (size_t)kSearchWarps * 2 * kTile * kCbStride * sizeof(float);
 
 struct DeviceCaps { int sms; int search_occ; };
 
@@ -825,7 +840,7 @@ int rma_chamfer_cd_backward(const float* own_x, const float* scat_x, int64_t nx,
   if (nx + ny == 0) return RMA_OK;
   long long grid = (nx + ny + 255) / 256;
   if (grid > 148LL * 16) grid = 148LL * 16;
-  RMA_CUDA_TRY(launch_pdl(cd_backward_kernel, (unsigned)grid, 256u, 0, (cudaStream_t)stream_, own_x,
+  RMA_CUDA_TRY(launch_dep(pdl_site(8), cd_backward_kernel, (unsigned)grid, 256u, 0, (cudaStream_t)stream_, own_x,
                           (const float4*)scat_x, (long long)nx, own_y, (const float4*)scat_y, (long long)ny, scalar_dev,
                           out_x, out_y));
   return RMA_OK;

@@ -94,7 +94,10 @@ struct FWorkspace {
   float4* rowpack;   // [B][Npad]               (x, y, z, |x|^2); padded rows (0,0,0,1e30)           (resolve)
   float4* rowsoa;    // [B][nRB][16][32]        per search thread its 16 rows as x[16], y[16], z[16], u[16],
                      //                         lane-coalesced: 16 LDG.128 whose halves are the packed row pairs
-  float4* colpack;   // [B][Mp]                 (-2x, -2y, -2z, |y|^2); padded columns (0,0,0,1e30)
+  float4* colpack;   // [B][Mp]                 (-2x, -2y, -2z, |y|^2); padded columns (0,0,0,1e30)            (resolve)
+  float4* colpair;   // [B][Mp/2][2]            the same, two columns (c, c+1) interleaved as (q0c, q0c', q1c, q1c')
+                     //                         (q2c, q2c', wc, wc'): the search's fp32x2 operands as they are read from
+                     //                         shared memory, so a chunk is one contiguous TMA bulk copy
   float* rowrec;     // [B][nT][Npad]           min over the tile's 64 columns of f (read only when a guard fails)
   float* rowtop;     // [B*nRBC][Smax][3][2048] per segment: smallest tile minimum, its tile, second smallest
   float* colrec;     // [B][nRB][2][Mp]         two smallest packed group minima of g over the row block
@@ -109,6 +112,7 @@ static FWorkspace f_carve(const FGeometry& g, void* base) {
   w.rowpack = (float4*)(p + off); off += align256((size_t)g.B * g.Npad * sizeof(float4));
   w.rowsoa = (float4*)(p + off);  off += align256((size_t)g.B * g.Npad * sizeof(float4));
   w.colpack = (float4*)(p + off); off += align256((size_t)g.B * g.Mp * sizeof(float4));
+  w.colpair = (float4*)(p + off); off += align256((size_t)g.B * g.Mp * sizeof(float4));
   w.rowrec = (float*)(p + off);   off += align256((size_t)g.B * g.nT * g.Npad * sizeof(float));
   w.rowtop = (float*)(p + off);   off += align256((size_t)g.B * g.nRBC * g.Smax * 3 * kFRowsPerCta * sizeof(float));
   w.colrec = (float*)(p + off);   off += align256((size_t)g.B * g.nRB * kFColTop * g.Mp * sizeof(float));
@@ -165,6 +169,13 @@ __global__ void __launch_bounds__(256) chamfer_fprep_kernel(
         if (zero_gy) zero_gy[(long long)b * g.M + j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       w.colpack[u] = v;
+      // pair pack: columns (c, c+1) sit in neighbouring lanes (nrow, Mp and the grid stride are even, so the pair
+      // never straddles a warp, the row/column boundary or the loop bound); the even lane stores (q0c, q0c', q1c, q1c'),
+      // the odd one (q2c, q2c', wc, wc') - one coalesced 16-byte store each
+      const bool odd = (u & 1) != 0;
+      const float s0 = odd ? v.x : v.z, s1 = odd ? v.y : v.w;            // what the partner lane needs from me
+      const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+      w.colpair[u] = odd ? make_float4(r0, v.z, r1, v.w) : make_float4(v.x, r0, v.y, r1);
     }
   }
 }
@@ -179,13 +190,15 @@ __device__ __forceinline__ void top2_insert(float& p1, float& p2, float v) {
   p1 = fminf(p1, v);
 }
 
+// dynamic shared memory: column double buffer, per-warp transpose buffers, per-row running top entries, two mbarriers
 constexpr size_t kFSearchSmemBase =
-    (size_t)(kFChunk + 4) * sizeof(float4) + (size_t)kFWarps * 2 * kFColTile * kFCbStride * sizeof(float);
-constexpr size_t kFSearchSmem = kFSearchSmemBase + (size_t)3 * 4 * kFThreads * sizeof(float4);
+    (size_t)2 * (kFChunk + 4) * sizeof(float4) + (size_t)kFWarps * 2 * kFColTile * kFCbStride * sizeof(float);
+constexpr size_t kFSearchSmemTop = kFSearchSmemBase + (size_t)3 * 4 * kFThreads * sizeof(float4);
+constexpr size_t kFSearchSmem = kFSearchSmemTop + 16;
 
 struct FSearchArgs {
   const float4* rowsoa;
-  const float4* colpack;
+  const float4* colpair;
   float* rowrec;
   float* rowtop;
   float* colrec;
@@ -195,8 +208,9 @@ struct FSearchArgs {
 
 __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kernel(FSearchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* scol = reinterpret_cast<float4*>(smem_raw);                                          // [kFChunk + 4]
-  float* cball = reinterpret_cast<float*>(smem_raw + (size_t)(kFChunk + 4) * sizeof(float4));   // [warps][2][32][36]
+  float4* scol = reinterpret_cast<float4*>(smem_raw);                                              // [2][kFChunk + 4]
+  float* cball = reinterpret_cast<float*>(smem_raw + (size_t)2 * (kFChunk + 4) * sizeof(float4));   // [warps][2][32][36]
+  u64* mbar = reinterpret_cast<u64*>(smem_raw + kFSearchSmemTop);                                  // [2]
   // per-row running (smallest tile minimum, its tile, second smallest): touched once per 64-column tile, so it lives
   // in shared memory ([plane][q][thread] float4, conflict-free) instead of 48 registers
   float4* stop = reinterpret_cast<float4*>(smem_raw + kFSearchSmemBase) + threadIdx.x;            // [3][4][kFThreads]
@@ -210,6 +224,10 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
 
   long long unit = (long long)blockIdx.x * a.U;
   const long long unit_end = min(unit + a.U, a.units);
+  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
+  __syncthreads();
+  int cur = 0;           // column buffer the next chunk lands in
+  unsigned phases = 0;   // bit s: parity the next wait on buffer s expects
   pdl_wait();
   pdl_launch_dependents();   // the resolve grid may be launched (it blocks in its own pdl_wait until we are done)
 
@@ -225,6 +243,12 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
     const int seg = blockIdx.x - (int)(((long long)brb * a.nT) / a.U);   // which of the row block's segments
     const int c0 = tile0 * kFRowTile;
     const int ncols = ntile * kFRowTile;
+
+    // Column chunks arrive by TMA bulk copy (one contiguous run of the interleaved pair pack) into a double buffer:
+    // the segment's first chunk is in flight while the rows are loaded, chunk k+1 while chunk k is computed.  Both
+    // buffers are free here: every chunk iteration ends with a __syncthreads.
+    const float4* cp = a.colpair + ((size_t)b * a.Mp + c0);
+    if (tid == 0) bulk_load(scol + cur * (kFChunk + 4), cp, (unsigned)min(kFChunk, ncols) * 16u, &mbar[cur]);
 
     u64 px[8], py[8], pz[8], pu[8];
     if (has_rows) {
@@ -245,7 +269,6 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
       stop[(8 + q) * kFThreads] = make_float4(inf, inf, inf, inf);
     }
 
-    const float4* cp = a.colpack + ((size_t)b * a.Mp + c0);
     float* rrec = a.rowrec + ((size_t)b * a.nT + tile0) * a.Npad + (size_t)rb * kFRowsPerWarp + lane * kFRowsPerThread;
     float* crec = a.colrec + ((size_t)(b * a.nRB + rb) * kFColTop) * a.Mp + c0 + lane;
 
@@ -256,26 +279,25 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
 
     for (int cs = 0; cs < ncols; cs += kFChunk) {
       const int nc = min(kFChunk, ncols - cs);
-      __syncthreads();   // previous chunk / segment fully consumed
-      // two columns (c, c+1) are staged interleaved as (q0c, q0c', q1c, q1c') (q2c, q2c', wc, wc'): an LDS.128 then
-      // delivers two ready-made fp32x2 operands of the column pair
-      for (int idx = tid; idx < (nc >> 1); idx += kFThreads) {
-        const float4 ca = cp[(size_t)cs + 2 * idx], cb = cp[(size_t)cs + 2 * idx + 1];
-        scol[2 * idx] = make_float4(ca.x, cb.x, ca.y, cb.y);
-        scol[2 * idx + 1] = make_float4(ca.z, cb.z, ca.w, cb.w);
-      }
-      __syncthreads();
-      if (!has_rows) continue;
+      // two columns (c, c+1) lie interleaved as (q0c, q0c', q1c, q1c') (q2c, q2c', wc, wc'): an LDS.128 delivers two
+      // ready-made fp32x2 operands of the column pair
+      if (tid == 0 && cs + kFChunk < ncols)
+        bulk_load(scol + (cur ^ 1) * (kFChunk + 4), cp + cs + kFChunk,
+                  (unsigned)min(kFChunk, ncols - cs - kFChunk) * 16u, &mbar[cur ^ 1]);
+      mbar_wait(&mbar[cur], (phases >> cur) & 1u);
+      phases ^= 1u << cur;
+      const float4* schunk = scol + cur * (kFChunk + 4);
+      cur ^= 1;
 
 #pragma unroll 1
-      for (int t0 = 0; t0 < nc; t0 += kFRowTile) {
+      for (int t0 = 0; has_rows && t0 < nc; t0 += kFRowTile) {
         float tm[kFRowsPerThread];
 #pragma unroll
         for (int r = 0; r < kFRowsPerThread; ++r) tm[r] = inf;
 
 #pragma unroll 1
         for (int h = 0; h < kFRowTile; h += kFColTile) {
-          const float4* sp = scol + t0 + h;
+          const float4* sp = schunk + t0 + h;
           float* cbw = cb + parity * (kFColTile * kFCbStride) + lane;
           const float4* cbr = reinterpret_cast<const float4*>(cb + (parity ^ 1) * (kFColTile * kFCbStride) +
                                                               lane * kFCbStride);
@@ -378,6 +400,7 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
           stop[q * kFThreads] = m1; stop[(4 + q) * kFThreads] = t1; stop[(8 + q) * kFThreads] = m2;
         }
       }
+      __syncthreads();   // chunk fully consumed: a later bulk copy may refill this buffer
     }
 
     if (has_rows) {
@@ -462,6 +485,11 @@ __device__ __forceinline__ void round_result(unsigned d, unsigned idx, unsigned&
   }
 }
 
+// Work distribution: the ceil(B*N/32) + ceil(B*M/32) warp items are dealt out evenly over the grid (CTA c takes items
+// [c*total/grid, (c+1)*total/grid), at most one per warp).  For a single-wave problem the grid is exactly
+// SMs x 4 resident CTAs, so every SM carries the same load wherever the block scheduler (or an early programmatic
+// launch behind the search's tail) places the CTAs: with one CTA per 8 items, 512 CTAs on 148 SMs leave some SMs with
+// 4 x 8 items against an average of 27.7.
 __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGeometry g, FWorkspace w, FinalizeArgs f) {
   __shared__ double lsum[kFinWarps];
   // per-warp staging of the 32 items' broadcast data: a round reads its 4 items with two LDS.128 (one address per
@@ -474,7 +502,11 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
   const unsigned row_warps = (nrow + 31u) / 32u;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const int grp = lane >> 3, sub = lane & 7;
-  const unsigned wi = blockIdx.x * kFinWarps + warp;
+  const unsigned total_warps = row_warps + (ncol + 31u) / 32u;
+  const unsigned w_begin = (unsigned)(((u64)blockIdx.x * total_warps) / gridDim.x);
+  const unsigned w_end = (unsigned)(((u64)(blockIdx.x + 1) * total_warps) / gridDim.x);
+  // warps beyond the CTA's share take the out-of-range item (valid == false on every lane)
+  const unsigned wi = w_begin + (unsigned)warp < w_end ? w_begin + (unsigned)warp : total_warps;
   const float coef_grad = 2.f * f.coef_loss;
   const unsigned full = 0xffffffffu;
   const float inf = __int_as_float(0x7f800000);
@@ -826,7 +858,7 @@ int f_launch_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
   FGeometry g; FWorkspace w;
   if (int e = f_setup(B, N, M, workspace, workspace_bytes, &g, &w)) return e;
   const long long slots = (long long)B * (g.Npad + g.Mp);
-  RMA_CUDA_TRY(launch_pdl(chamfer_fprep_kernel, (unsigned)grid_for(slots, 256), 256u, 0, (cudaStream_t)stream_,
+  RMA_CUDA_TRY(launch_dep(pdl_site(1), chamfer_fprep_kernel, (unsigned)grid_for(slots, 256), 256u, 0, (cudaStream_t)stream_,
                           x, (long long)xsb, (long long)xsn, (long long)xsc, y, (long long)ysb, (long long)ysn,
                           (long long)ysc, g, w, zero_loss, zero_gx, zero_gy));
   return RMA_OK;
@@ -848,12 +880,12 @@ int f_launch_search(int B, int N, int M, void* workspace, size_t workspace_bytes
   FGeometry g; FWorkspace w;
   if (int e = f_setup(B, N, M, workspace, workspace_bytes, &g, &w)) return e;
   FSearchArgs a;
-  a.rowsoa = w.rowsoa; a.colpack = w.colpack; a.rowrec = w.rowrec; a.rowtop = w.rowtop; a.colrec = w.colrec;
+  a.rowsoa = w.rowsoa; a.colpair = w.colpair; a.rowrec = w.rowrec; a.rowtop = w.rowtop; a.colrec = w.colrec;
   a.N = N; a.M = M; a.nRB = g.nRB; a.Npad = g.Npad; a.nRBC = g.nRBC; a.nT = g.nT; a.Mp = g.Mp;
   a.U = g.U; a.Smax = g.Smax; a.units = g.units();
   const long long ctas = (a.units + g.U - 1) / g.U;
   if (ctas > 0x7fffffffLL) return RMA_E_BADARG;
-  RMA_CUDA_TRY(launch_pdl(chamfer_fsearch_kernel, (unsigned)ctas, (unsigned)kFThreads, kFSearchSmem,
+  RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel, (unsigned)ctas, (unsigned)kFThreads, kFSearchSmem,
                           (cudaStream_t)stream_, a));
   return RMA_OK;
 }
@@ -863,7 +895,12 @@ int f_launch_resolve(int B, int N, int M, const FinalizeArgs& f, void* workspace
   FGeometry g; FWorkspace w;
   if (int e = f_setup(B, N, M, workspace, workspace_bytes, &g, &w)) return e;
   const long long warps = ((long long)B * N + 31) / 32 + ((long long)B * M + 31) / 32;
-  RMA_CUDA_TRY(launch_pdl(chamfer_fresolve_kernel, (unsigned)grid_for(warps, kFinWarps), (unsigned)(kFinWarps * 32), 0,
+  int sms = 0, occ = 0;
+  if (int e = f_caps(&sms, &occ)) return e;
+  long long grid = grid_for(warps, kFinWarps);            // one CTA per 8 items when that is more than one wave
+  const long long wave = (long long)sms * 4;              // resident resolve CTAs (launch bounds: 4 per SM)
+  if (grid <= wave) grid = warps < wave ? warps : wave;   // single wave: the same number of CTAs on every SM
+  RMA_CUDA_TRY(launch_dep(pdl_site(4), chamfer_fresolve_kernel, (unsigned)grid, (unsigned)(kFinWarps * 32), 0,
                           (cudaStream_t)stream_, g, w, f));
   return RMA_OK;
 }

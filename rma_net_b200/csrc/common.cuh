@@ -36,7 +36,7 @@ static inline bool pdl_enabled() {
 }
 
 template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
+static inline cudaError_t launch_dep(bool pdl, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
                                      cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid, 1, 1);
@@ -47,8 +47,20 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, un
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                                     cudaStream_t stream, Args&&... args) {
+  return launch_dep(true, kernel, grid, block, smem, stream, std::forward<Args>(args)...);
+}
+
+// Experiment hook: RMA_B200_PDL_SITES is a bit mask of the launch sites that keep the attribute
+// (1 prep, 2 search, 4 resolve, 8 cd_backward; default all).
+static inline bool pdl_site(int bit) {
+  static const int mask = [] { const char* e = std::getenv("RMA_B200_PDL_SITES"); return e ? std::atoi(e) : 15; }();
+  return (mask & bit) != 0;
 }
 
 // ---- packed fp32x2 arithmetic (sm_100+: FADD2 / FMUL2 / FFMA2). ------------------------------------------------
@@ -97,5 +109,39 @@ __device__ __forceinline__ float sqdist_neg(float x, float y, float z, float nyx
 }
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// ---- TMA 1-D bulk copy global -> shared (cp.async.bulk, SASS UBLKCP), completion counted on an mbarrier --------
+// The search kernels stage their target ("column") chunks with it: the chunk is a contiguous run of float4 in the
+// prep kernel's pack, so one elected thread issues one bulk copy per chunk and the copy of chunk k+1 runs behind the
+// FP32 work on chunk k (double buffer).  Source and destination 16-byte aligned, size a multiple of 16 bytes.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// makes the initialised barriers visible to the async proxy (the TMA unit) before the first copy is issued
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, u64* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(__cvta_generic_to_global(src_gmem)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE;\n"
+      "bra MBAR_WAIT;\n"
+      "MBAR_DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 
 }  // namespace rma
