@@ -333,6 +333,7 @@ def run_ours(args):
     e2e_serial_ms = ev0.elapsed_time(ev1) / args.steps
     e2e_ms, e2e_mode = e2e_serial_ms, "serial: H2D copy, fwd+bwd, D2H loss, host sync, one after the other"
     e2e_sync_ms = e2e_serial_ms
+    e2e_extra = {}
 
     if use_graph and pair_pin is not None:
         # The same K steps the way a training loop feeds them (rma_net_b200.data.PairBatchLoader, the replacement of
@@ -417,6 +418,58 @@ def run_ours(args):
         e2e_sync_ms = e2e_modes[0]
         e2e_ms = e2e_modes[1]
 
+        # Same pipeline with the copy of step k+1 as a parallel branch INSIDE step k's graph (fork / join on the copy
+        # stream during capture): one graph launch, one event record and one event wait per step on the host.  On a
+        # box with slow host cores the Python-driven event choreography above costs more than the device step.
+        fused = []
+        for i in range(2):
+            g_i = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_i):
+                cap = torch.cuda.current_stream()
+                copy_stream.wait_stream(cap)
+                with torch.cuda.stream(copy_stream):
+                    bufs[1 - i].copy_(pair_pin, non_blocking=True)        # inputs of step k+1
+                compute(i)                                                # step k on bufs[i]
+                cap.wait_stream(copy_stream)
+            fused.append(g_i)
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+
+        def run_fused(steps):
+            bufs[0].copy_(pair_pin, non_blocking=True)                    # inputs of step 0 (inside the timed region)
+            vals = []
+            for k in range(steps):
+                i = k & 1
+                fused[i].replay()
+                ev_done[i].record(main_stream)
+                if k >= 1:
+                    ev_done[1 - i].synchronize()
+                    vals.append(float(loss_pins[1 - i]))
+            main_stream.synchronize()
+            vals.append(float(loss_pins[(steps - 1) & 1]))
+            assert len(vals) == steps
+            return vals[-1]
+
+        run_fused(4)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        fused_loss = run_fused(args.steps)
+        ev1.record()
+        barrier()
+        if abs(fused_loss - serial_loss) > 1e-6 * abs(serial_loss):
+            raise RuntimeError(f"graph-pipelined e2e loss {fused_loss} != serial {serial_loss}")
+        e2e_fused_ms = ev0.elapsed_time(ev1) / args.steps
+        e2e_extra = {"copy_stream_host_loop_ms_per_step": e2e_ms, "copy_in_graph_ms_per_step": e2e_fused_ms,
+                     "note": "value = the faster of two drivers of the same pipeline: the H2D copy of step k+1 "
+                             "issued from Python on a copy stream with events, or captured as a parallel branch of "
+                             "step k's CUDA graph (fewer host calls per step)"}
+        e2e_ms = min(e2e_ms, e2e_fused_ms)
+        e2e_mode = ("double-buffered + lagged read: the H2D copy of step k+1 overlaps step k (second device buffer, copy "
+                    "stream; rma_net_b200.data.PairBatchLoader pattern) and the host reads step k's loss (own pinned "
+                    "slot, event) while step k+1 runs; every step copies its inputs and every loss is read by the host "
+                    "inside the timed region.  sync_ms_per_step: same, but the host reads each loss before it launches "
+                    "the next step; serial_ms_per_step: nothing overlapped")
+
     # ---- aggregate over ranks (max time) ------------------------------------------------------------------------
     t = torch.tensor([ms, e2e_ms, search_ms, e2e_serial_ms, e2e_sync_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -472,7 +525,7 @@ def run_ours(args):
                 "sync_value": world * pairs / (e2e_sync_ms * 1e-3) / 1e9, "serial_ms_per_step": e2e_serial_ms,
                 "serial_value": world * pairs / (e2e_serial_ms * 1e-3) / 1e9,
                 "host_layout": "one pinned [B,2N,3] pair batch (train_view.py:369-370), one H2D copy, strided slices"
-                               if pair_pin is not None else "two pinned clouds, two H2D copies"},
+                               if pair_pin is not None else "two pinned clouds, two H2D copies", **e2e_extra},
         "gpu_launches": 4 * args.steps,      # prep + search + resolve/finalize(+loss,+grads) + cd_backward per step
         "clocks": clocks,
         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
