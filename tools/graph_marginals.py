@@ -1,0 +1,96 @@
+"""Marginal in-graph cost of each kernel of the C2 step: CUDA graphs of growing prefixes of the pipeline, replayed
+back to back (L2-warm), time per replay.    python tools/graph_marginals.py [C2]"""
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from bench import WORKLOADS, make_workload  # noqa: E402
+from rma_net_b200 import _lib  # noqa: E402
+from rma_net_b200.model.loss import loss_on_cd  # noqa: E402
+
+
+def main():
+    wl = sys.argv[1] if len(sys.argv) > 1 else "C2"
+    B, N, M, _, _ = WORKLOADS[wl]
+    dev = torch.device("cuda:0")
+    x, y = make_workload(wl)
+    xd, yd = x.to(dev), y.to(dev)
+    lib = _lib.load()
+    P = lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr())
+    wsb = lib.rma_chamfer_workspace_bytes(B, N, M)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    gx = torch.empty(B, N, 3, device=dev); gy = torch.empty(B, M, 3, device=dev)
+    sx = torch.empty(B, N, 4, device=dev); sy = torch.empty(B, M, 4, device=dev)
+    ox = torch.empty_like(gx); oy = torch.empty_like(gy)
+    loss = torch.empty((), device=dev)
+    one = torch.ones((), device=dev)
+    xs, ys = xd.stride(), yd.stride()
+    xr, yr = xd.clone().requires_grad_(True), yd.clone().requires_grad_(True)
+
+    def st():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def k_prep():
+        assert lib.rma_chamfer_prep(P(xd), *xs, P(yd), *ys, B, N, M, P(ws), wsb, st()) == 0
+
+    def k_search():
+        assert lib.rma_chamfer_search(B, N, M, P(ws), wsb, st()) == 0
+
+    def k_fwd():
+        assert lib.rma_chamfer_cd_forward(P(xd), *xs, P(yd), *ys, B, N, M, P(loss), None, None, None, None,
+                                          P(gx), P(sx), P(gy), P(sy), P(ws), wsb, st()) == 0
+
+    def k_bwd():
+        assert lib.rma_chamfer_cd_backward(P(gx), P(sx), B * N, P(gy), P(sy), B * M, P(one), P(ox), P(oy), st()) == 0
+
+    def k_step():
+        xr.grad = None; yr.grad = None
+        loss_on_cd(xr, yr).backward()
+
+    variants = {
+        "search": [k_search],
+        "prep+search": [k_prep, k_search],
+        "prep+search+resolve (cd_forward)": [k_fwd],
+        "cd_forward+cd_backward": [k_fwd, k_bwd],
+        "public API step (adds autograd's seed fill)": [k_step],
+        "prep": [k_prep],
+        "cd_backward": [k_bwd],
+    }
+    k_prep(); k_search(); k_fwd(); k_bwd(); k_step()
+    torch.cuda.synchronize()
+    res = {}
+    for name, fns in variants.items():
+        for f in fns:
+            f()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for f in fns:
+                f()
+        for _ in range(5):
+            g.replay()
+        torch.cuda.synchronize()
+        reps = 200
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
+        res[name] = round(best, 2)
+        print(f"{name:50s} {best:8.2f} us per replay", flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"graph_marginals_{wl}.json"), "w") as f:
+        json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
