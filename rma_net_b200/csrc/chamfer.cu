@@ -599,15 +599,15 @@ int f_launch_resolve(int B, int N, int M, const FinalizeArgs& f, void* workspace
 int f_read_stats(void* workspace, int B, int N, int M, unsigned* out4, void* stream_);
 }  // namespace rma
 
-// Which search runs: the filter path whenever its records (B*N*M/16 + B*N*M/43 bytes) stay below the cap, else the
-// exact path (huge single pairs).  Both return identical results.
+// Which search runs: the filter path whenever its group records (B*N*M/64 bytes) stay below the cap, else the
+// exact path (huge single pairs, SURVEY.md config C5 on few GPUs).  Both return identical results.
 static int g_force_path = 0;                                  // experiment hook: 0 auto, 1 exact, 2 filter
-// Record cap: default 1 GiB; RMA_B200_FILTER_RECORD_CAP_MB overrides it (180 GB of HBM make tens of GB reasonable for
-// a single huge pair: the row records are write-mostly, ~2 % of the search time in traffic).
+// Record cap: default 4 GiB (C5 sharded over 4 or 8 GPUs stays on the filter path); RMA_B200_FILTER_RECORD_CAP_MB
+// overrides it (180 GB of HBM make tens of GB reasonable for a single huge pair).
 static size_t g_filter_record_cap = [] {
   const char* e = std::getenv("RMA_B200_FILTER_RECORD_CAP_MB");
   const long long mb = e ? std::atoll(e) : 0;
-  return mb > 0 ? (size_t)mb << 20 : (size_t)1 << 30;
+  return mb > 0 ? (size_t)mb << 20 : (size_t)4 << 30;
 }();
 
 static bool use_filter(int B, int N, int M) {

@@ -6,12 +6,14 @@
 //            fp32x2 over two columns with the row value as broadcast scalar (FFMA2 acc, Qpair, x_row.F32, acc):
 //              f_ij = |y_j|^2 - 2 x_i.y_j   (3 FFMA, chain seeded with |y_j|^2)         -> row direction  min_j f_ij
 //              g_ij = f_ij + |x_i|^2        (1 FADD)                                    -> column direction min_i g_ij
-//            The expanded form cancels, so f/g are only a FILTER.  Per row the minimum of f over every 64-column tile
-//            is written to a record; per column and 512-row block the two smallest 16-row-group minima are written
-//            (group id packed into the 5 low mantissa bits).  No atomics, no index bookkeeping in the inner loop.
+//            The expanded form cancels, so f/g are only a FILTER.  Per row the minimum of f over each 64-column tile
+//            is folded into a running (smallest tile minimum, its tile, second smallest) per search segment; per
+//            column and 512-row block the two smallest 16-row-group minima are written (group id packed into the 5
+//            low mantissa bits).  No atomics, no index bookkeeping in the inner loop.
 //   resolve  per row: every tile whose filter minimum lies within a rigorous rounding-error guard G of the smallest
 //            one is a candidate; its 64 columns are re-evaluated in the exact difference form and the (distance,
-//            index)-lexicographic minimum is kept.  Same per column with 16-row groups.  The candidate set provably
+//            index)-lexicographic minimum is kept (more than one candidate tile: every segment whose smallest entry
+//            is within G is re-evaluated whole).  Same per column with 16-row groups.  The candidate set provably
 //            contains every exact minimiser (guard derivation below), so the result is the exact path's bit for bit.
 //
 // Guard.  eps = 2^-24, a = |x_i|, b = |y_j|, D = |x_i - y_j|^2, all on the fp32 inputs.
@@ -35,7 +37,9 @@ constexpr int kFThreads = 32 * kFWarps;
 constexpr int kFRowsPerCta = kFRowsPerWarp * kFWarps;   // 2048
 constexpr int kFColTile = 32;                           // columns per column-direction tile (= lanes)
 constexpr int kFColTop = 2;                             // packed group minima recorded per column and row block
-constexpr int kFRowTile = 64;                           // columns per row-direction record
+constexpr int kFRowTile = 64;                           // columns per row-direction tile minimum
+constexpr int kFSubTiles = 16;                          // tiles per row-direction entry (sub-segment): bounds the
+                                                        // slow path's re-evaluation to 1024 columns per candidate
 #ifndef RMA_F_CHUNK
 #define RMA_F_CHUNK 1024
 #endif
@@ -56,6 +60,7 @@ struct FGeometry {
   int Mp;     // nT * 64
   int U;      // work units (CTA row block x 64-column tile) per search CTA
   int Smax;   // max segments (CTAs) that share one CTA row block
+  int P;      // row-direction entries per segment: ceil(U / kFSubTiles)
   long long units() const { return (long long)B * nRBC * nT; }
 };
 
@@ -87,6 +92,7 @@ static FGeometry f_make_geometry(int B, int N, int M, int slots, int force_run) 
   g.Mp = g.nT * kFRowTile;
   g.U = force_run > 0 ? force_run : f_choose_unit_run(g.units(), g.nT, slots);
   g.Smax = (g.nT + g.U - 1) / g.U + 1;
+  g.P = ((g.U < g.nT ? g.U : g.nT) + kFSubTiles - 1) / kFSubTiles;
   return g;
 }
 
@@ -98,8 +104,8 @@ struct FWorkspace {
   float4* colpair;   // [B][Mp/2][2]            the same, two columns (c, c+1) interleaved as (q0c, q0c', q1c, q1c')
                      //                         (q2c, q2c', wc, wc'): the search's fp32x2 operands as they are read from
                      //                         shared memory, so a chunk is one contiguous TMA bulk copy
-  float* rowrec;     // [B][nT][Npad]           min over the tile's 64 columns of f (read only when a guard fails)
-  float* rowtop;     // [B*nRBC][Smax][3][2048] per segment: smallest tile minimum, its tile, second smallest
+  float* rowtop;     // [B*nRBC][Smax*P][3][2048] per segment and run of <= 16 tiles in it ("entry"): smallest tile
+                     //                         minimum, its tile, second smallest; unused entries of a segment (inf, 0, inf)
   float* colrec;     // [B][nRB][2][Mp]         two smallest packed group minima of g over the row block
   unsigned* stats;   // [4] rows on the slow path, columns on the slow path, row-block rescans, unused
   size_t bytes;
@@ -113,8 +119,7 @@ static FWorkspace f_carve(const FGeometry& g, void* base) {
   w.rowsoa = (float4*)(p + off);  off += align256((size_t)g.B * g.Npad * sizeof(float4));
   w.colpack = (float4*)(p + off); off += align256((size_t)g.B * g.Mp * sizeof(float4));
   w.colpair = (float4*)(p + off); off += align256((size_t)g.B * g.Mp * sizeof(float4));
-  w.rowrec = (float*)(p + off);   off += align256((size_t)g.B * g.nT * g.Npad * sizeof(float));
-  w.rowtop = (float*)(p + off);   off += align256((size_t)g.B * g.nRBC * g.Smax * 3 * kFRowsPerCta * sizeof(float));
+  w.rowtop = (float*)(p + off);   off += align256((size_t)g.B * g.nRBC * g.Smax * g.P * 3 * kFRowsPerCta * sizeof(float));
   w.colrec = (float*)(p + off);   off += align256((size_t)g.B * g.nRB * kFColTop * g.Mp * sizeof(float));
   w.stats = (unsigned*)(p + off); off += 256;
   w.bytes = off;
@@ -199,10 +204,9 @@ constexpr size_t kFSearchSmem = kFSearchSmemTop + 16;
 struct FSearchArgs {
   const float4* rowsoa;
   const float4* colpair;
-  float* rowrec;
   float* rowtop;
   float* colrec;
-  int N, M, nRB, Npad, nRBC, nT, Mp, U, Smax;
+  int N, M, nRB, Npad, nRBC, nT, Mp, U, Smax, P;
   long long units;
 };
 
@@ -262,14 +266,33 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
         pu[2 * q] = pack2(vu.x, vu.y); pu[2 * q + 1] = pack2(vu.z, vu.w);
       }
     }
+    // The running (smallest, its tile, second smallest) goes to the segment's next entry every kFSubTiles tiles and at
+    // the segment's end, and starts again empty; entries the segment does not fill are written empty.
+    float* top = a.rowtop + ((size_t)(brb * a.Smax + seg) * a.P * 3) * kFRowsPerCta + warp * kFRowsPerWarp +
+                 lane * kFRowsPerThread;
+    int sub_tiles = 0, sub = 0;
+    auto reset_top = [&]() {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      stop[q * kFThreads] = make_float4(inf, inf, inf, inf);
-      stop[(4 + q) * kFThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
-      stop[(8 + q) * kFThreads] = make_float4(inf, inf, inf, inf);
-    }
+      for (int q = 0; q < 4; ++q) {
+        stop[q * kFThreads] = make_float4(inf, inf, inf, inf);
+        stop[(4 + q) * kFThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
+        stop[(8 + q) * kFThreads] = make_float4(inf, inf, inf, inf);
+      }
+    };
+    auto flush_top = [&]() {
+      float* o = top + (size_t)sub * (3 * kFRowsPerCta);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        reinterpret_cast<float4*>(o)[q] = stop[q * kFThreads];
+        reinterpret_cast<float4*>(o + kFRowsPerCta)[q] = stop[(4 + q) * kFThreads];          // tile ids (int bits)
+        reinterpret_cast<float4*>(o + 2 * kFRowsPerCta)[q] = stop[(8 + q) * kFThreads];
+      }
+      ++sub;
+      sub_tiles = 0;
+      reset_top();
+    };
+    reset_top();
 
-    float* rrec = a.rowrec + ((size_t)b * a.nT + tile0) * a.Npad + (size_t)rb * kFRowsPerWarp + lane * kFRowsPerThread;
     float* crec = a.colrec + ((size_t)(b * a.nRB + rb) * kFColTop) * a.Mp + c0 + lane;
 
     // Column direction, software-pipelined: while tile t is computed, lane l folds column l of tile t-1 (32 per-lane
@@ -379,14 +402,11 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
           __syncwarp();   // this tile's partial minima visible to all lanes; previous buffer free for reuse
         }
 
-        // Row direction: the tile's 16 filter minima go to the record (64 contiguous bytes per thread) and into the
-        // running (smallest, its tile, second smallest) of the segment.
+        // Row direction: the tile's 16 filter minima are folded into the running (smallest, its tile, second
+        // smallest) of the segment.  (A per-tile record in global memory - B*N*M/16 bytes, read only when a guard fails -
+        // cost 2.8 us of the 83 us C2 step in stores that evict dirty L2 lines; the slow path re-evaluates the
+        // candidate SEGMENTS instead.)
         const int tile = tile0 + (cs + t0) / kFRowTile;
-        float4* o = reinterpret_cast<float4*>(rrec + (size_t)((cs + t0) / kFRowTile) * a.Npad);
-        o[0] = make_float4(tm[0], tm[1], tm[2], tm[3]);
-        o[1] = make_float4(tm[4], tm[5], tm[6], tm[7]);
-        o[2] = make_float4(tm[8], tm[9], tm[10], tm[11]);
-        o[3] = make_float4(tm[12], tm[13], tm[14], tm[15]);
         const float tilef = __int_as_float(tile);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -399,6 +419,7 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
           m1.z = fminf(m1.z, tm[4 * q + 2]); m1.w = fminf(m1.w, tm[4 * q + 3]);
           stop[q * kFThreads] = m1; stop[(4 + q) * kFThreads] = t1; stop[(8 + q) * kFThreads] = m2;
         }
+        if (++sub_tiles == kFSubTiles) flush_top();
       }
       __syncthreads();   // chunk fully consumed: a later bulk copy may refill this buffer
     }
@@ -412,14 +433,8 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
         float* o = crec + pend_col;
         o[0] = p1; o[a.Mp] = p2;
       }
-      float* top = a.rowtop + ((size_t)(brb * a.Smax + seg) * 3) * kFRowsPerCta + warp * kFRowsPerWarp +
-                   lane * kFRowsPerThread;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        reinterpret_cast<float4*>(top)[q] = stop[q * kFThreads];
-        reinterpret_cast<float4*>(top + kFRowsPerCta)[q] = stop[(4 + q) * kFThreads];          // tile ids (int bits)
-        reinterpret_cast<float4*>(top + 2 * kFRowsPerCta)[q] = stop[(8 + q) * kFThreads];
-      }
+      if (sub_tiles > 0) flush_top();
+      while (sub < a.P) flush_top();   // empty entries
       __syncwarp();   // the next segment reuses the transpose buffers
     }
   }
@@ -529,9 +544,9 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       const int rbc = i / kFRowsPerCta, brb = b * g.nRBC + rbc;
       const int kfirst = (int)(((unsigned)brb * (unsigned)g.nT) / (unsigned)g.U);
       const int klast = (int)((((unsigned)brb + 1u) * (unsigned)g.nT - 1u) / (unsigned)g.U);
-      const float* top = w.rowtop + ((size_t)brb * g.Smax * 3) * kFRowsPerCta + (i - rbc * kFRowsPerCta);
-      const int nseg = klast - kfirst + 1;
-      constexpr int kSegBatch = 12;                 // records of up to 12 segments in flight: one latency for C2 (10)
+      const float* top = w.rowtop + ((size_t)brb * g.Smax * g.P * 3) * kFRowsPerCta + (i - rbc * kFRowsPerCta);
+      const int nseg = (klast - kfirst + 1) * g.P;  // entries: P per segment, consecutive
+      constexpr int kSegBatch = 12;                 // up to 12 entries in flight: one latency for C2 (10)
       for (int s0 = 0; s0 < nseg; s0 += kSegBatch) {
         float a1[kSegBatch], a2[kSegBatch];
         int at[kSegBatch];
@@ -551,7 +566,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       }
     }
     const float thr = M1 + guard_row(rp.w, M1);
-#ifdef RMA_EXP_NO_SLOW   // timing experiment only (tools/resolve_variants.py): wrong results for the slow-path items
+#if defined(RMA_EXP_NO_SLOW) || defined(RMA_EXP_NO_SLOW_ROWS)   // timing experiment only (tools/resolve_variants.py): wrong results for the slow-path items
     const bool fast = valid;
 #else
     const bool fast = valid && M2 > thr;
@@ -592,8 +607,10 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       if ((lane >> 2) == round) { best_d = rd; best_j = rj; }
     }
 
-    // Slow path (guard failed: several tiles within the rounding error of the smallest): the warp scans the row's tile
-    // records and re-evaluates every candidate tile exactly.
+    // Slow path (guard failed: several tiles within the rounding error of the smallest).  Every candidate tile lies in
+    // an entry (a run of up to 16 tiles of one search segment) whose smallest tile minimum is within the guard, so the
+    // warp re-evaluates those entries' tiles; the lowest column among the lanes that hold the minimum = torch.min's
+    // first index.
     unsigned slow = __ballot_sync(full, valid && !fast);
     if (slow && lane == 0) atomicAdd(w.stats + 0, (unsigned)__popc(slow));
     while (slow) {
@@ -601,24 +618,62 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       const int sb = __shfl_sync(full, b, src), si = __shfl_sync(full, i, src);
       const float sthr = __shfl_sync(full, thr, src);
       const float x = __shfl_sync(full, rp.x, src), y = __shfl_sync(full, rp.y, src), z = __shfl_sync(full, rp.z, src);
-      const float* rec = w.rowrec + (size_t)sb * g.nT * g.Npad + si;
+      const int srbc = si / kFRowsPerCta;
+      const unsigned sbrb = (unsigned)(sb * g.nRBC + srbc);
+      const unsigned u0 = sbrb * (unsigned)g.nT, u1 = u0 + (unsigned)g.nT;       // the row block's units [u0, u1)
+      const unsigned kfirst = u0 / (unsigned)g.U, klast = (u1 - 1u) / (unsigned)g.U;
+      const float* top = w.rowtop + ((size_t)sbrb * g.Smax * g.P * 3) * kFRowsPerCta + (si - srbc * kFRowsPerCta);
+      const float4* cq = w.colpack + (size_t)sb * g.Mp;
       unsigned bd = 0xffffffffu, bj = 0xffffffffu;
-      for (int base = 0; base < g.nT; base += 32) {
-        const int tile = base + lane;
-        unsigned hits = __ballot_sync(full, tile < g.nT && rec[(size_t)tile * g.Npad] <= sthr);
-        while (hits) {
-          const int ht = base + __ffs(hits) - 1; hits &= hits - 1;
-          const int ja = ht * kFRowTile + lane;
-          const float4 qa = w.colpack[(size_t)sb * g.Mp + ja], qb = w.colpack[(size_t)sb * g.Mp + ja + 32];
-          const unsigned d0 = ja < g.M ? __float_as_uint(sqdist_q(x, y, z, qa)) : 0xffffffffu;
-          const unsigned d1 = ja + 32 < g.M ? __float_as_uint(sqdist_q(x, y, z, qb)) : 0xffffffffu;
-          const unsigned dm = min(d0, d1);
-          const unsigned mn = __reduce_min_sync(full, dm);
-          const unsigned jm = __reduce_min_sync(full, dm == mn ? (unsigned)(d0 <= d1 ? ja : ja + 32) : 0xffffffffu);
-          if (mn < bd || (mn == bd && jm < bj)) { bd = mn; bj = jm; }
+      // One tile for this lane's 8-lane group: the fast path's re-filter (f_j <= thr, bit-identical to the search's
+      // chain; padded columns never pass) in front of the exact evaluation, 8 loads in flight per lane.
+      auto eval_tile = [&](unsigned tile) {
+        const int j0 = (int)tile * kFRowTile + sub;
+        float4 q[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) q[c] = cq[j0 + 8 * c];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float fj = __fmaf_rn(x, q[c].x, __fmaf_rn(y, q[c].y, __fmaf_rn(z, q[c].z, q[c].w)));
+          if (fj <= sthr) {
+            const unsigned d = __float_as_uint(sqdist_q(x, y, z, q[c])), jc = (unsigned)(j0 + 8 * c);
+            if (d < bd || (d == bd && jc < bj)) { bd = d; bj = jc; }
+          }
+        }
+      };
+      const unsigned nent = (klast - kfirst + 1u) * (unsigned)g.P;
+      for (unsigned base = 0; base < nent; base += 32u) {
+        // one entry per lane, all in flight; empty entries hold inf
+        const unsigned e = base + (unsigned)lane;
+        const float* tp = top + (size_t)(e < nent ? e : base) * (3 * kFRowsPerCta);
+        const float a1 = e < nent ? tp[0] : inf;
+        const unsigned t1 = (unsigned)__float_as_int(tp[kFRowsPerCta]);
+        const float a2 = e < nent ? tp[2 * kFRowsPerCta] : inf;
+        const bool hit = a1 <= sthr;
+        // An entry whose SECOND smallest tile minimum is above the threshold has one candidate tile, the recorded one:
+        // the usual case (two near-tied tiles in two entries) then costs a single round.
+        const unsigned singles = __ballot_sync(full, hit && !(a2 <= sthr));
+        unsigned wholes = __ballot_sync(full, hit && a2 <= sthr);
+        const int nsingle = __popc(singles);
+        for (int r = 0; r < nsingle; r += 4) {            // four tiles per round, one per 8-lane group
+          const int idx = r + grp;
+          const unsigned from = idx < nsingle ? __fns(singles, 0, idx + 1) : 0u;
+          const unsigned tile = __shfl_sync(full, t1, (int)from);
+          if (idx < nsingle) eval_tile(tile);
+        }
+        while (wholes) {                                  // every tile of the entry
+          const unsigned he = base + (unsigned)__ffs(wholes) - 1u; wholes &= wholes - 1u;
+          const unsigned k = kfirst + he / (unsigned)g.P, pe = he % (unsigned)g.P;
+          const unsigned ua = max(k * (unsigned)g.U, u0), ub = min((k + 1u) * (unsigned)g.U, u1);   // the segment's units
+          const unsigned ta = ua - u0 + pe * kFSubTiles;              // first tile of the entry, within the row block
+          const unsigned tb = min(ta + kFSubTiles, ub - u0);          // the entry's tiles [ta, tb)
+          for (unsigned tr = ta; tr < tb; tr += 4u)
+            if (tr + (unsigned)grp < tb) eval_tile(tr + (unsigned)grp);
         }
       }
-      if (lane == src) { best_d = bd; best_j = bj; }
+      const unsigned mn = __reduce_min_sync(full, bd);
+      const unsigned jm = __reduce_min_sync(full, bd == mn ? bj : 0xffffffffu);
+      if (lane == src) { best_d = mn; best_j = jm; }
     }
 
     myd = __uint_as_float(best_d);
@@ -670,7 +725,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       }
     }
     const float thr = M1 + guard_col(cq.w, M1);
-#ifdef RMA_EXP_NO_SLOW   // timing experiment only (tools/resolve_variants.py): wrong results for the slow-path items
+#if defined(RMA_EXP_NO_SLOW) || defined(RMA_EXP_NO_SLOW_COLS)   // timing experiment only (tools/resolve_variants.py): wrong results for the slow-path items
     const bool fast = valid;
 #else
     const bool fast = valid && M2 > thr;
@@ -802,10 +857,10 @@ bool f_sizes_ok(int B, int N, int M) {
   return true;
 }
 
-// Bytes of the filter's tile records alone (the dispatcher's size criterion; device independent).
+// Bytes of the filter's group records alone (the dispatcher's size criterion; device independent): B*N*M/64.
 size_t f_record_bytes(int B, int N, int M) {
   const FGeometry g = f_make_geometry(B, N, M, 296, 1);
-  return ((size_t)g.B * g.nT * g.Npad + (size_t)g.B * g.nRB * kFColTop * g.Mp) * sizeof(float);
+  return ((size_t)g.B * g.nRB * kFColTop * g.Mp) * sizeof(float);
 }
 
 // SM count and resident search CTAs per SM of the current device.  Immutable device properties, cached per device
@@ -880,9 +935,9 @@ int f_launch_search(int B, int N, int M, void* workspace, size_t workspace_bytes
   FGeometry g; FWorkspace w;
   if (int e = f_setup(B, N, M, workspace, workspace_bytes, &g, &w)) return e;
   FSearchArgs a;
-  a.rowsoa = w.rowsoa; a.colpair = w.colpair; a.rowrec = w.rowrec; a.rowtop = w.rowtop; a.colrec = w.colrec;
+  a.rowsoa = w.rowsoa; a.colpair = w.colpair; a.rowtop = w.rowtop; a.colrec = w.colrec;
   a.N = N; a.M = M; a.nRB = g.nRB; a.Npad = g.Npad; a.nRBC = g.nRBC; a.nT = g.nT; a.Mp = g.Mp;
-  a.U = g.U; a.Smax = g.Smax; a.units = g.units();
+  a.U = g.U; a.Smax = g.Smax; a.P = g.P; a.units = g.units();
   const long long ctas = (a.units + g.U - 1) / g.U;
   if (ctas > 0x7fffffffLL) return RMA_E_BADARG;
   RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel, (unsigned)ctas, (unsigned)kFThreads, kFSearchSmem,

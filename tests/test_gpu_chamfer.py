@@ -387,7 +387,7 @@ def test_paths_agree_and_auto_dispatch(cuda):
             assert lib.rma_exp_chamfer_path_info(3, 2500, 1900, None, None, None) == (0 if path == 1 or cap == 1 else 1)
             outs.append([t.cpu() for t in chamfer_dist_with_idx(x, y)])
     finally:
-        lib.rma_exp_set_chamfer_path(0, 1 << 30)
+        lib.rma_exp_set_chamfer_path(0, 4 << 30)                    # back to the default cap
     for o in outs[1:]:
         for a, b_ in zip(outs[0], o):
             assert torch.equal(a, b_)
@@ -465,4 +465,42 @@ def test_filter_path_fuzz_against_exact_path(cuda):
             for a, b_ in zip(*outs):
                 assert torch.equal(a, b_), (trial, kind, B, N, M, scale)
     finally:
+        lib.rma_exp_set_chamfer_path(0, 0)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lattice", "dups", "all_equal"])
+def test_filter_long_unit_runs_and_slow_path(cuda, kind):
+    """Forced unit runs of 1 .. 200 tiles per search CTA: segments with several row-direction entries (one per 16 tiles),
+    partially filled and empty entries, runs that cross row blocks and batch elements.  Tie-heavy clouds (lattice,
+    duplicated points, one repeated point) send most items through the slow path, which re-evaluates whole candidate
+    entries; the result must still equal the exact path's bit for bit (distances and indices)."""
+    from rma_net_b200 import _lib
+    from rma_net_b200.model.loss import chamfer_dist_with_idx
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+    B, N, M = 2, 3000, 5003                                      # nT = 79 tiles, 2 CTA row blocks per batch element
+
+    def cloud(n):
+        if kind == "uniform":
+            p = rng.uniform(-1, 1, (B, n, 3))
+        elif kind == "lattice":
+            p = rng.integers(-5, 6, (B, n, 3)).astype(np.float64) * 0.5
+        elif kind == "dups":
+            base = rng.uniform(-1, 1, (B, 40, 3))
+            p = base[:, rng.integers(0, 40, n)]
+        else:
+            p = np.tile(np.array([0.3, -0.2, 0.9]), (B, n, 1))
+        return p.astype(np.float32)
+    xt, yt = torch.from_numpy(cloud(N)).to(cuda), torch.from_numpy(cloud(M)).to(cuda)
+    try:
+        lib.rma_exp_set_chamfer_path(1, 0)
+        ref = [t.cpu() for t in chamfer_dist_with_idx(xt, yt)]
+        lib.rma_exp_set_chamfer_path(2, 0)
+        for run in (1, 15, 16, 17, 33, 79, 100, 200):
+            lib.rma_exp_set_search_debug(None, run, 0)
+            out = [t.cpu() for t in chamfer_dist_with_idx(xt, yt)]
+            for a, b_ in zip(out, ref):
+                assert torch.equal(a, b_), (kind, run)
+    finally:
+        lib.rma_exp_set_search_debug(None, 0, 0)
         lib.rma_exp_set_chamfer_path(0, 0)

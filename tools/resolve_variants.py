@@ -17,6 +17,8 @@ from rma_net_b200 import _lib, build as b  # noqa: E402
 VARIANTS = {
     "base": [],
     "noslow": ["-DRMA_EXP_NO_SLOW"],
+    "noslow_rows": ["-DRMA_EXP_NO_SLOW_ROWS"],
+    "noslow_cols": ["-DRMA_EXP_NO_SLOW_COLS"],
 }
 
 
