@@ -507,9 +507,9 @@ def run_ours(args):
         "roofline": {"bound": "fp32_fma", "kernel": search_kernel, "achieved": achieved_tflops,
                      "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the ncu --set full
-                     # capture of the C2 step (profiles/r01n_ncu_full_selected.csv): 2.12 MB read + 2.05 MB written
+                     # capture of the C2 step (profiles/r01p_ncu_full_selected.csv): 2.12 MB read + 0.51 MB written
                      # (compute-bound: inputs and records live in L2); not re-measured for other workloads
-                     "traffic": 4.17e6 if (name == "C2" and filt == 1) else None, "kernel_ms": search_ms,
+                     "traffic": 2.63e6 if (name == "C2" and filt == 1) else None, "kernel_ms": search_ms,
                      "note": ("achieved = ALGORITHMIC 12 FLOP (6 FMA) per point-pair (SURVEY.md section 8d) / kernel "
                               "time.  The filter kernel itself issues 3 FFMA + 1 FADD + 2 min per pair (its exact "
                               "re-evaluation of the candidates runs in the resolve kernel), so frac is a fraction "

@@ -87,6 +87,21 @@ def main():
             best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
         res[name] = round(best, 2)
         print(f"{name:50s} {best:8.2f} us per replay", flush=True)
+        if name.startswith("public API"):
+            # the bench's protocol on the same graph: one event pair per replay, without / with the 256 MiB L2 flush
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+            for label, do_flush in (("per-replay events, no flush", False), ("per-replay events, L2 flush", True)):
+                ts = []
+                for _ in range(60):
+                    if do_flush:
+                        flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); g.replay(); e1.record()
+                    ts.append((e0, e1))
+                torch.cuda.synchronize()
+                v = sorted(a.elapsed_time(b) * 1e3 for a, b in ts[10:])
+                res[label] = round(v[len(v) // 2], 2)
+                print(f"{label:50s} {v[len(v) // 2]:8.2f} us (median)", flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"graph_marginals_{wl}.json"), "w") as f:
         json.dump(res, f, indent=1)
