@@ -540,10 +540,15 @@ def run_ours(args):
             "value": sample_b * N * M / sec / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"first {sample_b} of {B} batch elements, best of 3, torch CPU fp32 (reference formulation: "
                       f"expanded-form [B,N,M] matrix + autograd)"}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0:
+        # the JSON line must be the LAST line of stdout: NCCL's version banner sits in the C stdio buffer when stdout
+        # is a pipe and would otherwise be flushed behind it at exit
+        import ctypes as _ct
+        sys.stdout.flush()
+        _ct.CDLL(None).fflush(None)
+        print(json.dumps(line), flush=True)
 
 
 def main():
