@@ -403,18 +403,24 @@ def run_ours(args):
             assert len(vals) == steps
             return vals[-1]
 
+        # Every e2e figure below is the best of E2E_REPS runs of K steps each: a single host hiccup (a few ms on a
+        # shared box) is a quarter of a K = 200 run of 18 ms, and the host is inside every one of these loops.
+        E2E_REPS = 3
         e2e_modes = {}
         for lag in (0, 1):
             run_pipelined(4, lag=lag)
-            barrier()
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-            pipelined_loss = run_pipelined(args.steps, ev0, lag=lag)
-            ev1.record()
-            barrier()
-            if abs(pipelined_loss - serial_loss) > 1e-6 * abs(serial_loss):
-                raise RuntimeError(f"pipelined e2e loss {pipelined_loss} != serial {serial_loss}")
-            e2e_modes[lag] = ev0.elapsed_time(ev1) / args.steps
+            best = float("inf")
+            for _ in range(E2E_REPS):
+                barrier()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                pipelined_loss = run_pipelined(args.steps, ev0, lag=lag)
+                ev1.record()
+                barrier()
+                if abs(pipelined_loss - serial_loss) > 1e-6 * abs(serial_loss):
+                    raise RuntimeError(f"pipelined e2e loss {pipelined_loss} != serial {serial_loss}")
+                best = min(best, ev0.elapsed_time(ev1) / args.steps)
+            e2e_modes[lag] = best
         e2e_sync_ms = e2e_modes[0]
         e2e_ms = e2e_modes[1]
 
@@ -450,15 +456,17 @@ def run_ours(args):
             return vals[-1]
 
         run_fused(4)
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        fused_loss = run_fused(args.steps)
-        ev1.record()
-        barrier()
-        if abs(fused_loss - serial_loss) > 1e-6 * abs(serial_loss):
-            raise RuntimeError(f"graph-pipelined e2e loss {fused_loss} != serial {serial_loss}")
-        e2e_fused_ms = ev0.elapsed_time(ev1) / args.steps
+        e2e_fused_ms = float("inf")
+        for _ in range(E2E_REPS):
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            fused_loss = run_fused(args.steps)
+            ev1.record()
+            barrier()
+            if abs(fused_loss - serial_loss) > 1e-6 * abs(serial_loss):
+                raise RuntimeError(f"graph-pipelined e2e loss {fused_loss} != serial {serial_loss}")
+            e2e_fused_ms = min(e2e_fused_ms, ev0.elapsed_time(ev1) / args.steps)
         e2e_extra = {"copy_stream_host_loop_ms_per_step": e2e_ms, "copy_in_graph_ms_per_step": e2e_fused_ms,
                      "note": "value = the faster of two drivers of the same pipeline: the H2D copy of step k+1 "
                              "issued from Python on a copy stream with events, or captured as a parallel branch of "
@@ -468,7 +476,8 @@ def run_ours(args):
                     "stream; rma_net_b200.data.PairBatchLoader pattern) and the host reads step k's loss (own pinned "
                     "slot, event) while step k+1 runs; every step copies its inputs and every loss is read by the host "
                     "inside the timed region.  sync_ms_per_step: same, but the host reads each loss before it launches "
-                    "the next step; serial_ms_per_step: nothing overlapped")
+                    "the next step; serial_ms_per_step: nothing overlapped.  Pipelined figures: best of 3 runs of K "
+                    "steps each")
 
     # ---- aggregate over ranks (max time) ------------------------------------------------------------------------
     t = torch.tensor([ms, e2e_ms, search_ms, e2e_serial_ms, e2e_sync_ms], dtype=torch.float64, device=dev)
