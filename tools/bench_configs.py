@@ -93,6 +93,20 @@ def main():
             return loss
 
         ms_fused = timed(step_fused, dev, 10, world)
+
+        # the same two steps replayed as CUDA graphs: eager, the 8 warp forward / backward pairs and the autograd glue
+        # are host-bound (a warp fwd+bwd pair costs ~0.2 ms of Python against ~10 us of device time)
+        def graphed(fn):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                fn()
+            return timed(gr.replay, dev, 20, world)
+
+        ms_graph = graphed(step)
+        ms_fused_graph = graphed(step_fused)
         pairs = T * B * N * N
         # warp kernels alone (HBM-bound): fwd 40 B/point, bwd reads src+prev+w+go, writes grad_w
         prev = src.clone()
@@ -107,6 +121,10 @@ def main():
                     "fp32_fma_peak_frac": 6 * pairs / (ms * 1e-3) / PEAK_FMA,
                     "ms_per_step_stage_fused": ms_fused,
                     "fp32_fma_peak_frac_stage_fused": 6 * pairs / (ms_fused * 1e-3) / PEAK_FMA,
+                    "ms_per_step_cuda_graph": ms_graph,
+                    "fp32_fma_peak_frac_cuda_graph": 6 * pairs / (ms_graph * 1e-3) / PEAK_FMA,
+                    "ms_per_step_stage_fused_cuda_graph": ms_fused_graph,
+                    "fp32_fma_peak_frac_stage_fused_cuda_graph": 6 * pairs / (ms_fused_graph * 1e-3) / PEAK_FMA,
                     "warp_fwd_bwd_pair_ms": wms,
                     "warp_fwd_bwd_algorithmic_GBps": B * N * (40 + 44) / (wms * 1e-3) / 1e9})
     if "C4" in cfgs:
