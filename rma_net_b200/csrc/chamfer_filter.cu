@@ -678,7 +678,8 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
 
     myd = __uint_as_float(best_d);
     wb = (valid && f.batch_weight) ? f.batch_weight[b] : 1.f;
-    const int j = (int)best_j;
+    // no candidate at all happens only for NaN coordinates (every comparison fails): NaN distance, index 0
+    const int j = best_d == 0xffffffffu ? 0 : (int)best_j;
     if (valid) {
       if (f.dist1) f.dist1[t] = myd;
       if (f.idx1) f.idx1[t] = j;
@@ -806,7 +807,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
 
     myd = __uint_as_float(best_d);
     wb = (valid && f.batch_weight) ? f.batch_weight[b] : 1.f;
-    const int i = (int)best_i;
+    const int i = best_d == 0xffffffffu ? 0 : (int)best_i;
     if (valid) {
       if (f.dist2) f.dist2[t] = myd;
       if (f.idx2) f.idx2[t] = i;

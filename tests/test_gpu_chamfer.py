@@ -504,3 +504,24 @@ def test_filter_long_unit_runs_and_slow_path(cuda, kind):
     finally:
         lib.rma_exp_set_search_debug(None, 0, 0)
         lib.rma_exp_set_chamfer_path(0, 0)
+
+
+def test_nan_point_does_not_corrupt_anything(cuda, chamfer_path):
+    """NaN coordinates are outside the contract, but they must not send an index out of range (the
+    gradient scatter would write there): every index stays inside [0, M) / [0, N); on the filter path the NaN point's own
+    distance is NaN."""
+    from rma_net_b200.model.loss import chamfer_dist_with_idx, loss_on_cd
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(2, 700, 3, generator=g) * 2 - 1)
+    y = (torch.rand(2, 900, 3, generator=g) * 2 - 1)
+    x[0, 13, 1] = float("nan")
+    y[1, 77, 0] = float("nan")
+    xd, yd = x.to(cuda).requires_grad_(True), y.to(cuda).requires_grad_(True)
+    d1, d2, i1, i2 = chamfer_dist_with_idx(xd, yd)
+    torch.cuda.synchronize()
+    if chamfer_path == "filter":                       # the exact path's minimum skips NaN candidates instead
+        assert torch.isnan(d1[0, 13]) and torch.isnan(d2[1, 77])
+    assert int(i1.min()) >= 0 and int(i1.max()) < 900 and int(i2.min()) >= 0 and int(i2.max()) < 700
+    loss_on_cd(xd, yd).backward()
+    torch.cuda.synchronize()
+    assert xd.grad.shape == x.shape and yd.grad.shape == y.shape
