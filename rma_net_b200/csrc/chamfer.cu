@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(256) chamfer_backward_kernel(
     const float* __restrict__ y, long long ysb, long long ysn, long long ysc,
     int B, int N, int M, const float* __restrict__ g1, const float* __restrict__ g2,
     const int* __restrict__ idx1, const int* __restrict__ idx2, float* __restrict__ grad_x,
-    float* __restrict__ grad_y) {
+    float* __restrict__ grad_y, int vec_ok) {
   const long long nrow = (long long)B * N, ncol = (long long)B * M;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // grid covers whole warps
   // Every lane of the warp takes part in the match/shuffle; out-of-range or zero-gradient lanes carry a unique
@@ -474,6 +474,7 @@ __global__ void __launch_bounds__(256) chamfer_backward_kernel(
   long long key = -1 - (long long)lane_id();
   float* own = nullptr;
   float* other = nullptr;
+  long long self = 0, partner = 0;
   bool live = false;
   if (t < nrow) {
     if (g1) {
@@ -484,8 +485,9 @@ __global__ void __launch_bounds__(256) chamfer_backward_kernel(
       const float* q = y + b * ysb + j * ysn;
       vx = gg * (p[0] - q[0]); vy = gg * (p[xsc] - q[ysc]); vz = gg * (p[2 * xsc] - q[2 * ysc]);
       own = grad_x ? grad_x + t * 3 : nullptr;
-      other = grad_y ? grad_y + ((long long)b * M + j) * 3 : nullptr;
-      key = (long long)b * M + j;
+      other = grad_y;
+      self = t; partner = (long long)b * M + j;
+      key = partner;
       live = true;
     }
   } else if (t < nrow + ncol) {
@@ -498,15 +500,24 @@ __global__ void __launch_bounds__(256) chamfer_backward_kernel(
       const float* q = x + b * xsb + i * xsn;
       vx = gg * (p[0] - q[0]); vy = gg * (p[ysc] - q[xsc]); vz = gg * (p[2 * ysc] - q[2 * xsc]);
       own = grad_y ? grad_y + u * 3 : nullptr;
-      other = grad_x ? grad_x + ((long long)b * N + i) * 3 : nullptr;
-      key = ncol + (long long)b * N + i;   // x->y keys live in [0, ncol): disjoint (a warp can straddle both halves)
+      other = grad_x;
+      self = u; partner = (long long)b * N + i;
+      key = ncol + partner;   // x->y keys live in [0, ncol): disjoint (a warp can straddle both halves)
       live = true;
     }
   }
+  // The kernel is bound by L2 transactions (profiles/r01p_hbm_kernels_dram.md): with 8-byte aligned outputs a point's
+  // (x, y) or (y, z) pair goes out as one vector atomic, two transactions per point instead of three.
   if (live && own) {   // own-point term: one writer per address from this half, the other half scatters into it
-    atomicAdd(own + 0, vx); atomicAdd(own + 1, vy); atomicAdd(own + 2, vz);
+    if (vec_ok) {
+      if ((self & 1) == 0) { atomicAdd(reinterpret_cast<float2*>(own), make_float2(vx, vy)); atomicAdd(own + 2, vz); }
+      else { atomicAdd(own, vx); atomicAdd(reinterpret_cast<float2*>(own + 1), make_float2(vy, vz)); }
+    } else {
+      atomicAdd(own + 0, vx); atomicAdd(own + 1, vy); atomicAdd(own + 2, vz);
+    }
   }
-  scatter_add3(other, key, live && other != nullptr, -vx, -vy, -vz);
+  if (vec_ok) scatter_add3_v2(other, partner, key, live && other != nullptr, -vx, -vy, -vz);
+  else scatter_add3(other ? other + partner * 3 : nullptr, key, live && other != nullptr, -vx, -vy, -vz);
 }
 
 __global__ void __launch_bounds__(256) sqrdis_map_kernel(
@@ -857,8 +868,10 @@ int rma_chamfer_backward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
   if (grad_y) RMA_CUDA_TRY(cudaMemsetAsync(grad_y, 0, (size_t)B * M * 3 * sizeof(float), stream));
   if ((!grad_x && !grad_y) || (!g1 && !g2)) return RMA_OK;
   const long long n = (long long)B * ((long long)N + M);
+  // vector atomics need 8-byte aligned bases (any cudaMalloc / torch allocation; an odd float offset falls back)
+  const int vec_ok = (((uintptr_t)grad_x | (uintptr_t)grad_y) & 7u) == 0;
   chamfer_backward_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, g1,
-                                                                g2, idx1, idx2, grad_x, grad_y);
+                                                                g2, idx1, idx2, grad_x, grad_y, vec_ok);
   RMA_LAUNCH_CHECK();
   return RMA_OK;
 }

@@ -42,6 +42,26 @@ __device__ __forceinline__ void scatter_add3(float* dst, long long key, bool liv
   }
 }
 
+// Same into a dense [.,3] float buffer whose base is 8-byte aligned: point p starts at byte 12 p, so either its (x, y) or
+// its (y, z) pair is 8-byte aligned and goes out as one vector atomic - two L2 transactions per target instead of three
+// (the generic backward is bound by L2 transactions, profiles/r01p_hbm_kernels_dram.md).
+__device__ __forceinline__ void scatter_add3_v2(float* base, long long point, long long key, bool live, float vx,
+                                                float vy, float vz) {
+  if (!live) key = -1 - (long long)lane_id();
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  if (__any_sync(0xffffffffu, peers != (1u << lane_id()))) reduce_peers(peers, vx, vy, vz);
+  if (live && (unsigned)(__ffs(peers) - 1) == lane_id()) {
+    float* dst = base + point * 3;
+    if ((point & 1) == 0) {
+      atomicAdd(reinterpret_cast<float2*>(dst), make_float2(vx, vy));
+      atomicAdd(dst + 2, vz);
+    } else {
+      atomicAdd(dst, vx);
+      atomicAdd(reinterpret_cast<float2*>(dst + 1), make_float2(vy, vz));
+    }
+  }
+}
+
 // Warp-aggregated scatter into a float4-strided buffer: one 16-byte vector atomic (RED.128) per distinct target.
 __device__ __forceinline__ void scatter_add4(float4* dst, long long key, bool live, float vx, float vy, float vz) {
   if (!live) key = -1 - (long long)lane_id();
