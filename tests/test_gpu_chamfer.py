@@ -525,3 +525,33 @@ def test_nan_point_does_not_corrupt_anything(cuda, chamfer_path):
     loss_on_cd(xd, yd).backward()
     torch.cuda.synchronize()
     assert xd.grad.shape == x.shape and yd.grad.shape == y.shape
+
+
+@pytest.mark.parametrize("shape", [(4, 16384, 12000), (1, 65536, 40001)])
+@pytest.mark.parametrize("kind", ["uniform", "lattice"])
+def test_filter_equals_exact_at_large_sizes(cuda, shape, kind):
+    """Sizes at which a search CTA's run (chosen automatically) spans several row-direction entries and the resolve reads
+    dozens of entries per row; the lattice cloud (41^3 positions, many duplicates) sends a large share of the items through
+    the slow path.  Filter path == exact path bit for bit (tools/parity_large.py runs the longer list)."""
+    from rma_net_b200 import _lib
+    from rma_net_b200.model.loss import chamfer_dist_with_idx
+    lib = _lib.load()
+    B, N, M = shape
+    rng = np.random.default_rng(11)
+
+    def cloud(n):
+        if kind == "uniform":
+            p = rng.uniform(-1, 1, (B, n, 3))
+        else:
+            p = rng.integers(-20, 21, (B, n, 3)).astype(np.float64) * 0.05
+        return torch.from_numpy(p.astype(np.float32)).to(cuda)
+    x, y = cloud(N), cloud(M)
+    outs = []
+    try:
+        for path in (2, 1):
+            lib.rma_exp_set_chamfer_path(path, 0)
+            outs.append([t.cpu() for t in chamfer_dist_with_idx(x, y)])
+    finally:
+        lib.rma_exp_set_chamfer_path(0, 0)
+    for a, b_ in zip(*outs):
+        assert torch.equal(a, b_)
