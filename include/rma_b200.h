@@ -147,11 +147,14 @@ int rma_se3_transform_forward(const float* g, const float* a, int64_t a_st, int6
                               void* stream);
 /* Backward of transform (torch matmul autograd in the reference): grad_a = R^T go; grad_g[:3,:3] = sum_k go a^T;
  * grad_g[:3,3] = sum_k go; grad_g[3,:] = 0.  grad_g [G,4,4] contiguous (overwritten), grad_a strided like a.
- * Either output may be NULL. */
+ * Either output may be NULL.  The sums over the P points are accumulated in double (they feed the cancelling cross
+ * products of ExpMap.backward) and rounded once; scratch: G*12 doubles (8-byte aligned), needed when grad_g is wanted
+ * and P >= 64, zeroed inside the call. */
 int rma_se3_transform_backward(const float* g, const float* a, int64_t a_st, int64_t a_sk, int64_t a_sc,
                                const float* go, int64_t go_st, int64_t go_sk, int64_t go_sc,
                                int64_t G, int64_t P, float* grad_g,
-                               float* grad_a, int64_t ga_st, int64_t ga_sk, int64_t ga_sc, void* stream);
+                               float* grad_a, int64_t ga_st, int64_t ga_sk, int64_t ga_sc, double* scratch,
+                               void* stream);
 
 /* Fused recurrent-loop warp (model/network.py:652-655; stage 0: 567-570; rigid net: 840-843):
  *   g = exp(phi[b]);  rigid = R src[b,k] + p;  out[b,k] = w ? w[b,k]*rigid + (1-w[b,k])*prev[b,k] : rigid
@@ -162,16 +165,21 @@ int rma_warp_forward(const float* phi, const float* src, int64_t s_sb, int64_t s
                      const float* w, const float* prev, int64_t p_sb, int64_t p_sn, int64_t p_sc,
                      int B, int N, float* out, int64_t o_sb, int64_t o_sn, int64_t o_sc,
                      float* g_out, float* rigid_out, void* stream);
-/* Backward of the fused warp w.r.t. phi and w (prev is detached in the reference, network.py:606; src is data):
- *   grad_w[b,k] = sum_c go[b,k,c] (rigid_c - prev_c);  grad_rigid = w*go (or go);  then transform backward and
- *   ExpMap.backward chained:  grad_phi [B,6] (overwritten).  grad_src (optional, strided like src) = R^T grad_rigid.
- * scratch: B*12 floats, zeroed inside the call. */
+/* Backward of the fused warp w.r.t. phi and w (prev is detached in the reference, network.py:606; src is data).
+ * Three gradients can arrive, one per output of the forward (any may be NULL, not all of go / go_rigid / grad_g_in
+ * need be given): go = d/d out, go_rigid = d/d rigid_out (same strides as go; deform_rigid_points_list), grad_g_in
+ * [B,4,4] = d/d g_out (rigid_matrix_list -> loss_on_tran, loss.py:224-230, 311-319).
+ *   grad_w[b,k] = sum_c go[b,k,c] (rigid_c - prev_c);  grad_rigid = w*go (or go) + go_rigid;  then transform backward
+ *   (+ grad_g_in) and ExpMap.backward chained:  grad_phi [B,6] (overwritten).  grad_src (optional, strided like src)
+ *   = R^T grad_rigid.
+ * The 12 per-batch sums and the cross products of ExpMap.backward are accumulated in double.
+ * scratch: B*12 doubles (8-byte aligned), zeroed inside the call. */
 int rma_warp_backward(const float* phi, const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc,
                       const float* w, const float* prev, int64_t p_sb, int64_t p_sn, int64_t p_sc,
-                      const float* go, int64_t g_sb, int64_t g_sn, int64_t g_sc,
-                      int B, int N, float* grad_phi, float* grad_w,
+                      const float* go, const float* go_rigid, int64_t g_sb, int64_t g_sn, int64_t g_sc,
+                      const float* grad_g_in, int B, int N, float* grad_phi, float* grad_w,
                       float* grad_src, int64_t gs_sb, int64_t gs_sn, int64_t gs_sc,
-                      float* scratch, void* stream);
+                      double* scratch, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * point_render / point_masker — the reference's `model/exfunc` CUDA extension.

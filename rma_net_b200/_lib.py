@@ -37,11 +37,11 @@ SIGNATURES = {
     "rma_se3_exp_backward": (c_int, [_P, _P, _I64, _P, _P]),
     "rma_se3_transform_forward": (c_int, [_P, _P, _I64, _I64, _I64, _I64, _I64, _P, _I64, _I64, _I64, _P]),
     "rma_se3_transform_backward": (c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P,
-                                           _P, _I64, _I64, _I64, _P]),
+                                           _P, _I64, _I64, _I64, _P, _P]),
     "rma_warp_forward": (c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _I64, _I64, _I64, c_int, c_int,
                                  _P, _I64, _I64, _I64, _P, _P, _P]),
-    "rma_warp_backward": (c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _I64, _I64, _I64, _P, _I64, _I64, _I64,
-                                  c_int, c_int, _P, _P, _P, _I64, _I64, _I64, _P, _P]),
+    "rma_warp_backward": (c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _I64, _I64, _I64, _P, _P, _I64, _I64, _I64,
+                                  _P, c_int, c_int, _P, _P, _P, _I64, _I64, _I64, _P, _P]),
     "rma_point_render_forward": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                          _P, _P, _P, _P, _P, _P, _P, _P]),
     "rma_point_render_backward": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),

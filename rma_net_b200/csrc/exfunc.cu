@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kMaskThreads) mask_norm_kernel(const float* __
                                                                  int splits, const MaskEntry* __restrict__ entries,
                                                                  const int* __restrict__ counts,
                                                                  float* __restrict__ spart) {
-  __shared__ float2 sp[kMaskThreads];
+  __shared__ __align__(16) float2 sp[kMaskThreads];   // read back as float4 (two points per LDS.128)
   const int b = blockIdx.y, split = blockIdx.z;
   const int count = counts[b];
   const int per = (N + splits - 1) / splits;

@@ -63,19 +63,21 @@ __device__ __forceinline__ void se3_exp(const float* __restrict__ x, float (&g)[
   g[11] = V20 * v1 + V21 * v2 + V22 * v3;
 }
 
-// ExpMap.backward closed form (se3.py:133-152): go = rows 0..2 of grad_g (row-major 12 floats).
-__device__ __forceinline__ void se3_exp_bwd(const float (&g)[12], const float (&go)[12], float* __restrict__ gx) {
-  float a = 0.f, b = 0.f, c = 0.f;
+// ExpMap.backward closed form (se3.py:133-152): go = rows 0..2 of grad_g (row-major 12 values).  The three cross
+// products cancel (grad_w is a difference of sums over N points), so they are formed in double: the result then
+// carries only the rounding of its inputs (gradients within 1e-5 of the fp64 oracle at any N).
+__device__ __forceinline__ void se3_exp_bwd(const float (&g)[12], const double (&go)[12], float* __restrict__ gx) {
+  double a = 0.0, b = 0.0, c = 0.0;
 #pragma unroll
   for (int col = 0; col < 4; ++col) {
-    const float g0 = g[col], g1 = g[4 + col], g2 = g[8 + col];
-    const float o0 = go[col], o1 = go[4 + col], o2 = go[8 + col];
+    const double g0 = g[col], g1 = g[4 + col], g2 = g[8 + col];
+    const double o0 = go[col], o1 = go[4 + col], o2 = go[8 + col];
     a += g1 * o2 - g2 * o1;
     b += g2 * o0 - g0 * o2;
     c += g0 * o1 - g1 * o0;
   }
-  gx[0] = a; gx[1] = b; gx[2] = c;
-  gx[3] = go[3]; gx[4] = go[7]; gx[5] = go[11];
+  gx[0] = (float)a; gx[1] = (float)b; gx[2] = (float)c;
+  gx[3] = (float)go[3]; gx[4] = (float)go[7]; gx[5] = (float)go[11];
 }
 
 __global__ void __launch_bounds__(256) se3_exp_fwd_kernel(const float* __restrict__ x, long long n,
@@ -96,7 +98,8 @@ __global__ void __launch_bounds__(256) se3_exp_bwd_kernel(const float* __restric
                                                           float* __restrict__ grad_x) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  float g[12], go[12];
+  float g[12];
+  double go[12];
   se3_exp(x + t * 6, g);
   const float4* gi = reinterpret_cast<const float4*>(grad_g + t * 16);
 #pragma unroll
@@ -126,8 +129,11 @@ __global__ void __launch_bounds__(256) se3_transform_fwd_kernel(
   }
 }
 
-// Sum `v[12]` over the block and add lane-0-of-warp-0's total into dst[0..11] with atomics.
-__device__ __forceinline__ void block_sum12_atomic(float (&v)[12], float* dst, float* smem /* [warps][12] */) {
+// Sum `v[12]` over the block and add the total into dst[0..11] with (double) atomics.  Everything beyond a thread's
+// own few terms is accumulated in double: the sums feed cross products that cancel (se3_exp_bwd), and fp32 partial
+// sums over N >= 5000 points cost 3e-5 of the gradient's norm (round-1 tests); the order of the double atomics is
+// unspecified but moves the result by ~1e-16 relative.
+__device__ __forceinline__ void block_sum12_atomic(double (&v)[12], double* dst, double* smem /* [warps][12] */) {
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
@@ -140,24 +146,32 @@ __device__ __forceinline__ void block_sum12_atomic(float (&v)[12], float* dst, f
   }
   __syncthreads();
   if (threadIdx.x < 12) {
-    float s = 0.f;
+    double s = 0.0;
     for (unsigned w = 0; w < nwarps; ++w) s += smem[w * 12 + threadIdx.x];
     atomicAdd(dst + threadIdx.x, s);
   }
 }
 
-// Backward, many points per transform: grid = (chunks, G); block-reduce the 12 sums, atomics into grad_g.
+// One point's contribution to the 12 sums of grad_g = sum_k go_k [a_k^T 1]: fp32 products, double accumulation.
+__device__ __forceinline__ void acc12(double (&acc)[12], float ox, float oy, float oz, float x, float y, float z) {
+  acc[0] += (double)(ox * x); acc[1] += (double)(ox * y); acc[2] += (double)(ox * z); acc[3] += (double)ox;
+  acc[4] += (double)(oy * x); acc[5] += (double)(oy * y); acc[6] += (double)(oy * z); acc[7] += (double)oy;
+  acc[8] += (double)(oz * x); acc[9] += (double)(oz * y); acc[10] += (double)(oz * z); acc[11] += (double)oz;
+}
+
+// Backward, many points per transform: grid = (chunks, G); block-reduce the 12 sums in double, double atomics into
+// gsum [G,12] (zeroed by the launcher); sum12_to_grad_g_kernel rounds them once into grad_g.
 __global__ void __launch_bounds__(256) se3_transform_bwd_kernel(
     const float* __restrict__ g, const float* __restrict__ a, long long a_st, long long a_sk, long long a_sc,
     const float* __restrict__ go, long long go_st, long long go_sk, long long go_sc, long long P,
-    float* __restrict__ grad_g, float* __restrict__ grad_a, long long ga_st, long long ga_sk, long long ga_sc) {
-  __shared__ float red[8 * 12];
+    double* __restrict__ gsum, float* __restrict__ grad_a, long long ga_st, long long ga_sk, long long ga_sc) {
+  __shared__ double red[8 * 12];
   const long long t = blockIdx.y;
   const float4* gm = reinterpret_cast<const float4*>(g + t * 16);
   const float4 r0 = gm[0], r1 = gm[1], r2 = gm[2];
-  float acc[12];
+  double acc[12];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 12; ++i) acc[i] = 0.0;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < P;
        k += (long long)gridDim.x * blockDim.x) {
     const float* q = go + t * go_st + k * go_sk;
@@ -168,15 +182,24 @@ __global__ void __launch_bounds__(256) se3_transform_bwd_kernel(
       d[ga_sc] = r0.y * ox + r1.y * oy + r2.y * oz;
       d[2 * ga_sc] = r0.z * ox + r1.z * oy + r2.z * oz;
     }
-    if (grad_g) {
+    if (gsum) {
       const float* p = a + t * a_st + k * a_sk;
-      const float x = p[0], y = p[a_sc], z = p[2 * a_sc];
-      acc[0] += ox * x; acc[1] += ox * y; acc[2] += ox * z; acc[3] += ox;
-      acc[4] += oy * x; acc[5] += oy * y; acc[6] += oy * z; acc[7] += oy;
-      acc[8] += oz * x; acc[9] += oz * y; acc[10] += oz * z; acc[11] += oz;
+      acc12(acc, ox, oy, oz, p[0], p[a_sc], p[2 * a_sc]);
     }
   }
-  if (grad_g) block_sum12_atomic(acc, grad_g + t * 16, red);
+  if (gsum) block_sum12_atomic(acc, gsum + t * 12, red);
+}
+
+__global__ void __launch_bounds__(256) sum12_to_grad_g_kernel(const double* __restrict__ gsum, long long G,
+                                                              float* __restrict__ grad_g) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= G) return;
+  const double* v = gsum + t * 12;
+  float4* o = reinterpret_cast<float4*>(grad_g + t * 16);
+  o[0] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+  o[1] = make_float4((float)v[4], (float)v[5], (float)v[6], (float)v[7]);
+  o[2] = make_float4((float)v[8], (float)v[9], (float)v[10], (float)v[11]);
+  o[3] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // Backward, few points per transform (per-point transforms, P small): one thread per transform, no atomics.
@@ -188,9 +211,9 @@ __global__ void __launch_bounds__(256) se3_transform_bwd_small_kernel(
   if (t >= G) return;
   const float4* gm = reinterpret_cast<const float4*>(g + t * 16);
   const float4 r0 = gm[0], r1 = gm[1], r2 = gm[2];
-  float acc[12];
+  double acc[12];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 12; ++i) acc[i] = 0.0;
   for (long long k = 0; k < P; ++k) {
     const float* q = go + t * go_st + k * go_sk;
     const float ox = q[0], oy = q[go_sc], oz = q[2 * go_sc];
@@ -201,16 +224,13 @@ __global__ void __launch_bounds__(256) se3_transform_bwd_small_kernel(
       d[2 * ga_sc] = r0.z * ox + r1.z * oy + r2.z * oz;
     }
     const float* p = a + t * a_st + k * a_sk;
-    const float x = p[0], y = p[a_sc], z = p[2 * a_sc];
-    acc[0] += ox * x; acc[1] += ox * y; acc[2] += ox * z; acc[3] += ox;
-    acc[4] += oy * x; acc[5] += oy * y; acc[6] += oy * z; acc[7] += oy;
-    acc[8] += oz * x; acc[9] += oz * y; acc[10] += oz * z; acc[11] += oz;
+    acc12(acc, ox, oy, oz, p[0], p[a_sc], p[2 * a_sc]);
   }
   if (grad_g) {
     float4* o = reinterpret_cast<float4*>(grad_g + t * 16);
-    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    o[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
+    o[0] = make_float4((float)acc[0], (float)acc[1], (float)acc[2], (float)acc[3]);
+    o[1] = make_float4((float)acc[4], (float)acc[5], (float)acc[6], (float)acc[7]);
+    o[2] = make_float4((float)acc[8], (float)acc[9], (float)acc[10], (float)acc[11]);
     o[3] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
@@ -265,14 +285,16 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(
   }
 }
 
+// `gr` (optional, strided like go) is the gradient that arrives through the returned rigid points
+// (deform_rigid_points_list, network.py:654): the rigid points receive w*go + gr.
 __global__ void __launch_bounds__(256) warp_bwd_kernel(
     const float* __restrict__ phi, const float* __restrict__ src, long long s_sb, long long s_sn, long long s_sc,
     const float* __restrict__ w, const float* __restrict__ prev, long long p_sb, long long p_sn, long long p_sc,
-    const float* __restrict__ go, long long g_sb, long long g_sn, long long g_sc, int N,
+    const float* __restrict__ go, const float* __restrict__ gr, long long g_sb, long long g_sn, long long g_sc, int N,
     float* __restrict__ grad_w, float* __restrict__ grad_src, long long gs_sb, long long gs_sn, long long gs_sc,
-    float* __restrict__ scratch) {
+    double* __restrict__ scratch) {
   __shared__ float sg[12];
-  __shared__ float red[8 * 12];
+  __shared__ double red[8 * 12];
   const int b = blockIdx.y;
   if (threadIdx.x == 0) {
     float g[12];
@@ -284,14 +306,17 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(
   float g[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) g[i] = sg[i];
-  float acc[12];
+  double acc[12];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 12; ++i) acc[i] = 0.0;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
     const float* p = src + b * s_sb + k * s_sn;
     const float x = p[0], y = p[s_sc], z = p[2 * s_sc];
-    const float* q = go + b * g_sb + k * g_sn;
-    float ox = q[0], oy = q[g_sc], oz = q[2 * g_sc];
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    if (go) {
+      const float* q = go + b * g_sb + k * g_sn;
+      ox = q[0]; oy = q[g_sc]; oz = q[2 * g_sc];
+    }
     if (w) {
       const float ww = w[(long long)b * N + k];
       if (grad_w) {
@@ -303,15 +328,17 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(
       }
       ox *= ww; oy *= ww; oz *= ww;
     }
+    if (gr) {
+      const float* q = gr + b * g_sb + k * g_sn;
+      ox += q[0]; oy += q[g_sc]; oz += q[2 * g_sc];
+    }
     if (grad_src) {
       float* d = grad_src + b * gs_sb + k * gs_sn;
       d[0] = g[0] * ox + g[4] * oy + g[8] * oz;
       d[gs_sc] = g[1] * ox + g[5] * oy + g[9] * oz;
       d[2 * gs_sc] = g[2] * ox + g[6] * oy + g[10] * oz;
     }
-    acc[0] += ox * x; acc[1] += ox * y; acc[2] += ox * z; acc[3] += ox;
-    acc[4] += oy * x; acc[5] += oy * y; acc[6] += oy * z; acc[7] += oy;
-    acc[8] += oz * x; acc[9] += oz * y; acc[10] += oz * z; acc[11] += oz;
+    acc12(acc, ox, oy, oz, x, y, z);
   }
   block_sum12_atomic(acc, scratch + (long long)b * 12, red);
 }
@@ -388,10 +415,10 @@ __global__ void __launch_bounds__(256) warp_fwd_vec_kernel(
 
 __global__ void __launch_bounds__(256) warp_bwd_vec_kernel(
     const float* __restrict__ phi, const float* __restrict__ src, const float* __restrict__ w,
-    const float* __restrict__ prev, const float* __restrict__ go, int N, float* __restrict__ grad_w,
-    float* __restrict__ grad_src, float* __restrict__ scratch) {
+    const float* __restrict__ prev, const float* __restrict__ go, const float* __restrict__ gr, int N,
+    float* __restrict__ grad_w, float* __restrict__ grad_src, double* __restrict__ scratch) {
   __shared__ float sg[12];
-  __shared__ float red[8 * 12];
+  __shared__ double red[8 * 12];
   const int b = blockIdx.y;
   if (threadIdx.x == 0) {
     float g[12];
@@ -403,14 +430,20 @@ __global__ void __launch_bounds__(256) warp_bwd_vec_kernel(
   float g[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) g[i] = sg[i];
-  float acc[12];
+  double acc[12];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 12; ++i) acc[i] = 0.0;
   const long long base = (long long)b * N;
   for (int k4 = blockIdx.x * blockDim.x + threadIdx.x; k4 < N / 4; k4 += gridDim.x * blockDim.x) {
     const long long o3 = (base + 4LL * k4) * 3;
     const Pts4 p = load_pts4(src + o3);
-    Pts4 o = load_pts4(go + o3);
+    Pts4 o;
+    if (go) {
+      o = load_pts4(go + o3);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { o.x[e] = 0.f; o.y[e] = 0.f; o.z[e] = 0.f; }
+    }
     if (w) {
       const float4 wv = *reinterpret_cast<const float4*>(w + base + 4LL * k4);
       const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
@@ -429,6 +462,11 @@ __global__ void __launch_bounds__(256) warp_bwd_vec_kernel(
 #pragma unroll
       for (int e = 0; e < 4; ++e) { o.x[e] *= ww[e]; o.y[e] *= ww[e]; o.z[e] *= ww[e]; }
     }
+    if (gr) {
+      const Pts4 r = load_pts4(gr + o3);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { o.x[e] += r.x[e]; o.y[e] += r.y[e]; o.z[e] += r.z[e]; }
+    }
     if (grad_src) {
       Pts4 d;
 #pragma unroll
@@ -439,12 +477,18 @@ __global__ void __launch_bounds__(256) warp_bwd_vec_kernel(
       }
       store_pts4(grad_src + o3, d);
     }
+    // the thread's 4 points in fp32 (4 terms per sum), everything beyond in double
+    float s[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = 0.f;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      acc[0] += o.x[e] * p.x[e]; acc[1] += o.x[e] * p.y[e]; acc[2] += o.x[e] * p.z[e]; acc[3] += o.x[e];
-      acc[4] += o.y[e] * p.x[e]; acc[5] += o.y[e] * p.y[e]; acc[6] += o.y[e] * p.z[e]; acc[7] += o.y[e];
-      acc[8] += o.z[e] * p.x[e]; acc[9] += o.z[e] * p.y[e]; acc[10] += o.z[e] * p.z[e]; acc[11] += o.z[e];
+      s[0] += o.x[e] * p.x[e]; s[1] += o.x[e] * p.y[e]; s[2] += o.x[e] * p.z[e]; s[3] += o.x[e];
+      s[4] += o.y[e] * p.x[e]; s[5] += o.y[e] * p.y[e]; s[6] += o.y[e] * p.z[e]; s[7] += o.y[e];
+      s[8] += o.z[e] * p.x[e]; s[9] += o.z[e] * p.y[e]; s[10] += o.z[e] * p.z[e]; s[11] += o.z[e];
     }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] += (double)s[i];
   }
   block_sum12_atomic(acc, scratch + (long long)b * 12, red);
 }
@@ -454,15 +498,21 @@ static bool contig_aos(const void* t, long long sb, long long sn, long long sc, 
   return !t || (sc == 1 && sn == 3 && sb == 3LL * N && (((uintptr_t)t) & 15u) == 0);
 }
 
-// grad_g rows (scratch [B,12]) -> grad_phi through ExpMap.backward.
-__global__ void warp_bwd_phi_kernel(const float* __restrict__ phi, const float* __restrict__ scratch, int B,
-                                    float* __restrict__ grad_phi) {
+// grad_g rows (scratch [B,12], double) -> grad_phi through ExpMap.backward.  grad_g_in (optional, [B,4,4]) is the
+// gradient that arrives through the returned rigid matrix (rigid_matrix_list -> loss_on_tran, loss.py:224-230).
+__global__ void warp_bwd_phi_kernel(const float* __restrict__ phi, const double* __restrict__ scratch,
+                                    const float* __restrict__ grad_g_in, int B, float* __restrict__ grad_phi) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  float g[12], go[12];
+  float g[12];
+  double go[12];
   se3_exp(phi + (long long)b * 6, g);
 #pragma unroll
   for (int i = 0; i < 12; ++i) go[i] = scratch[(long long)b * 12 + i];
+  if (grad_g_in) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) go[i] += (double)grad_g_in[(long long)b * 16 + i];
+  }
   se3_exp_bwd(g, go, grad_phi + (long long)b * 6);
 }
 
@@ -505,7 +555,7 @@ int rma_se3_transform_forward(const float* g, const float* a, int64_t a_st, int6
 int rma_se3_transform_backward(const float* g, const float* a, int64_t a_st, int64_t a_sk, int64_t a_sc,
                                const float* go, int64_t go_st, int64_t go_sk, int64_t go_sc, int64_t G, int64_t P,
                                float* grad_g, float* grad_a, int64_t ga_st, int64_t ga_sk, int64_t ga_sc,
-                               void* stream_) {
+                               double* scratch, void* stream_) {
   if (!g || !a || !go || G <= 0 || P <= 0) return RMA_E_BADARG;
   if (!grad_g && !grad_a) return RMA_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -513,12 +563,17 @@ int rma_se3_transform_backward(const float* g, const float* a, int64_t a_st, int
     se3_transform_bwd_small_kernel<<<grid1d(G, 256, 0x7fffffffLL), 256, 0, stream>>>(
         g, a, a_st, a_sk, a_sc, go, go_st, go_sk, go_sc, G, P, grad_g, grad_a, ga_st, ga_sk, ga_sc);
   } else {
-    if (grad_g) RMA_CUDA_TRY(cudaMemsetAsync(grad_g, 0, (size_t)G * 16 * sizeof(float), stream));
+    if (grad_g && (!scratch || (((uintptr_t)scratch) & 7u))) return RMA_E_BADARG;
+    if (grad_g) RMA_CUDA_TRY(cudaMemsetAsync(scratch, 0, (size_t)G * 12 * sizeof(double), stream));
     long long chunks = (P + 256 * 4 - 1) / (256 * 4);
     if (chunks > 1024) chunks = 1024;
     dim3 grid((unsigned)chunks, (unsigned)G);
-    se3_transform_bwd_kernel<<<grid, 256, 0, stream>>>(g, a, a_st, a_sk, a_sc, go, go_st, go_sk, go_sc, P, grad_g,
-                                                       grad_a, ga_st, ga_sk, ga_sc);
+    se3_transform_bwd_kernel<<<grid, 256, 0, stream>>>(g, a, a_st, a_sk, a_sc, go, go_st, go_sk, go_sc, P,
+                                                       grad_g ? scratch : nullptr, grad_a, ga_st, ga_sk, ga_sc);
+    if (grad_g) {
+      RMA_LAUNCH_CHECK();
+      sum12_to_grad_g_kernel<<<grid1d(G, 256, 0x7fffffffLL), 256, 0, stream>>>(scratch, G, grad_g);
+    }
   }
   RMA_LAUNCH_CHECK();
   return RMA_OK;
@@ -549,29 +604,32 @@ int rma_warp_forward(const float* phi, const float* src, int64_t s_sb, int64_t s
 }
 
 int rma_warp_backward(const float* phi, const float* src, int64_t s_sb, int64_t s_sn, int64_t s_sc, const float* w,
-                      const float* prev, int64_t p_sb, int64_t p_sn, int64_t p_sc, const float* go, int64_t g_sb,
-                      int64_t g_sn, int64_t g_sc, int B, int N, float* grad_phi, float* grad_w, float* grad_src,
-                      int64_t gs_sb, int64_t gs_sn, int64_t gs_sc, float* scratch, void* stream_) {
-  if (!phi || !src || !go || !grad_phi || !scratch || B <= 0 || N <= 0 || B > 65535) return RMA_E_BADARG;
+                      const float* prev, int64_t p_sb, int64_t p_sn, int64_t p_sc, const float* go,
+                      const float* go_rigid, int64_t g_sb, int64_t g_sn, int64_t g_sc, const float* grad_g_in, int B,
+                      int N, float* grad_phi, float* grad_w, float* grad_src, int64_t gs_sb, int64_t gs_sn,
+                      int64_t gs_sc, double* scratch, void* stream_) {
+  if (!phi || !src || !grad_phi || !scratch || B <= 0 || N <= 0 || B > 65535) return RMA_E_BADARG;
+  if ((((uintptr_t)scratch) & 7u) != 0) return RMA_E_BADARG;
   if (w && !prev) return RMA_E_BADARG;
   cudaStream_t stream = (cudaStream_t)stream_;
-  RMA_CUDA_TRY(cudaMemsetAsync(scratch, 0, (size_t)B * 12 * sizeof(float), stream));
+  RMA_CUDA_TRY(cudaMemsetAsync(scratch, 0, (size_t)B * 12 * sizeof(double), stream));
   if (N % 4 == 0 && contig_aos(src, s_sb, s_sn, s_sc, N) && contig_aos(go, g_sb, g_sn, g_sc, N) &&
+      contig_aos(go_rigid, g_sb, g_sn, g_sc, N) &&
       contig_aos(grad_src, gs_sb, gs_sn, gs_sc, N) &&
       (!w || (contig_aos(prev, p_sb, p_sn, p_sc, N) && (((uintptr_t)w) & 15u) == 0 && (((uintptr_t)grad_w) & 15u) == 0))) {
     int vchunks = (N / 4 + 256 * 2 - 1) / (256 * 2);
     if (vchunks > 2048) vchunks = 2048;
-    warp_bwd_vec_kernel<<<dim3((unsigned)vchunks, (unsigned)B), 256, 0, stream>>>(phi, src, w, prev, go, N, grad_w,
-                                                                              grad_src, scratch);
+    warp_bwd_vec_kernel<<<dim3((unsigned)vchunks, (unsigned)B), 256, 0, stream>>>(phi, src, w, prev, go, go_rigid, N,
+                                                                              grad_w, grad_src, scratch);
   } else {
     int chunks = (N + 256 * 4 - 1) / (256 * 4);
     if (chunks > 1024) chunks = 1024;
     dim3 grid((unsigned)chunks, (unsigned)B);
-    warp_bwd_kernel<<<grid, 256, 0, stream>>>(phi, src, s_sb, s_sn, s_sc, w, prev, p_sb, p_sn, p_sc, go, g_sb, g_sn,
-                                              g_sc, N, grad_w, grad_src, gs_sb, gs_sn, gs_sc, scratch);
+    warp_bwd_kernel<<<grid, 256, 0, stream>>>(phi, src, s_sb, s_sn, s_sc, w, prev, p_sb, p_sn, p_sc, go, go_rigid,
+                                              g_sb, g_sn, g_sc, N, grad_w, grad_src, gs_sb, gs_sn, gs_sc, scratch);
   }
   RMA_LAUNCH_CHECK();
-  warp_bwd_phi_kernel<<<(B + 127) / 128, 128, 0, stream>>>(phi, scratch, B, grad_phi);
+  warp_bwd_phi_kernel<<<(B + 127) / 128, 128, 0, stream>>>(phi, scratch, grad_g_in, B, grad_phi);
   RMA_LAUNCH_CHECK();
   return RMA_OK;
 }

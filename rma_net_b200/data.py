@@ -67,8 +67,9 @@ class PairBatchLoader:
     """Iterate (source [B,N,3], target [B,N,3], start_pos) device views over a PointPairFile.
 
     Two pinned host buffers and two device buffers; batch k+1 is read from the file into pinned memory and copied
-    on a side stream while the caller works on batch k.  The views returned for batch k stay valid until the
-    NEXT-but-one call of __next__ (double buffering); the consumer's current stream is made to wait for the copy."""
+    on a side stream while the caller works on batch k.  The views returned for batch k stay valid until the NEXT
+    call of __next__ (by then the step on batch k has been enqueued; that call marks the point on the consumer's
+    stream after which batch k's device buffer may be refilled); the consumer's stream is made to wait for the copy."""
 
     def __init__(self, pairs: PointPairFile, batch_size: int, device: torch.device, start_pos: int = 0,
                  steps: Optional[int] = None):
@@ -83,6 +84,8 @@ class PairBatchLoader:
         self._consumed = [torch.cuda.Event() for _ in range(2)]
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._slot = 0
+        self._last: Optional[int] = None
+        self._copied = [False, False]
         self._inflight: Optional[Tuple[int, int]] = None
         self._prefetch()
 
@@ -91,12 +94,14 @@ class PairBatchLoader:
             self._inflight = None
             return
         s = self._slot
-        self._consumed[s].synchronize()                      # the pinned buffer of slot s is free again (2 steps ago)
+        if self._copied[s]:
+            self._ready[s].synchronize()                     # the slot's previous H2D copy has left the pinned buffer
         self.pairs.read_batch(self.pos, self.batch_size, out=self._pin[s].numpy())
         with torch.cuda.stream(self._copy_stream):
-            self._copy_stream.wait_event(self._consumed[s])  # the device buffer too
+            self._copy_stream.wait_event(self._consumed[s])  # the kernels that read the device buffer have finished
             self._dev[s].copy_(self._pin[s], non_blocking=True)
             self._ready[s].record(self._copy_stream)
+        self._copied[s] = True
         self._inflight = (s, self.pos % len(self.pairs))
         self.pos = (self.pos + self.batch_size) % len(self.pairs)
         self.done += 1
@@ -110,21 +115,22 @@ class PairBatchLoader:
             raise StopIteration
         s, start = self._inflight
         cur = torch.cuda.current_stream(self.device)
+        # The step on the batch handed out last has been enqueued by now: everything on the consumer's stream up to
+        # here must finish before that batch's device buffer (the slot the prefetch below refills) is overwritten.
+        if self._last is not None:
+            self._consumed[self._last].record(cur)
         cur.wait_event(self._ready[s])
         batch = self._dev[s]
         self._prefetch()                                     # next batch: file read + H2D overlap the caller's step
         n = self.pairs.point_num
-        # the caller's work on this batch is ordered before the slot's reuse by an event recorded on ITS stream the
-        # next time this slot comes up; recording here (after the views are handed out) would be too early, so the
-        # event is recorded lazily in release()
         self._last = s
         return batch[:, :n, :], batch[:, n:, :], start
 
     def release(self) -> None:
-        """Call after the step on the batch returned last has been ENQUEUED: marks the point on the current stream
-        after which the batch's device buffer may be overwritten.  (Without it the loader is still correct as long
-        as the caller synchronises once per step, e.g. by reading the loss.)"""
-        self._consumed[self._last].record(torch.cuda.current_stream(self.device))
+        """Optional earlier marker: call after the step on the batch returned last has been ENQUEUED to let the
+        refill of its buffer start before the next __next__ (which records the same marker itself)."""
+        if self._last is not None:
+            self._consumed[self._last].record(torch.cuda.current_stream(self.device))
 
 
 def read_obj_vertices(path: str, with_colors: bool = False):

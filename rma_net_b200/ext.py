@@ -330,13 +330,15 @@ def se3_transform_backward(plan: TransformPlan, grad_out: torch.Tensor, g_shape,
                            need_g: bool, need_a: bool):
     go = grad_out.to(torch.float32).contiguous()
     dev = go.device
-    grad_g = torch.empty((plan.G, 4, 4), dtype=torch.float32, device=dev) if need_g else None
-    grad_a = torch.empty(plan.out_shape, dtype=torch.float32, device=dev) if need_a else None
+    # zeros, not empty: with no points (go.numel() == 0) nothing is launched and the sums over points are 0
+    grad_g = torch.zeros((plan.G, 4, 4), dtype=torch.float32, device=dev) if need_g else None
+    grad_a = torch.zeros(plan.out_shape, dtype=torch.float32, device=dev) if need_a else None
     if go.numel():
+        scratch = torch.empty((plan.G, 12), dtype=torch.float64, device=dev) if need_g else None
         with torch.cuda.device(dev):
             rc = _lib.load().rma_se3_transform_backward(
                 _ptr(plan.g_flat), _ptr(plan.a), *plan.a_strides, _ptr(go), *plan.o_strides, plan.G, plan.P,
-                _ptr(grad_g), _ptr(grad_a), *plan.o_strides, _stream())
+                _ptr(grad_g), _ptr(grad_a), *plan.o_strides, _ptr(scratch), _stream())
             _lib.check(rc, "rma_se3_transform_backward")
     if grad_g is not None:
         lead_g = plan.lead[:plan.split] + (1,) * (len(plan.lead) - plan.split)
@@ -383,25 +385,28 @@ def warp_forward(phi, src, w=None, prev=None, want_rigid: bool = True, want_g: b
     return out, rigid, g
 
 
-def warp_backward(phi, src, w, prev, grad_out, need_w: bool, need_src: bool):
-    """Returns (grad_phi [B,6], grad_w [B,N] or None, grad_src [B,N,3] or None)."""
+def warp_backward(phi, src, w, prev, grad_out, need_w: bool, need_src: bool, grad_rigid=None, grad_g=None):
+    """grad_out / grad_rigid [B,N,3] / grad_g [B,4,4] = gradients w.r.t. the three outputs of warp_forward (any may be
+    None).  Returns (grad_phi [B,6], grad_w [B,N] or None, grad_src [B,N,3] or None)."""
     B, N = src.shape[0], src.shape[1]
     dev = src.device
     phic = phi.contiguous().view(-1, 6)
     blend = w is not None
     wc = w.to(torch.float32).contiguous().view(B, N) if blend else None
-    go = grad_out.to(torch.float32).contiguous()
+    go = grad_out.to(torch.float32).contiguous() if grad_out is not None else None
+    gr = grad_rigid.to(torch.float32).contiguous() if grad_rigid is not None else None
+    gg = grad_g.to(torch.float32).contiguous().view(B, 4, 4) if grad_g is not None else None
     grad_phi = torch.empty((B, 6), dtype=torch.float32, device=dev)
     grad_w = torch.empty((B, N), dtype=torch.float32, device=dev) if (need_w and blend) else None
     grad_src = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if need_src else None
-    scratch = torch.empty((B, 12), dtype=torch.float32, device=dev)
+    scratch = torch.empty((B, 12), dtype=torch.float64, device=dev)
     ss = src.stride()
     ps = prev.stride() if blend else (0, 0, 0)
     with torch.cuda.device(dev):
         rc = _lib.load().rma_warp_backward(_ptr(phic), _ptr(src), ss[0], ss[1], ss[2], _ptr(wc),
                                            _ptr(prev if blend else None), ps[0], ps[1], ps[2],
-                                           _ptr(go), 3 * N, 3, 1, B, N, _ptr(grad_phi), _ptr(grad_w),
-                                           _ptr(grad_src), 3 * N, 3, 1, _ptr(scratch), _stream())
+                                           _ptr(go), _ptr(gr), 3 * N, 3, 1, _ptr(gg), B, N, _ptr(grad_phi),
+                                           _ptr(grad_w), _ptr(grad_src), 3 * N, 3, 1, _ptr(scratch), _stream())
         _lib.check(rc, "rma_warp_backward")
     return grad_phi.view(phi.shape), grad_w, grad_src
 

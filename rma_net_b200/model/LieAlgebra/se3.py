@@ -57,15 +57,18 @@ Exp = ExpMap.apply
 class _Transform(torch.autograd.Function):
     @staticmethod
     def forward(ctx, g, a):
-        out, plan = ext.se3_transform_forward(g, a)
-        ctx.plan = plan
-        ctx.g_shape, ctx.a_shape = g.shape, a.shape
+        out, _ = ext.se3_transform_forward(g, a)
+        # saved through autograd (version-counter check, saved-tensor hooks, freed with the graph); the launch plan
+        # is a few integers and is rebuilt in backward
+        ctx.save_for_backward(g, a)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
+        g, a = ctx.saved_tensors
         need_g, need_a = ctx.needs_input_grad
-        grad_g, grad_a = ext.se3_transform_backward(ctx.plan, grad_out, ctx.g_shape, ctx.a_shape, need_g, need_a)
+        plan = ext.TransformPlan(g, a)
+        grad_g, grad_a = ext.se3_transform_backward(plan, grad_out, g.shape, a.shape, need_g, need_a)
         return grad_g, grad_a
 
 

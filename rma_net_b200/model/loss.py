@@ -330,14 +330,18 @@ def sample_view_angles(view_divide, jitter=True, rng=random):
     """The view_divide^2 Euler angle triples in host double precision, exactly as the reference computes them:
     the regular grid of Loss.__init__ (loss.py:137-140) or, with jitter, the re-sampled grid of loss_on_depth
     (loss.py:152-158), drawing rng.random() twice per view in the reference's order (x, then y)."""
+    # the reference's pi (loss.py:29: torch.pi = torch.acos(torch.zeros(1)).item() * 2) is the float32-rounded value
+    # 3.1415927410125732, not math.pi: after the float32 cast of the angles the two can differ by 1 ulp, which moves
+    # points across pixel boundaries in Render / Masker
+    pi = torch.acos(torch.zeros(1)).item() * 2
     out = []
     for view_id in range(view_divide ** 2):
         euler_x = view_id // view_divide
         euler_y = view_id - euler_x * view_divide
         rx = rng.random() if jitter else 0.0
         ry = rng.random() if jitter else 0.0
-        out.append([-math.pi + 2 * math.pi * (euler_x + rx) / view_divide,
-                    -math.pi + 2 * math.pi * (euler_y + ry) / view_divide, 0.0])
+        out.append([-pi + 2 * pi * (euler_x + rx) / view_divide,
+                    -pi + 2 * pi * (euler_y + ry) / view_divide, 0.0])
     return out
 
 

@@ -50,7 +50,7 @@ def main():
     go = torch.randn(B, N, 3, generator=g).to(dev)
     gphi = torch.empty(B, 6, device=dev)
     gw = torch.empty(B, N, device=dev)
-    scratch = torch.empty(B * 12, device=dev)
+    scratch = torch.empty(B * 12, dtype=torch.float64, device=dev)
     ss = src.stride()
 
     def warp_fwd():
@@ -62,8 +62,8 @@ def main():
                              None, None, st())
 
     def warp_bwd():
-        lib.rma_warp_backward(P(phi), P(src), ss[0], ss[1], ss[2], P(w), P(prev), ss[0], ss[1], ss[2], P(go), ss[0],
-                              ss[1], ss[2], B, N, P(gphi), P(gw), None, 0, 0, 0, P(scratch), st())
+        lib.rma_warp_backward(P(phi), P(src), ss[0], ss[1], ss[2], P(w), P(prev), ss[0], ss[1], ss[2], P(go), None,
+                              ss[0], ss[1], ss[2], None, B, N, P(gphi), P(gw), None, 0, 0, 0, P(scratch), st())
     t = timed(warp_fwd); out["warp_fwd_GBps"] = 40 * B * N / t / 1e9
     t = timed(warp_fwd0); out["warp_fwd_stage0_GBps"] = 24 * B * N / t / 1e9
     t = timed(warp_bwd); out["warp_bwd_GBps"] = (12 + 12 + 4 + 12 + 4) * B * N / t / 1e9    # src, prev, w, go in; grad_w out
