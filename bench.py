@@ -9,6 +9,13 @@ over one synthetic batch (SURVEY.md §8d seeds), through the repo's public API
 Multi-GPU (torchrun, one rank per GPU): batch-sharded, every rank runs its own C2-sized batch, no collective on the
 data path ("scaling": "weak"); value = pairs of all ranks / max-over-ranks device time.
 
+The line also carries `secondary`: the other BASELINE.json configurations, measured in the same run (device time, max
+over ranks): C3 = the recurrent alignment step (8 x (se3 warp + chamfer), B=16, N=M=8192, every rank its own batch);
+C4 = B=512, N=M=2048 split over the ranks by parallel.shard_batch (strong scaling, with the one-GPU time of the whole
+batch measured beside it); C5 = one pair N=M=2^20 through parallel.SourceShardedChamfer (sources sharded, NCCL
+all-reduce MIN of packed (distance, index) keys and SUM of grad_target inside the timed region) with a self-check
+of the merged result against a single-GPU recomputation and the fp64 C oracle on sampled points.
+
 Printed JSON keys beyond the base contract:
   roofline     FP32-FMA roofline of the dominant kernel (chamfer_search_kernel): algorithmic 12 FLOP per point-pair
                 / that kernel's mean duration, measured live with CUDA events around the
@@ -17,8 +24,10 @@ Printed JSON keys beyond the base contract:
                host cores on a bounded sample, rank 0 at N=1 only.  Reported baseline, not the target.
   e2e          same metric through the public API with HOST (pinned) inputs: every step copies its [B,2N,3] pair batch
                H2D, runs fwd+bwd and reads the loss back (D2H + host sync) inside the timed region.  `value` is the
-               double-buffered loop a training step uses (copy of step k+1 on a copy stream while step k computes,
-               as rma_net_b200.data.PairBatchLoader does); `serial_value` is the same with nothing overlapped.
+               MEDIAN of 5 runs of K steps of ONE driver: the double-buffered loop a training step uses (copy of step
+               k+1 on a copy stream while step k computes, as rma_net_b200.data.PairBatchLoader does, the host reading
+               step k's loss while k+1 runs); `sync_value`: the host reads each loss before launching the next step;
+               `serial_value`: nothing overlapped; `copy_in_graph_*`: the same pipeline driven by one graph per step.
 """
 from __future__ import annotations
 
@@ -52,6 +61,22 @@ def make_workload(name: str, rank: int = 0):
     x = torch.rand(B, N, 3, generator=g) * 2 - 1
     y = torch.rand(B, M, 3, generator=g) * 2 - 1
     return x, y
+
+
+def search_traffic(workload: str, kernel: str):
+    """DRAM bytes per launch of the search kernel from the committed ncu capture (profiles/search_dram_traffic.json:
+    {"workload", "kernel", "dram_bytes_read", "dram_bytes_write", "source"}), or null when there is none for this
+    workload / kernel."""
+    p = os.path.join(ROOT, "profiles", "search_dram_traffic.json")
+    try:
+        with open(p) as f:
+            for e in json.load(f):
+                if e["workload"] == workload and e["kernel"] == kernel:
+                    return {"traffic": float(e["dram_bytes_read"]) + float(e["dram_bytes_write"]),
+                            "traffic_source": e["source"]}
+    except (OSError, ValueError, KeyError):
+        pass
+    return {"traffic": None, "traffic_source": None}
 
 
 def measured_peaks():
@@ -135,7 +160,7 @@ def run_reference(args):
     B, N, M, _, _ = WORKLOADS[name]
     x, y = make_workload(name)
     threads = os.cpu_count() or 1
-    sample_b = min(B, 2)
+    sample_b = B            # the whole batch: same config as our arm (~0.6 s per step at C2 on 16 cores)
     from oracle.chamfer_oracle import ref_fwd_bwd
     torch.set_num_threads(threads)
     xs, ys = x[:sample_b].contiguous(), y[:sample_b].contiguous()
@@ -147,12 +172,14 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     pairs = sample_b * N * M
     val = pairs / dt / 1e9
-    sample = f"first {sample_b} of {B} batch elements per step (N=M={N}), torch CPU fp32, {threads} threads"
+    sample = (f"all {sample_b} of {B} batch elements per step (N=M={N}), torch CPU fp32, {threads} threads: the "
+              f"reference formulation (expanded-form [B,N,M] matrix + torch autograd, model/loss.py:45-70, 200-205)")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}: chamfer fwd+bwd B={B} N=M={N} (SURVEY.md §8d), bounded CPU sample",
+        "config": {"workload": f"{name}: chamfer fwd+bwd of loss_on_cd, B={B} per GPU, N=M={N}, uniform cube, "
+                               f"seed {WORKLOADS[name][3]} (SURVEY.md §8d)",
                    "sample": sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -160,6 +187,200 @@ def run_reference(args):
     }
     print(json.dumps(line), flush=True)
 
+
+
+# ------------------------------------------------------------------------------------------------------------
+# secondary configurations of BASELINE.json (C3, C4, C5), measured in the same run
+# ------------------------------------------------------------------------------------------------------------
+def _timed_max(fn, reps, warm, dev, world):
+    """Mean device milliseconds per call of fn over `reps` calls (CUDA events on the launching stream, after `warm`
+    untimed calls, barrier + synchronize on both sides), MAX over ranks."""
+    import torch.distributed as dist
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _graphed(fn):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g
+
+
+def secondary_c3(dev, world, rank, peak_fma):
+    """BASELINE.json configs[2]: 8 iterations of se3 exp-map warp + chamfer, B=16 (per GPU), N=M=8192, fwd+bwd to
+    every phi_k / w_k, gamma = 0.8 (network.py:567-570, 606, 652-655 + loss.py:260-267; SURVEY.md section 8d seeds).
+    The network produces all stage outputs, Loss.forward then evaluates the stage loop - here as ONE batched chamfer
+    call (loss_cd_stages_fused); replayed as a CUDA graph."""
+    from rma_net_b200.model.exfunc.functions import Warp
+    from rma_net_b200.model.loss import loss_cd_stages_fused
+    B, N, T, gamma = 16, 8192, 8, 0.8
+    g = torch.Generator().manual_seed(2 + 1000 * rank)
+    src = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
+    tgt = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
+    phis = [(torch.randn(B, 6, generator=g) * 0.1).to(dev).requires_grad_(True) for _ in range(T)]
+    ws = [torch.rand(B, 1, N, generator=g).to(dev).requires_grad_(True) for _ in range(T)]
+    warp = Warp()
+
+    def step():
+        for p in phis + ws:
+            p.grad = None
+        outs, prev = [], None
+        for k in range(T):
+            out_k, _, _ = warp(phis[k], src, None if k == 0 else ws[k], prev)
+            outs.append(out_k.transpose(1, 2))          # [B,3,N] as the network holds the stage outputs
+            prev = out_k
+        loss = loss_cd_stages_fused(outs, tgt, gamma=gamma)
+        loss.backward()
+        return loss
+
+    graph = _graphed(step)
+    ms = _timed_max(graph.replay, 10, 2, dev, world)
+    pairs = T * B * N * N
+    return {"what": "8 x (se3 exp-map warp + chamfer) fwd+bwd, B=16 per GPU, N=M=8192, gamma=0.8, CUDA graph; the 8 "
+                    "stage chamfers run as one batched call (loss_cd_stages_fused)",
+            "n_gpus": world, "scaling": "weak", "ms_per_step": ms, "G_pairs_per_s": world * pairs / ms / 1e6,
+            "fp32_fma_peak_frac_per_gpu": 6.0 * pairs / (ms * 1e-3) / peak_fma,
+            "gpu_launches_per_step": 2 * T * 2 + 4}
+
+
+def secondary_c4(dev, world, rank, peak_fma):
+    """BASELINE.json configs[3]: B=512, N=M=2048 split contiguously over the ranks (parallel.shard_batch), no
+    collective; strong scaling: the one-GPU time of the WHOLE batch is measured beside it on every rank."""
+    from rma_net_b200 import parallel
+    from rma_net_b200.model.loss import loss_on_cd
+    B, N, _, seed, _ = WORKLOADS["C4"]
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, N, 3, generator=g) * 2 - 1
+    y = torch.rand(B, N, 3, generator=g) * 2 - 1
+    xd_full, yd_full = x.to(dev), y.to(dev)
+
+    def make(xs_, ys_):
+        xr, yr = xs_.detach().requires_grad_(True), ys_.detach().requires_grad_(True)
+
+        def step():
+            xr.grad = None
+            yr.grad = None
+            loss_on_cd(xr, yr).backward()
+        return _graphed(step)
+
+    xs_, ys_ = parallel.shard_batch(xd_full, rank, world), parallel.shard_batch(yd_full, rank, world)
+    ms = _timed_max(make(xs_, ys_).replay, 20, 3, dev, world)
+    pairs = B * N * N
+    out = {"what": f"chamfer fwd+bwd, B=512 split over {world} GPU(s) ({xs_.shape[0]} per GPU), N=M=2048, CUDA graph, "
+                   f"no collective",
+           "n_gpus": world, "scaling": "strong", "ms_per_step": ms, "G_pairs_per_s": pairs / ms / 1e6,
+           "fp32_fma_peak_frac_per_gpu": 6.0 * pairs / world / (ms * 1e-3) / peak_fma}
+    if world > 1:
+        ms1 = _timed_max(make(xd_full, yd_full).replay, 10, 3, dev, world)
+        out["one_gpu_ms_per_step"] = ms1
+        out["strong_scaling_efficiency"] = ms1 / (world * ms)
+    return out
+
+
+def secondary_c5(dev, world, rank, peak_fma):
+    """BASELINE.json configs[4]: one pair N=M=2^20, SOURCE points sharded over the ranks, target replicated
+    (parallel.SourceShardedChamfer): the target->source direction is merged by one NCCL all-reduce MIN over packed
+    (distance, index) keys, grad_target by one all-reduce SUM; both collectives are inside the timed fwd+bwd.
+    Self-check (outside the timed region): the merged dist2/idx2 on 4096 sampled targets and dist1/idx1 on 4096 sampled
+    local sources are BIT-equal to a single-GPU recomputation against the full clouds, and 256 of the targets agree
+    with the fp64 C oracle (index equal or a near-tie below fp32 resolution, distance within 1e-5)."""
+    import torch.distributed as dist
+    from rma_net_b200 import ext, parallel
+    N = M = 1 << 20
+    g = torch.Generator().manual_seed(4)
+    x_full = torch.rand(1, N, 3, generator=g) * 2 - 1
+    y_full = torch.rand(1, M, 3, generator=g) * 2 - 1
+    s0, s1 = parallel.shard_range(N, rank, world)
+    xl = x_full[:, s0:s1].to(dev).requires_grad_(True)
+    yd = y_full.to(dev).requires_grad_(True)
+    keep = {}
+
+    def step():
+        xl.grad = None
+        yd.grad = None
+        d1, d2, i1, i2 = parallel.SourceShardedChamfer.apply(xl, yd, s0, None)
+        loss = (d1.sum() + d2.sum()) * 0.5
+        loss.backward()
+        keep.update(d1=d1.detach(), d2=d2.detach(), i1=i1, i2=i2)
+
+    ms = _timed_max(step, 3, 1, dev, world)
+    pairs = N * M
+    # ---- self-check ------------------------------------------------------------------------------------------
+    ok = True
+    notes = {}
+    gs = torch.Generator().manual_seed(99)
+    samp_t = torch.randperm(M, generator=gs)[:4096].to(dev)
+    samp_s = torch.randperm(s1 - s0, generator=gs)[:4096].to(dev)
+    with torch.no_grad():
+        xf = x_full.to(dev)
+        _, d2s, _, i2s = ext.chamfer_forward(xf, yd.detach()[:, samp_t].contiguous())     # all sources x sampled targets
+        eq_t = bool(torch.equal(d2s[0], keep["d2"][0, samp_t]) and torch.equal(i2s[0], keep["i2"][0, samp_t]))
+        d1s, _, i1s, _ = ext.chamfer_forward(xl.detach()[:, samp_s].contiguous(), yd.detach())   # sampled local sources
+        eq_s = bool(torch.equal(d1s[0], keep["d1"][0, samp_s]) and torch.equal(i1s[0], keep["i1"][0, samp_s]))
+        del xf
+    ok &= eq_t and eq_s
+    notes["targets_bit_equal_4096"] = eq_t
+    notes["local_sources_bit_equal_4096"] = eq_s
+    # every rank holds the same merged result
+    chk = torch.stack([keep["i2"].sum(dtype=torch.int64), keep["d2"].double().sum().view(torch.int64)])
+    lo, hi = chk.clone(), chk.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same = bool(torch.equal(lo, hi))
+    ok &= same
+    notes["ranks_hold_identical_merge"] = same
+    if rank == 0:
+        try:
+            import numpy as np
+            from oracle import c_oracle           # the checker (test infrastructure), never the thing measured
+            t256 = samp_t[:256].cpu()
+            e = c_oracle.chamfer_fwd(x_full.numpy(), y_full[:, t256].numpy(), "f64")
+            d_gpu = keep["d2"][0, samp_t[:256]].double().cpu().numpy()
+            i_gpu = keep["i2"][0, samp_t[:256]].cpu().numpy()
+            rel = np.abs(d_gpu - e["dist2"][0]) / np.maximum(e["dist2"][0], 1e-30)
+            xf64 = x_full[0].double().numpy()
+            yt = y_full[0, t256].double().numpy()
+            d_at_gpu_idx = ((xf64[i_gpu] - yt) ** 2).sum(-1)
+            near_tie = np.abs(d_at_gpu_idx - e["dist2"][0]) <= 2.0 ** -20 * e["dist2"][0]
+            oracle_ok = bool((rel <= 1e-5).all() and ((i_gpu == e["idx2"][0]) | near_tie).all())
+            notes["fp64_oracle_256_targets"] = oracle_ok
+            notes["fp64_oracle_max_rel_err"] = float(rel.max())
+            notes["fp64_oracle_index_mismatches_all_near_ties"] = int((i_gpu != e["idx2"][0]).sum())
+            ok &= oracle_ok
+        except Exception as ex:       # the oracle library is missing on this box: say so, do not pass silently
+            notes["fp64_oracle_256_targets"] = f"not run: {type(ex).__name__}: {ex}"
+            ok = False
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    path = ext.chamfer_path(1, s1 - s0, M)
+    return {"what": f"one pair N=M=2^20, sources sharded over {world} GPU(s) ({s1 - s0} per GPU), target replicated; "
+                    f"fwd+bwd incl. NCCL all-reduce MIN of packed (distance,index) keys [M] and SUM of grad_target",
+            "n_gpus": world, "scaling": "strong", "ms_per_step": ms, "G_pairs_per_s": pairs / ms / 1e6,
+            "fp32_fma_peak_frac_per_gpu": 6.0 * pairs / world / (ms * 1e-3) / peak_fma,
+            "search_path": path, "collectives_per_step": 0 if world == 1 else 2,
+            "c5_parity": bool(flag.item() == 1), "c5_checks": notes}
 
 # ------------------------------------------------------------------------------------------------------------
 # our arm
@@ -240,7 +461,7 @@ def run_ours(args):
     # ---- roofline leg: the dominant kernel alone, events around the rma_chamfer_search stage -------------------
     lib = _lib.load()
     import ctypes
-    wsb = lib.rma_chamfer_workspace_bytes(B, N, M)
+    wsb = lib.rma_chamfer_workspace_bytes(B, N, M, None)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     d1 = torch.empty(B, N, device=dev)
     d2 = torch.empty(B, M, device=dev)
@@ -253,12 +474,13 @@ def run_ours(args):
     for it in range(args.steps + 3):
         flush.zero_()
         _lib.check(lib.rma_chamfer_prep(P(xd), xs_[0], xs_[1], xs_[2], P(yd), ys_[0], ys_[1], ys_[2], B, N, M,
-                                        P(ws), wsb, stream), "prep")
+                                        P(ws), wsb, None, stream), "prep")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.check(lib.rma_chamfer_search(B, N, M, P(ws), wsb, stream), "search")
+        _lib.check(lib.rma_chamfer_search(B, N, M, P(ws), wsb, None, stream), "search")
         e1.record()
-        _lib.check(lib.rma_chamfer_finalize(B, N, M, P(d1), P(d2), P(i1), P(i2), P(ws), wsb, stream), "finalize")
+        _lib.check(lib.rma_chamfer_finalize(B, N, M, P(d1), P(d2), P(i1), P(i2), P(ws), wsb, None, stream),
+                   "finalize")
         torch.cuda.synchronize()
         if it >= 3:
             k_ms.append(e0.elapsed_time(e1))
@@ -266,7 +488,9 @@ def run_ours(args):
     clocks = sampler.stop()
     # which search implementation ran for this size, and how often the filter's guard sent an item to the slow path
     stats = (ctypes.c_uint * 4)()
-    filt = lib.rma_exp_chamfer_path_info(B, N, M, P(ws), ctypes.cast(stats, ctypes.c_void_p), stream)
+    filt = 1 if lib.rma_chamfer_path(B, N, M, None) == _lib.PATH_FILTER else 0
+    _lib.check(lib.rma_chamfer_guard_stats(B, N, M, P(ws), None, ctypes.cast(stats, ctypes.c_void_p), stream),
+               "guard_stats")
     search_kernel = "chamfer_fsearch_kernel" if filt == 1 else "chamfer_search_kernel"
 
     # ---- e2e leg: host (pinned) inputs, public API, H2D + fwd+bwd + D2H loss every step -------------------------
@@ -403,13 +627,13 @@ def run_ours(args):
             assert len(vals) == steps
             return vals[-1]
 
-        # Every e2e figure below is the best of E2E_REPS runs of K steps each: a single host hiccup (a few ms on a
-        # shared box) is a quarter of a K = 200 run of 18 ms, and the host is inside every one of these loops.
-        E2E_REPS = 3
-        e2e_modes = {}
+        # Every pipelined e2e figure below is the MEDIAN of E2E_REPS runs of K steps each (the host is inside every
+        # one of these loops; min and max of the repeats are reported beside the headline driver).
+        E2E_REPS = 5
+        e2e_modes, e2e_spread = {}, {}
         for lag in (0, 1):
             run_pipelined(4, lag=lag)
-            best = float("inf")
+            reps_ms = []
             for _ in range(E2E_REPS):
                 barrier()
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -419,8 +643,9 @@ def run_ours(args):
                 barrier()
                 if abs(pipelined_loss - serial_loss) > 1e-6 * abs(serial_loss):
                     raise RuntimeError(f"pipelined e2e loss {pipelined_loss} != serial {serial_loss}")
-                best = min(best, ev0.elapsed_time(ev1) / args.steps)
-            e2e_modes[lag] = best
+                reps_ms.append(ev0.elapsed_time(ev1) / args.steps)
+            e2e_modes[lag] = statistics.median(reps_ms)
+            e2e_spread[lag] = [min(reps_ms), max(reps_ms)]
         e2e_sync_ms = e2e_modes[0]
         e2e_ms = e2e_modes[1]
 
@@ -456,7 +681,7 @@ def run_ours(args):
             return vals[-1]
 
         run_fused(4)
-        e2e_fused_ms = float("inf")
+        fused_ms = []
         for _ in range(E2E_REPS):
             barrier()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -466,18 +691,38 @@ def run_ours(args):
             barrier()
             if abs(fused_loss - serial_loss) > 1e-6 * abs(serial_loss):
                 raise RuntimeError(f"graph-pipelined e2e loss {fused_loss} != serial {serial_loss}")
-            e2e_fused_ms = min(e2e_fused_ms, ev0.elapsed_time(ev1) / args.steps)
-        e2e_extra = {"copy_stream_host_loop_ms_per_step": e2e_ms, "copy_in_graph_ms_per_step": e2e_fused_ms,
-                     "note": "value = the faster of two drivers of the same pipeline: the H2D copy of step k+1 "
-                             "issued from Python on a copy stream with events, or captured as a parallel branch of "
-                             "step k's CUDA graph (fewer host calls per step)"}
-        e2e_ms = min(e2e_ms, e2e_fused_ms)
+            fused_ms.append(ev0.elapsed_time(ev1) / args.steps)
+        e2e_fused_ms = statistics.median(fused_ms)
+        e2e_extra = {"driver": "copy_stream_host_loop", "repeats": E2E_REPS,
+                     "ms_per_step_min_max": e2e_spread[1], "sync_ms_per_step_min_max": e2e_spread[0],
+                     "copy_in_graph_ms_per_step": e2e_fused_ms,
+                     "copy_in_graph_value": world * pairs / (e2e_fused_ms * 1e-3) / 1e9,
+                     "note": "value = MEDIAN of 5 runs of K steps of the copy_stream_host_loop driver (the H2D copy of "
+                             "step k+1 issued from Python on a copy stream with events).  copy_in_graph_*: the same "
+                             "pipeline with that copy captured as a parallel branch of step k's CUDA graph (one graph "
+                             "launch per step), median of 5 as well; reported beside it, not folded into value"}
         e2e_mode = ("double-buffered + lagged read: the H2D copy of step k+1 overlaps step k (second device buffer, copy "
                     "stream; rma_net_b200.data.PairBatchLoader pattern) and the host reads step k's loss (own pinned "
                     "slot, event) while step k+1 runs; every step copies its inputs and every loss is read by the host "
                     "inside the timed region.  sync_ms_per_step: same, but the host reads each loss before it launches "
-                    "the next step; serial_ms_per_step: nothing overlapped.  Pipelined figures: best of 3 runs of K "
+                    "the next step; serial_ms_per_step: nothing overlapped.  Pipelined figures: median of 5 runs of K "
                     "steps each")
+
+    # ---- secondary configurations (C3, C4, C5) -----------------------------------------------------------------
+    info = ext.device_info()
+    peaks, peak_src = measured_peaks()
+    sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    peak_fma = info["sm_count"] * 128 * sm_max_mhz * 1e6          # FMA/s per GPU
+    secondary = {}
+    if not args.no_secondary:
+        del flush
+        torch.cuda.empty_cache()
+        for key, fn in (("C3", secondary_c3), ("C4", secondary_c4), ("C5", secondary_c5)):
+            try:
+                secondary[key] = fn(dev, world, rank, peak_fma)
+            except Exception as ex:          # a failed secondary must not take the headline line with it
+                secondary[key] = {"error": f"{type(ex).__name__}: {ex}"}
+            torch.cuda.empty_cache()
 
     # ---- aggregate over ranks (max time) ------------------------------------------------------------------------
     t = torch.tensor([ms, e2e_ms, search_ms, e2e_serial_ms, e2e_sync_ms], dtype=torch.float64, device=dev)
@@ -487,13 +732,11 @@ def run_ours(args):
     value = world * pairs / (ms * 1e-3) / 1e9
     e2e_value = world * pairs / (e2e_ms * 1e-3) / 1e9
 
-    info = ext.device_info()
-    peaks, peak_src = measured_peaks()
-    sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
     peak_tflops = info["sm_count"] * 128 * 2 * sm_max_mhz * 1e6 / 1e12
     achieved_tflops = FLOP_PER_PAIR * pairs / (search_ms * 1e-3) / 1e12
     ctas, thr, spl, occ = (ctypes.c_int() for _ in range(4))
-    lib.rma_chamfer_search_config(B, N, M, ctypes.byref(ctas), ctypes.byref(thr), ctypes.byref(spl), ctypes.byref(occ))
+    lib.rma_chamfer_search_config(B, N, M, None, ctypes.byref(ctas), ctypes.byref(thr), ctypes.byref(spl),
+                                  ctypes.byref(occ))
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -515,10 +758,13 @@ def run_ours(args):
         "fp32_fma_peak_frac_step": FLOP_PER_PAIR * pairs / (ms * 1e-3) / 1e12 / peak_tflops,
         "roofline": {"bound": "fp32_fma", "kernel": search_kernel, "achieved": achieved_tflops,
                      "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the ncu --set full
-                     # capture of the C2 step (profiles/r01p_ncu_full_selected.csv): 2.12 MB read + 0.51 MB written
-                     # (compute-bound: inputs and records live in L2); not re-measured for other workloads
-                     "traffic": 2.63e6 if (name == "C2" and filt == 1) else None, "kernel_ms": search_ms,
+                     # the north-star quantity: the same algorithmic FLOP over the WHOLE fwd+bwd step (prep + search +
+                     # resolve + backward), L2 flushed before every step
+                     "step_frac": FLOP_PER_PAIR * pairs / (ms * 1e-3) / 1e12 / peak_tflops,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch cannot be measured inside
+                     # this run (it needs ncu): taken from the committed ncu --set full capture named in
+                     # traffic_source, for this workload and search kernel only
+                     **search_traffic(name, search_kernel), "kernel_ms": search_ms,
                      "note": ("achieved = ALGORITHMIC 12 FLOP (6 FMA) per point-pair (SURVEY.md section 8d) / kernel "
                               "time.  The filter kernel itself issues 3 FFMA + 1 FADD + 2 min per pair (its exact "
                               "re-evaluation of the candidates runs in the resolve kernel), so frac is a fraction "
@@ -536,6 +782,7 @@ def run_ours(args):
                 "host_layout": "one pinned [B,2N,3] pair batch (train_view.py:369-370), one H2D copy, strided slices"
                                if pair_pin is not None else "two pinned clouds, two H2D copies", **e2e_extra},
         "gpu_launches": 4 * args.steps,      # prep + search + resolve/finalize(+loss,+grads) + cd_backward per step
+        "secondary": secondary,
         "clocks": clocks,
         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
         "step_ms_min_max": [min(step_ms), max(step_ms)],
@@ -543,12 +790,12 @@ def run_ours(args):
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sample_b = min(B, 4)
+        sample_b = B
         sec = cpu_reference_time(x_host, y_host, sample_b, reps=3, threads=threads)
         line["cpu_baseline"] = {
             "value": sample_b * N * M / sec / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"first {sample_b} of {B} batch elements, best of 3, torch CPU fp32 (reference formulation: "
-                      f"expanded-form [B,N,M] matrix + autograd)"}
+            "sample": f"all {sample_b} of {B} batch elements, best of 3, torch CPU fp32 (reference formulation: "
+                      f"expanded-form [B,N,M] matrix + autograd, model/loss.py:45-70, 200-205)"}
     if world > 1:
         dist.destroy_process_group()
     if rank == 0:
@@ -569,6 +816,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C3 / C4 / C5 legs of the `secondary` object")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RMA_B200_ABI_VERSION 1
+#define RMA_B200_ABI_VERSION 2
 
 #define RMA_OK 0
 #define RMA_E_BADARG (-1)     /* null pointer / non-positive size / size overflow */
@@ -50,26 +50,49 @@ int rma_b200_device_info(int* sm_count, int* clock_khz, int* cc_major, int* cc_m
  * batch-strided slices (train_view.py:369-370) and transposed stage outputs (loss.py:264) are taken as they are.
  * dist1/idx1 are contiguous [B,N]; dist2/idx2 contiguous [B,M].  idx1/idx2 may be NULL (forward-only metric calls).
  * Distances are evaluated in fp32 DIFFERENCE form (dx*dx, fma(dy,dy,.), fma(dz,dz,.)), never the expanded form;
- * the [B,N,M] matrix is never materialised.  workspace: rma_chamfer_workspace_bytes(B,N,M) bytes, 256-B aligned.
+ * the [B,N,M] matrix is never materialised.  workspace: rma_chamfer_workspace_bytes(B,N,M,opts) bytes, 256-B aligned.
+ *
+ * Per-call options (`opts`, may be NULL = all defaults; the SAME opts must be passed to workspace_bytes and to every
+ * stage that works on that workspace).  Two search implementations return identical results: the filter + exact
+ * resolve path (default) and the exact difference-form path, which takes over when the filter's group records
+ * (B*N*M/64 bytes) would exceed record_cap_bytes (default 4 GiB, or RMA_B200_FILTER_RECORD_CAP_MB read once at load
+ * time).  Everything is decided from the call's own arguments: the library keeps no mutable state between calls.
  */
-size_t rma_chamfer_workspace_bytes(int B, int N, int M);
+#define RMA_CHAMFER_PATH_AUTO 0
+#define RMA_CHAMFER_PATH_EXACT 1
+#define RMA_CHAMFER_PATH_FILTER 2
+typedef struct rma_chamfer_opts {
+  int32_t path;               /* RMA_CHAMFER_PATH_*: force one search implementation (parity tests, A/B timing) */
+  int32_t unit_run;           /* > 0: 64-column tiles per search CTA (filter path) / column splits (exact path) */
+  int64_t record_cap_bytes;   /* > 0: switch-over size of the automatic choice */
+} rma_chamfer_opts;
+size_t rma_chamfer_workspace_bytes(int B, int N, int M, const rma_chamfer_opts* opts);
+/* RMA_CHAMFER_PATH_EXACT or RMA_CHAMFER_PATH_FILTER: what (B,N,M,opts) runs (< 0: bad sizes). */
+int rma_chamfer_path(int B, int N, int M, const rma_chamfer_opts* opts);
+/* Guard statistics of the LAST resolve on this workspace (filter path; zeros on the exact path): rows on the slow
+ * path, columns on the slow path, 512-row block rescans, unused.  Synchronises `stream`. */
+int rma_chamfer_guard_stats(int B, int N, int M, void* workspace, const rma_chamfer_opts* opts,
+                            uint32_t* stats4_host, void* stream);
 int rma_chamfer_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
                         const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
                         int B, int N, int M,
                         float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
-                        void* workspace, size_t workspace_bytes, void* stream);
+                        void* workspace, size_t workspace_bytes, const rma_chamfer_opts* opts, void* stream);
 
 /* The three stages of rma_chamfer_forward as separate calls on the same workspace (prep -> search -> finalize).
  * rma_chamfer_forward is exactly their composition; they exist so that a harness can bracket the dominant kernel
  * (search) with its own events (bench.py roofline leg) or capture the stages in a graph individually. */
 int rma_chamfer_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
                      const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
-                     int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream);
-int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream);
+                     int B, int N, int M, void* workspace, size_t workspace_bytes, const rma_chamfer_opts* opts,
+                     void* stream);
+int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_bytes, const rma_chamfer_opts* opts,
+                       void* stream);
 int rma_chamfer_finalize(int B, int N, int M, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
-                         void* workspace, size_t workspace_bytes, void* stream);
-/* Launch shape the search kernel will use for (B,N,M) on the current device (reporting only). */
-int rma_chamfer_search_config(int B, int N, int M, int* ctas, int* threads, int* splits, int* ctas_per_sm);
+                         void* workspace, size_t workspace_bytes, const rma_chamfer_opts* opts, void* stream);
+/* Launch shape the search kernel will use for (B,N,M,opts) on the current device (reporting only). */
+int rma_chamfer_search_config(int B, int N, int M, const rma_chamfer_opts* opts, int* ctas, int* threads, int* splits,
+                              int* ctas_per_sm);
 
 /* Fused loss_on_cd (model/loss.py:200-205 on top of chamfer_dist): in the same three launches,
  *   *loss = 0.5 * (sum dist1 + sum dist2) / B                       (device scalar, overwritten)
@@ -83,7 +106,7 @@ int rma_chamfer_cd_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc
                            const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
                            int B, int N, int M, float* loss, float* dist1, float* dist2, int32_t* idx1,
                            int32_t* idx2, float* own_x, float* scat_x, float* own_y, float* scat_y,
-                           void* workspace, size_t workspace_bytes, void* stream);
+                           void* workspace, size_t workspace_bytes, const rma_chamfer_opts* opts, void* stream);
 /* The same with per-batch-element weights (device array [B] or NULL = 1) and an explicit coefficient:
  *   *loss = coef * sum_b batch_weight[b] * (sum dist1[b] + sum dist2[b]),   gradients scaled accordingly.
  * This is the stage loop of Loss.forward (loss.py:260-267) as ONE call: stack the T stage outputs as a [T*B,N,3] batch,
@@ -93,7 +116,7 @@ int rma_chamfer_cd_forward_weighted(const float* x, int64_t xsb, int64_t xsn, in
                                     int B, int N, int M, const float* batch_weight, float coef, float* loss,
                                     float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* own_x,
                                     float* scat_x, float* own_y, float* scat_y, void* workspace,
-                                    size_t workspace_bytes, void* stream);
+                                    size_t workspace_bytes, const rma_chamfer_opts* opts, void* stream);
 /* out_x[p,c] = *scalar_dev * (own_x[p,c] + scat_x[p,c]) for p < nx points (out_x [nx,3]); same for y.  The upstream
  * scalar is read on the device (no host sync).  Either half may be empty (n = 0). */
 int rma_chamfer_cd_backward(const float* own_x, const float* scat_x, int64_t nx, const float* own_y,

@@ -11,22 +11,35 @@ LIB_PATH = os.path.join(_HERE, "lib", "librma_b200.so")
 _P = c_void_p
 _I64 = c_int64
 
+
+class ChamferOpts(ctypes.Structure):
+    """`rma_chamfer_opts` of include/rma_b200.h: per-call choice of the search implementation (no library state)."""
+    _fields_ = [("path", c_int32), ("unit_run", c_int32), ("record_cap_bytes", c_int64)]
+
+
+PATH_AUTO, PATH_EXACT, PATH_FILTER = 0, 1, 2
+_O = ctypes.POINTER(ChamferOpts)
+
 # name -> (restype, argtypes); mirrors include/rma_b200.h declaration by declaration.
 SIGNATURES = {
     "rma_b200_abi_version": (c_int, []),
     "rma_b200_error_string": (c_char_p, [c_int]),
     "rma_b200_device_info": (c_int, [_P, _P, _P, _P]),
-    "rma_chamfer_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "rma_chamfer_workspace_bytes": (c_size_t, [c_int, c_int, c_int, _O]),
+    "rma_chamfer_path": (c_int, [c_int, c_int, c_int, _O]),
+    "rma_chamfer_guard_stats": (c_int, [c_int, c_int, c_int, _P, _O, _P, _P]),
     "rma_chamfer_forward": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, c_int, c_int, c_int,
-                                    _P, _P, _P, _P, _P, c_size_t, _P]),
-    "rma_chamfer_prep": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P, c_size_t, _P]),
-    "rma_chamfer_search": (c_int, [c_int, c_int, c_int, _P, c_size_t, _P]),
-    "rma_chamfer_finalize": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
-    "rma_chamfer_search_config": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
+                                    _P, _P, _P, _P, _P, c_size_t, _O, _P]),
+    "rma_chamfer_prep": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P, c_size_t, _O,
+                                 _P]),
+    "rma_chamfer_search": (c_int, [c_int, c_int, c_int, _P, c_size_t, _O, _P]),
+    "rma_chamfer_finalize": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _O, _P]),
+    "rma_chamfer_search_config": (c_int, [c_int, c_int, c_int, _O, _P, _P, _P, _P]),
     "rma_chamfer_cd_forward": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, c_int, c_int, c_int,
-                                       _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+                                       _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _O, _P]),
     "rma_chamfer_cd_forward_weighted": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, c_int, c_int, c_int,
-                                                _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+                                                _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _O,
+                                                _P]),
     "rma_chamfer_cd_backward": (c_int, [_P, _P, _I64, _P, _P, _I64, _P, _P, _P, _P]),
     "rma_chamfer_backward": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, c_int, c_int, c_int,
                                      _P, _P, _P, _P, _P, _P, _P]),
@@ -57,13 +70,6 @@ SIGNATURES = {
     "rma_chamfer_loss_host": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
 }
 
-# Experiment / test hooks exported by the library but deliberately not part of include/rma_b200.h.
-EXPERIMENT_SIGNATURES = {
-    "rma_exp_set_chamfer_path": (c_int, [c_int, c_int64]),        # 0 auto, 1 exact search, 2 filter + resolve
-    "rma_exp_chamfer_path_info": (c_int, [c_int, c_int, c_int, _P, _P, _P]),
-    "rma_exp_set_search_debug": (c_int, [_P, c_int, c_int]),
-}
-
 _lib = None
 
 
@@ -86,11 +92,16 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)          # AttributeError here == header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    for name, (res, args) in EXPERIMENT_SIGNATURES.items():
+    _lib = lib
+    return lib
+
+
+def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
+    """Declare the header's signatures on another build of this library (tools/: -D variants of one kernel)."""
+    for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
     return lib
 
 

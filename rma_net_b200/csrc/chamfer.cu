@@ -598,33 +598,49 @@ using namespace rma;
 namespace rma {
 bool f_sizes_ok(int B, int N, int M);
 size_t f_record_bytes(int B, int N, int M);
-size_t f_workspace_bytes(int B, int N, int M);
+size_t f_workspace_bytes(int B, int N, int M, int unit_run);
 int f_launch_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc, const float* y, int64_t ysb, int64_t ysn,
-                  int64_t ysc, int B, int N, int M, void* workspace, size_t workspace_bytes, float* zero_loss,
-                  float4* zero_gx, float4* zero_gy, void* stream_);
-int f_search_config(int B, int N, int M, int* ctas, int* threads, int* splits, int* ctas_per_sm);
-int f_launch_search(int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream_);
-void f_set_force_unit_run(int u);
-int f_launch_resolve(int B, int N, int M, const FinalizeArgs& f, void* workspace, size_t workspace_bytes,
-                     void* stream_);
-int f_read_stats(void* workspace, int B, int N, int M, unsigned* out4, void* stream_);
+                  int64_t ysc, int B, int N, int M, int unit_run, void* workspace, size_t workspace_bytes,
+                  float* zero_loss, float4* zero_gx, float4* zero_gy, void* stream_);
+int f_search_config(int B, int N, int M, int unit_run, int* ctas, int* threads, int* splits, int* ctas_per_sm);
+int f_launch_search(int B, int N, int M, int unit_run, void* workspace, size_t workspace_bytes, void* stream_);
+int f_launch_resolve(int B, int N, int M, int unit_run, const FinalizeArgs& f, void* workspace,
+                     size_t workspace_bytes, void* stream_);
+int f_read_stats(void* workspace, int B, int N, int M, int unit_run, unsigned* out4, void* stream_);
 }  // namespace rma
 
 // Which search runs: the filter path whenever its group records (B*N*M/64 bytes) stay below the cap, else the
-// exact path (huge single pairs, SURVEY.md config C5 on few GPUs).  Both return identical results.
-static int g_force_path = 0;                                  // experiment hook: 0 auto, 1 exact, 2 filter
-// Record cap: default 4 GiB (C5 sharded over 4 or 8 GPUs stays on the filter path); RMA_B200_FILTER_RECORD_CAP_MB
-// overrides it (180 GB of HBM make tens of GB reasonable for a single huge pair).
-static size_t g_filter_record_cap = [] {
+// exact path (huge single pairs, SURVEY.md config C5 on few GPUs).  Both return identical results.  Every choice is
+// a function of the call's own arguments (sizes + rma_chamfer_opts): the library keeps no mutable state.
+// Default record cap: 4 GiB (C5 sharded over 4 or 8 GPUs stays on the filter path); the environment variable
+// RMA_B200_FILTER_RECORD_CAP_MB, read once when the library is loaded, changes the default (180 GB of HBM make tens
+// of GB reasonable for a single huge pair).
+static const size_t g_default_record_cap = [] {
   const char* e = std::getenv("RMA_B200_FILTER_RECORD_CAP_MB");
   const long long mb = e ? std::atoll(e) : 0;
   return mb > 0 ? (size_t)mb << 20 : (size_t)4 << 30;
 }();
 
-static bool use_filter(int B, int N, int M) {
-  if (g_force_path == 1 || !f_sizes_ok(B, N, M)) return false;
-  if (g_force_path == 2) return true;
-  return f_record_bytes(B, N, M) <= g_filter_record_cap;
+struct ChamferOpts {
+  int path;        // RMA_CHAMFER_PATH_*
+  int unit_run;    // 0 = automatic
+  size_t cap;      // filter record cap in bytes
+};
+
+static ChamferOpts make_opts(const rma_chamfer_opts* o) {
+  ChamferOpts r = {RMA_CHAMFER_PATH_AUTO, 0, g_default_record_cap};
+  if (o) {
+    if (o->path == RMA_CHAMFER_PATH_EXACT || o->path == RMA_CHAMFER_PATH_FILTER) r.path = o->path;
+    if (o->unit_run > 0) r.unit_run = o->unit_run;
+    if (o->record_cap_bytes > 0) r.cap = (size_t)o->record_cap_bytes;
+  }
+  return r;
+}
+
+static bool use_filter(int B, int N, int M, const ChamferOpts& o) {
+  if (o.path == RMA_CHAMFER_PATH_EXACT || !f_sizes_ok(B, N, M)) return false;
+  if (o.path == RMA_CHAMFER_PATH_FILTER) return true;
+  return f_record_bytes(B, N, M) <= o.cap;
 }
 
 extern "C" {
@@ -659,15 +675,27 @@ static bool sizes_ok(int B, int N, int M) {
   return true;
 }
 
-size_t rma_chamfer_workspace_bytes(int B, int N, int M) {
+size_t rma_chamfer_workspace_bytes(int B, int N, int M, const rma_chamfer_opts* opts) {
   if (!sizes_ok(B, N, M)) return 0;
+  const ChamferOpts o = make_opts(opts);
   const Geometry g = make_geometry(B, N, M);
   size_t bytes = carve(g, nullptr).bytes;
-  if (use_filter(B, N, M)) { const size_t fb = f_workspace_bytes(B, N, M); if (fb > bytes) bytes = fb; }
+  if (use_filter(B, N, M, o)) { const size_t fb = f_workspace_bytes(B, N, M, o.unit_run); if (fb > bytes) bytes = fb; }
   return bytes;
 }
 
-static int g_force_splits = 0;   // experiment hook, see rma_exp_set_search_debug
+int rma_chamfer_path(int B, int N, int M, const rma_chamfer_opts* opts) {
+  if (!sizes_ok(B, N, M)) return RMA_E_BADARG;
+  return use_filter(B, N, M, make_opts(opts)) ? RMA_CHAMFER_PATH_FILTER : RMA_CHAMFER_PATH_EXACT;
+}
+
+int rma_chamfer_guard_stats(int B, int N, int M, void* workspace, const rma_chamfer_opts* opts,
+                            uint32_t* stats4_host, void* stream) {
+  if (!sizes_ok(B, N, M) || !workspace || !stats4_host) return RMA_E_BADARG;
+  const ChamferOpts o = make_opts(opts);
+  if (!use_filter(B, N, M, o)) { stats4_host[0] = stats4_host[1] = stats4_host[2] = stats4_host[3] = 0u; return RMA_OK; }
+  return f_read_stats(workspace, B, N, M, o.unit_run, stats4_host, stream);
+}
 
 static int forward_setup(const float* x, const float* y, int B, int N, int M, void* workspace,
                          size_t workspace_bytes, Geometry* g, Workspace* w) {
@@ -681,11 +709,11 @@ static int forward_setup(const float* x, const float* y, int B, int N, int M, vo
 
 static int launch_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
                        const float* y, int64_t ysb, int64_t ysn, int64_t ysc, int B, int N, int M,
-                       void* workspace, size_t workspace_bytes, float* zero_loss, float4* zero_gx, float4* zero_gy,
-                       void* stream_) {
-  if (x && y && sizes_ok(B, N, M) && use_filter(B, N, M))
-    return f_launch_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, workspace, workspace_bytes, zero_loss,
-                         zero_gx, zero_gy, stream_);
+                       const ChamferOpts& o, void* workspace, size_t workspace_bytes, float* zero_loss,
+                       float4* zero_gx, float4* zero_gy, void* stream_) {
+  if (x && y && sizes_ok(B, N, M) && use_filter(B, N, M, o))
+    return f_launch_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, o.unit_run, workspace, workspace_bytes,
+                         zero_loss, zero_gx, zero_gy, stream_);
   Geometry g; Workspace w;
   if (int e = forward_setup(x, y, B, N, M, workspace, workspace_bytes, &g, &w)) return e;
   const long long slots = (long long)B * (g.Npad + g.Mp);
@@ -697,14 +725,16 @@ static int launch_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
 
 int rma_chamfer_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
                      const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
-                     int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream_) {
-  return launch_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, workspace, workspace_bytes, nullptr, nullptr,
-                     nullptr, stream_);
+                     int B, int N, int M, void* workspace, size_t workspace_bytes, const rma_chamfer_opts* opts,
+                     void* stream_) {
+  return launch_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, make_opts(opts), workspace, workspace_bytes,
+                     nullptr, nullptr, nullptr, stream_);
 }
 
-int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream_) {
-  if (sizes_ok(B, N, M) && use_filter(B, N, M))
-    return f_launch_search(B, N, M, workspace, workspace_bytes, stream_);
+static int launch_search(int B, int N, int M, const ChamferOpts& o, void* workspace, size_t workspace_bytes,
+                         void* stream_) {
+  if (sizes_ok(B, N, M) && use_filter(B, N, M, o))
+    return f_launch_search(B, N, M, o.unit_run, workspace, workspace_bytes, stream_);
   Geometry g; Workspace w;
   if (int e = forward_setup((const float*)workspace, (const float*)workspace, B, N, M, workspace, workspace_bytes,
                             &g, &w)) return e;
@@ -716,7 +746,7 @@ int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_by
   a.rowbest = w.rowbest;
   a.colbest = w.colbest;
   a.N = N; a.M = M; a.nRB = g.nRB; a.Npad = g.Npad; a.nRBC = g.nRBC; a.Mp = g.Mp;
-  a.S = g_force_splits > 0 ? g_force_splits : choose_splits(g, caps);
+  a.S = o.unit_run > 0 ? o.unit_run : choose_splits(g, caps);   // exact path: unit_run = column splits per row block
   const long long ctas = (long long)B * g.nRBC * a.S;
   if (ctas > 0x7fffffffLL) return RMA_E_BADARG;
   RMA_CUDA_TRY(launch_pdl(chamfer_search_kernel, (unsigned)ctas, (unsigned)kSearchThreads, kSearchSmem,
@@ -724,33 +754,15 @@ int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_by
   return RMA_OK;
 }
 
-// Experiment hook (tools/fsearch_variants.py only; not part of include/rma_b200.h, not used by the product path):
-// forces the column splits of the exact search / the unit run (64-column tiles per CTA) of the filter search.
-// The first and third arguments are ignored (kept for the tools' call signature).
-int rma_exp_set_search_debug(long long* /*unused*/, int force_splits, int /*unused*/) {
-  g_force_splits = force_splits;
-  f_set_force_unit_run(force_splits);
-  return RMA_OK;
+int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_bytes, const rma_chamfer_opts* opts,
+                       void* stream_) {
+  return launch_search(B, N, M, make_opts(opts), workspace, workspace_bytes, stream_);
 }
 
-// 0 = auto, 1 = exact search, 2 = filter + resolve; record_cap_bytes > 0 changes the automatic switch-over.
-int rma_exp_set_chamfer_path(int path, long long record_cap_bytes) {
-  g_force_path = path;
-  if (record_cap_bytes > 0) g_filter_record_cap = (size_t)record_cap_bytes;
-  return RMA_OK;
-}
-// 1 if (B,N,M) runs the filter path.  stats4_host (optional, filter path only): extra row candidates, extra column
-// candidates, row-block rescans of the last resolve on this workspace (synchronises the stream).
-int rma_exp_chamfer_path_info(int B, int N, int M, void* workspace, unsigned* stats4_host, void* stream_) {
-  if (!sizes_ok(B, N, M)) return RMA_E_BADARG;
-  const int filt = use_filter(B, N, M) ? 1 : 0;
-  if (filt && workspace && stats4_host) { if (int e = f_read_stats(workspace, B, N, M, stats4_host, stream_)) return e; }
-  return filt;
-}
-
-static int launch_finalize(int B, int N, int M, const FinalizeArgs& f, void* workspace, size_t workspace_bytes,
-                           void* stream_) {
-  if (sizes_ok(B, N, M) && use_filter(B, N, M)) return f_launch_resolve(B, N, M, f, workspace, workspace_bytes, stream_);
+static int launch_finalize(int B, int N, int M, const ChamferOpts& o, const FinalizeArgs& f, void* workspace,
+                           size_t workspace_bytes, void* stream_) {
+  if (sizes_ok(B, N, M) && use_filter(B, N, M, o))
+    return f_launch_resolve(B, N, M, o.unit_run, f, workspace, workspace_bytes, stream_);
   Geometry g; Workspace w;
   if (int e = forward_setup((const float*)workspace, (const float*)workspace, B, N, M, workspace, workspace_bytes,
                             &g, &w)) return e;
@@ -761,19 +773,21 @@ static int launch_finalize(int B, int N, int M, const FinalizeArgs& f, void* wor
 }
 
 int rma_chamfer_finalize(int B, int N, int M, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
-                         void* workspace, size_t workspace_bytes, void* stream_) {
+                         void* workspace, size_t workspace_bytes, const rma_chamfer_opts* opts, void* stream_) {
   if (!dist1 || !dist2) return RMA_E_BADARG;
   FinalizeArgs f = {dist1, dist2, idx1, idx2, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr};
-  return launch_finalize(B, N, M, f, workspace, workspace_bytes, stream_);
+  return launch_finalize(B, N, M, make_opts(opts), f, workspace, workspace_bytes, stream_);
 }
 
-int rma_chamfer_search_config(int B, int N, int M, int* ctas, int* threads, int* splits, int* ctas_per_sm) {
+int rma_chamfer_search_config(int B, int N, int M, const rma_chamfer_opts* opts, int* ctas, int* threads, int* splits,
+                              int* ctas_per_sm) {
   if (!sizes_ok(B, N, M)) return RMA_E_BADARG;
-  if (use_filter(B, N, M)) return f_search_config(B, N, M, ctas, threads, splits, ctas_per_sm);
+  const ChamferOpts o = make_opts(opts);
+  if (use_filter(B, N, M, o)) return f_search_config(B, N, M, o.unit_run, ctas, threads, splits, ctas_per_sm);
   const Geometry g = make_geometry(B, N, M);
   DeviceCaps caps;
   if (int e = get_caps(&caps)) return e;
-  const int S = choose_splits(g, caps);
+  const int S = o.unit_run > 0 ? o.unit_run : choose_splits(g, caps);
   if (ctas) *ctas = B * g.nRBC * S;
   if (threads) *threads = kSearchThreads;
   if (splits) *splits = S;
@@ -784,12 +798,12 @@ int rma_chamfer_search_config(int B, int N, int M, int* ctas, int* threads, int*
 int rma_chamfer_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
                         const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
                         int B, int N, int M, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
-                        void* workspace, size_t workspace_bytes, void* stream) {
+                        void* workspace, size_t workspace_bytes, const rma_chamfer_opts* opts, void* stream) {
   if (!dist1 || !dist2) return RMA_E_BADARG;
-  if (int e = rma_chamfer_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, workspace, workspace_bytes, stream))
+  if (int e = rma_chamfer_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, workspace, workspace_bytes, opts, stream))
     return e;
-  if (int e = rma_chamfer_search(B, N, M, workspace, workspace_bytes, stream)) return e;
-  return rma_chamfer_finalize(B, N, M, dist1, dist2, idx1, idx2, workspace, workspace_bytes, stream);
+  if (int e = rma_chamfer_search(B, N, M, workspace, workspace_bytes, opts, stream)) return e;
+  return rma_chamfer_finalize(B, N, M, dist1, dist2, idx1, idx2, workspace, workspace_bytes, opts, stream);
 }
 
 int rma_chamfer_cd_forward_weighted(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
@@ -797,28 +811,29 @@ int rma_chamfer_cd_forward_weighted(const float* x, int64_t xsb, int64_t xsn, in
                                     int B, int N, int M, const float* batch_weight, float coef, float* loss,
                                     float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* own_x,
                                     float* scat_x, float* own_y, float* scat_y, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+                                    size_t workspace_bytes, const rma_chamfer_opts* opts, void* stream) {
   if (!loss) return RMA_E_BADARG;
+  const ChamferOpts o = make_opts(opts);
   if ((own_x == nullptr) != (scat_x == nullptr) || (own_y == nullptr) != (scat_y == nullptr)) return RMA_E_BADARG;
   if ((((uintptr_t)scat_x) | ((uintptr_t)scat_y)) & 15u) return RMA_E_BADARG;
-  if (int e = launch_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, workspace, workspace_bytes, loss,
+  if (int e = launch_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, o, workspace, workspace_bytes, loss,
                           (float4*)scat_x, (float4*)scat_y, stream))
     return e;
-  if (int e = rma_chamfer_search(B, N, M, workspace, workspace_bytes, stream)) return e;
+  if (int e = launch_search(B, N, M, o, workspace, workspace_bytes, stream)) return e;
   FinalizeArgs f = {dist1, dist2, idx1, idx2, loss, own_x, own_y, (float4*)scat_x, (float4*)scat_y, coef,
                     batch_weight};
-  return launch_finalize(B, N, M, f, workspace, workspace_bytes, stream);
+  return launch_finalize(B, N, M, o, f, workspace, workspace_bytes, stream);
 }
 
 int rma_chamfer_cd_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
                            const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
                            int B, int N, int M, float* loss, float* dist1, float* dist2, int32_t* idx1,
                            int32_t* idx2, float* own_x, float* scat_x, float* own_y, float* scat_y,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+                           void* workspace, size_t workspace_bytes, const rma_chamfer_opts* opts, void* stream) {
   if (B <= 0) return RMA_E_BADARG;
   return rma_chamfer_cd_forward_weighted(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, nullptr, 0.5f / (float)B, loss,
                                          dist1, dist2, idx1, idx2, own_x, scat_x, own_y, scat_y, workspace,
-                                         workspace_bytes, stream);
+                                         workspace_bytes, opts, stream);
 }
 
 // out[p, c] = scalar * (own[p, c] + scat[p].c): combines the two gradient halves of the fused forward and applies
@@ -927,7 +942,7 @@ int rma_chamfer_loss_host(const float* x_host, const float* y_host, int B, int N
                           float* grad_x_host, float* grad_y_host) {
   if (!x_host || !y_host || !sizes_ok(B, N, M)) return RMA_E_BADARG;
   const size_t nx = (size_t)B * N, ny = (size_t)B * M;
-  const size_t wsb = rma_chamfer_workspace_bytes(B, N, M);
+  const size_t wsb = rma_chamfer_workspace_bytes(B, N, M, nullptr);
   const bool want_grad = grad_x_host || grad_y_host;
   // one device allocation, carved
   size_t off = 0;
@@ -946,7 +961,7 @@ int rma_chamfer_loss_host(const float* x_host, const float* y_host, int B, int N
   TRY_(cudaMemcpyAsync(d + o_y, y_host, ny * 12, cudaMemcpyHostToDevice, st));
   rc = rma_chamfer_forward((float*)(d + o_x), (int64_t)N * 3, 3, 1, (float*)(d + o_y), (int64_t)M * 3, 3, 1, B, N, M,
                            (float*)(d + o_d1), (float*)(d + o_d2), (int32_t*)(d + o_i1), (int32_t*)(d + o_i2),
-                           d + o_ws, wsb, st);
+                           d + o_ws, wsb, nullptr, st);
   if (rc) return fail(rc);
   TRY_(cudaMemsetAsync(d + o_acc, 0, 8, st));
   loss_sum_kernel<<<148, 256, 0, st>>>((float*)(d + o_d1), (long long)nx, (float*)(d + o_d2), (long long)ny,

@@ -25,6 +25,8 @@
 //   then D_j* <= D_jf (1 + 10.1 eps), hence f_j* <= f_jf + 2 e(a, beta) + 10.1 eps D_jf with beta >= b_jf, b_j*;
 //   beta = a + sqrt(1.0001 D_jf) by the triangle inequality, and D_jf <= 1.001 (f_jf + u_i)^+ + 1e-5 u_i.
 //   guard_row / guard_col below evaluate these bounds with >= 1% slack plus an absolute 1e-30 for underflow.
+#include <atomic>
+
 #include "chamfer_common.cuh"
 #include "../../include/rma_b200.h"
 
@@ -566,7 +568,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       }
     }
     const float thr = M1 + guard_row(rp.w, M1);
-#if defined(RMA_EXP_NO_SLOW) || defined(RMA_EXP_NO_SLOW_ROWS)   // timing experiment only (tools/resolve_variants.py): wrong results for the slow-path items
+#if defined(RMA_B200_EXPERIMENTS) && (defined(RMA_EXP_NO_SLOW) || defined(RMA_EXP_NO_SLOW_ROWS))   // timing experiment only (tools/resolve_variants.py): wrong results for the slow-path items
     const bool fast = valid;
 #else
     const bool fast = valid && M2 > thr;
@@ -726,7 +728,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       }
     }
     const float thr = M1 + guard_col(cq.w, M1);
-#if defined(RMA_EXP_NO_SLOW) || defined(RMA_EXP_NO_SLOW_COLS)   // timing experiment only (tools/resolve_variants.py): wrong results for the slow-path items
+#if defined(RMA_B200_EXPERIMENTS) && (defined(RMA_EXP_NO_SLOW) || defined(RMA_EXP_NO_SLOW_COLS))   // timing experiment only (tools/resolve_variants.py): wrong results for the slow-path items
     const bool fast = valid;
 #else
     const bool fast = valid && M2 > thr;
@@ -845,9 +847,6 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
 // ---------------------------------------------------------------------------------------------------------------
 // host side (called from the dispatcher in chamfer.cu)
 // ---------------------------------------------------------------------------------------------------------------
-static int g_force_unit_run = 0;   // experiment hook
-void f_set_force_unit_run(int u) { g_force_unit_run = u; }
-
 bool f_sizes_ok(int B, int N, int M) {
   if (B <= 0 || N <= 0 || M <= 0) return false;
   if ((long long)N > (1LL << 30) || (long long)M > (1LL << 30)) return false;
@@ -864,42 +863,48 @@ size_t f_record_bytes(int B, int N, int M) {
   return ((size_t)g.B * g.nRB * kFColTop * g.Mp) * sizeof(float);
 }
 
-// SM count and resident search CTAs per SM of the current device.  Immutable device properties, cached per device
-// (the occupancy query costs ~10 us of host time, which matters for eager callers at ~90 us per step).
+// SM count and resident search CTAs per SM of the current device.  Immutable device properties, memoised per device
+// (the occupancy query costs ~10 us of host time, which matters for eager callers at ~90 us per step).  The memo is
+// a pure cache of constants: one packed atomic word per device (release / acquire), so concurrent first calls from
+// several threads at worst query twice and store the same value.
 static int f_caps(int* sms, int* occ) {
-  static int cache_sms[64], cache_occ[64];
-  static bool cache_ok[64];
+  static std::atomic<unsigned> memo[64];   // 0 = empty, else (sms << 8) | occ
   int dev = 0;
   RMA_CUDA_TRY(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && cache_ok[dev]) { *sms = cache_sms[dev]; *occ = cache_occ[dev]; return 0; }
+  if (dev >= 0 && dev < 64) {
+    const unsigned m = memo[dev].load(std::memory_order_acquire);
+    if (m) { *sms = (int)(m >> 8); *occ = (int)(m & 0xffu); return 0; }
+  }
   RMA_CUDA_TRY(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
   RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)kFSearchSmem));
   RMA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, chamfer_fsearch_kernel, kFThreads, kFSearchSmem));
   if (*occ < 1) *occ = 1;
-  if (dev >= 0 && dev < 64) { cache_sms[dev] = *sms; cache_occ[dev] = *occ; cache_ok[dev] = true; }
+  if (*occ > 255) *occ = 255;
+  if (dev >= 0 && dev < 64) memo[dev].store(((unsigned)*sms << 8) | (unsigned)*occ, std::memory_order_release);
   return 0;
 }
 
 // Geometry for the current device (the unit run depends on SM count x resident CTAs).  Re-derived per call: the
 // library keeps no state, and every stage of one forward derives the identical geometry.
-static int f_geometry(int B, int N, int M, FGeometry* g, int* occ_out) {
+static int f_geometry(int B, int N, int M, int unit_run, FGeometry* g, int* occ_out) {
   int sms = 0, occ = 0;
   if (int e = f_caps(&sms, &occ)) return e;
-  *g = f_make_geometry(B, N, M, sms * occ, g_force_unit_run);
+  *g = f_make_geometry(B, N, M, sms * occ, unit_run);
   if (occ_out) *occ_out = occ;
   return 0;
 }
 
-size_t f_workspace_bytes(int B, int N, int M) {
+size_t f_workspace_bytes(int B, int N, int M, int unit_run) {
   FGeometry g;
-  if (f_geometry(B, N, M, &g, nullptr)) return 0;
+  if (f_geometry(B, N, M, unit_run, &g, nullptr)) return 0;
   return f_carve(g, nullptr).bytes;
 }
 
-static int f_setup(int B, int N, int M, void* workspace, size_t workspace_bytes, FGeometry* g, FWorkspace* w) {
+static int f_setup(int B, int N, int M, int unit_run, void* workspace, size_t workspace_bytes, FGeometry* g,
+                   FWorkspace* w) {
   if (!workspace || !f_sizes_ok(B, N, M)) return RMA_E_BADARG;
-  if (int e = f_geometry(B, N, M, g, nullptr)) return e;
+  if (int e = f_geometry(B, N, M, unit_run, g, nullptr)) return e;
   if (((uintptr_t)workspace & 255u) != 0) return RMA_E_WORKSPACE;
   *w = f_carve(*g, workspace);
   if (workspace_bytes < w->bytes) return RMA_E_WORKSPACE;
@@ -907,12 +912,12 @@ static int f_setup(int B, int N, int M, void* workspace, size_t workspace_bytes,
 }
 
 int f_launch_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
-                  const float* y, int64_t ysb, int64_t ysn, int64_t ysc, int B, int N, int M,
+                  const float* y, int64_t ysb, int64_t ysn, int64_t ysc, int B, int N, int M, int unit_run,
                   void* workspace, size_t workspace_bytes, float* zero_loss, float4* zero_gx, float4* zero_gy,
                   void* stream_) {
   if (!x || !y) return RMA_E_BADARG;
   FGeometry g; FWorkspace w;
-  if (int e = f_setup(B, N, M, workspace, workspace_bytes, &g, &w)) return e;
+  if (int e = f_setup(B, N, M, unit_run, workspace, workspace_bytes, &g, &w)) return e;
   const long long slots = (long long)B * (g.Npad + g.Mp);
   RMA_CUDA_TRY(launch_dep(pdl_site(1), chamfer_fprep_kernel, (unsigned)grid_for(slots, 256), 256u, 0, (cudaStream_t)stream_,
                           x, (long long)xsb, (long long)xsn, (long long)xsc, y, (long long)ysb, (long long)ysn,
@@ -920,11 +925,11 @@ int f_launch_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
   return RMA_OK;
 }
 
-int f_search_config(int B, int N, int M, int* ctas, int* threads, int* splits, int* ctas_per_sm) {
+int f_search_config(int B, int N, int M, int unit_run, int* ctas, int* threads, int* splits, int* ctas_per_sm) {
   if (!f_sizes_ok(B, N, M)) return RMA_E_BADARG;
   FGeometry g;
   int occ = 0;
-  if (int e = f_geometry(B, N, M, &g, &occ)) return e;
+  if (int e = f_geometry(B, N, M, unit_run, &g, &occ)) return e;
   if (ctas) *ctas = (int)((g.units() + g.U - 1) / g.U);
   if (threads) *threads = kFThreads;
   if (splits) *splits = g.U;          // for this path: 64-column tiles per CTA
@@ -932,9 +937,9 @@ int f_search_config(int B, int N, int M, int* ctas, int* threads, int* splits, i
   return RMA_OK;
 }
 
-int f_launch_search(int B, int N, int M, void* workspace, size_t workspace_bytes, void* stream_) {
+int f_launch_search(int B, int N, int M, int unit_run, void* workspace, size_t workspace_bytes, void* stream_) {
   FGeometry g; FWorkspace w;
-  if (int e = f_setup(B, N, M, workspace, workspace_bytes, &g, &w)) return e;
+  if (int e = f_setup(B, N, M, unit_run, workspace, workspace_bytes, &g, &w)) return e;
   FSearchArgs a;
   a.rowsoa = w.rowsoa; a.colpair = w.colpair; a.rowtop = w.rowtop; a.colrec = w.colrec;
   a.N = N; a.M = M; a.nRB = g.nRB; a.Npad = g.Npad; a.nRBC = g.nRBC; a.nT = g.nT; a.Mp = g.Mp;
@@ -946,10 +951,10 @@ int f_launch_search(int B, int N, int M, void* workspace, size_t workspace_bytes
   return RMA_OK;
 }
 
-int f_launch_resolve(int B, int N, int M, const FinalizeArgs& f, void* workspace, size_t workspace_bytes,
-                     void* stream_) {
+int f_launch_resolve(int B, int N, int M, int unit_run, const FinalizeArgs& f, void* workspace,
+                     size_t workspace_bytes, void* stream_) {
   FGeometry g; FWorkspace w;
-  if (int e = f_setup(B, N, M, workspace, workspace_bytes, &g, &w)) return e;
+  if (int e = f_setup(B, N, M, unit_run, workspace, workspace_bytes, &g, &w)) return e;
   const long long warps = ((long long)B * N + 31) / 32 + ((long long)B * M + 31) / 32;
   int sms = 0, occ = 0;
   if (int e = f_caps(&sms, &occ)) return e;
@@ -961,9 +966,9 @@ int f_launch_resolve(int B, int N, int M, const FinalizeArgs& f, void* workspace
   return RMA_OK;
 }
 
-int f_read_stats(void* workspace, int B, int N, int M, unsigned* out4_host, void* stream_) {
+int f_read_stats(void* workspace, int B, int N, int M, int unit_run, unsigned* out4_host, void* stream_) {
   FGeometry g;
-  if (int e = f_geometry(B, N, M, &g, nullptr)) return e;
+  if (int e = f_geometry(B, N, M, unit_run, &g, nullptr)) return e;
   FWorkspace w = f_carve(g, workspace);
   RMA_CUDA_TRY(cudaMemcpyAsync(out4_host, w.stats, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost,
                                (cudaStream_t)stream_));

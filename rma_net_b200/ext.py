@@ -8,7 +8,9 @@ PyTorch is used for memory and streams only; there is no CPU path.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
+import threading
 from typing import Optional, Tuple
 
 import torch
@@ -45,8 +47,42 @@ def _same_device(*ts: torch.Tensor) -> None:
 # ------------------------------------------------------------------------------------------------------------
 # chamfer
 # ------------------------------------------------------------------------------------------------------------
+# `rma_chamfer_opts` is a per-call argument of the C ABI (the library keeps no state).  On the Python side the
+# options of the enclosing `chamfer_options(...)` block (thread-local) are passed with every call; outside such a
+# block NULL is passed = the library's defaults.
+_tls = threading.local()
+_PATHS = {None: _lib.PATH_AUTO, "auto": _lib.PATH_AUTO, "exact": _lib.PATH_EXACT, "filter": _lib.PATH_FILTER,
+          0: _lib.PATH_AUTO, 1: _lib.PATH_EXACT, 2: _lib.PATH_FILTER}
+
+
+def _opts():
+    o = getattr(_tls, "opts", None)
+    return ctypes.byref(o) if o is not None else None
+
+
+@contextlib.contextmanager
+def chamfer_options(path=None, unit_run: int = 0, record_cap_bytes: int = 0):
+    """Run the chamfer calls of this block (and this thread) with explicit options: path "auto" | "exact" | "filter"
+    (both give identical results; parity tests and A/B timing force one), unit_run (tiles per search CTA) and the
+    record cap of the automatic choice.  Backward passes of ops created inside the block do not depend on it."""
+    prev = getattr(_tls, "opts", None)
+    _tls.opts = _lib.ChamferOpts(_PATHS[path], int(unit_run), int(record_cap_bytes))
+    try:
+        yield
+    finally:
+        _tls.opts = prev
+
+
 def chamfer_workspace_bytes(B: int, N: int, M: int) -> int:
-    return int(_lib.load().rma_chamfer_workspace_bytes(B, N, M))
+    return int(_lib.load().rma_chamfer_workspace_bytes(B, N, M, _opts()))
+
+
+def chamfer_path(B: int, N: int, M: int) -> str:
+    """Which search implementation (B,N,M) runs under the current options: "filter" or "exact"."""
+    rc = _lib.load().rma_chamfer_path(B, N, M, _opts())
+    if rc < 0:
+        raise RuntimeError(f"problem size not supported: B={B}, N={N}, M={M}")
+    return "filter" if rc == _lib.PATH_FILTER else "exact"
 
 
 def chamfer_forward(points_x: torch.Tensor, points_y: torch.Tensor, want_idx: bool = True):
@@ -61,7 +97,7 @@ def chamfer_forward(points_x: torch.Tensor, points_y: torch.Tensor, want_idx: bo
         raise RuntimeError("chamfer_dist needs non-empty point sets (min over an empty dimension)")
     lib = _lib.load()
     with torch.cuda.device(points_x.device):
-        wsb = lib.rma_chamfer_workspace_bytes(B, N, M)
+        wsb = lib.rma_chamfer_workspace_bytes(B, N, M, _opts())
         if wsb == 0:
             raise RuntimeError(f"problem size not supported: B={B}, N={N}, M={M}")
         dev = points_x.device
@@ -73,7 +109,7 @@ def chamfer_forward(points_x: torch.Tensor, points_y: torch.Tensor, want_idx: bo
         xs, ys = points_x.stride(), points_y.stride()
         rc = lib.rma_chamfer_forward(_ptr(points_x), xs[0], xs[1], xs[2], _ptr(points_y), ys[0], ys[1], ys[2],
                                      B, N, M, _ptr(dist1), _ptr(dist2), _ptr(idx1), _ptr(idx2),
-                                     _ptr(ws), wsb, _stream())
+                                     _ptr(ws), wsb, _opts(), _stream())
         _lib.check(rc, "rma_chamfer_forward")
     return dist1, dist2, idx1, idx2
 
@@ -119,7 +155,7 @@ def chamfer_cd_forward(points_x: torch.Tensor, points_y: torch.Tensor, need_x: b
     lib = _lib.load()
     dev = points_x.device
     with torch.cuda.device(dev):
-        wsb = lib.rma_chamfer_workspace_bytes(B, N, M)
+        wsb = lib.rma_chamfer_workspace_bytes(B, N, M, _opts())
         if wsb == 0:
             raise RuntimeError(f"problem size not supported: B={B}, N={N}, M={M}")
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
@@ -139,7 +175,7 @@ def chamfer_cd_forward(points_x: torch.Tensor, points_y: torch.Tensor, need_x: b
                                         _ptr(loss), _ptr(d1), _ptr(d2), None, None,
                                         _ptr(gx[0] if gx else None), _ptr(gx[1] if gx else None),
                                         _ptr(gy[0] if gy else None), _ptr(gy[1] if gy else None),
-                                        _ptr(ws), wsb, _stream())
+                                        _ptr(ws), wsb, _opts(), _stream())
         _lib.check(rc, "rma_chamfer_cd_forward_weighted")
     if want_dist:
         return loss, gx, gy, d1, d2

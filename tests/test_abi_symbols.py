@@ -33,20 +33,30 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in rma_b200.h but not exported"
 
 
+def test_library_exports_nothing_but_the_header():
+    """No experiment hooks (`rma_exp_*`) or other undeclared entry points in the product build: every choice the
+    library makes is a function of the call's arguments (`rma_chamfer_opts`), it keeps no state between calls."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted({l.split()[-1] for l in out.splitlines() if " T " in l and l.split()[-1].startswith("rma_")})
+    assert exported == _declared()
+    assert not [n for n in exported if n.startswith("rma_exp")]
+
+
 def test_ctypes_table_matches_header():
     assert sorted(_lib.SIGNATURES) == _declared()
     lib = _lib.load()
-    assert lib.rma_b200_abi_version() == 1
+    assert lib.rma_b200_abi_version() == 2
     assert b"workspace" in lib.rma_b200_error_string(-2)
 
 
 def test_workspace_bytes_is_host_only_and_monotone():
     lib = _lib.load()
-    a = lib.rma_chamfer_workspace_bytes(16, 4096, 4096)
-    b = lib.rma_chamfer_workspace_bytes(16, 8192, 8192)
+    a = lib.rma_chamfer_workspace_bytes(16, 4096, 4096, None)
+    b = lib.rma_chamfer_workspace_bytes(16, 8192, 8192, None)
     assert 0 < a < b and a % 256 == 0
-    assert lib.rma_chamfer_workspace_bytes(0, 10, 10) == 0
-    assert lib.rma_chamfer_workspace_bytes(1, 1 << 20, 1 << 20) > 0
+    assert lib.rma_chamfer_workspace_bytes(0, 10, 10, None) == 0
+    assert lib.rma_chamfer_workspace_bytes(1, 1 << 20, 1 << 20, None) > 0
 
 
 def test_no_cpu_fallback():

@@ -27,11 +27,9 @@ def chamfer_path(request):
     import torch as _t
     if not _t.cuda.is_available():
         pytest.skip("no CUDA device")
-    from rma_net_b200 import _lib
-    lib = _lib.load()
-    lib.rma_exp_set_chamfer_path(2 if request.param == "filter" else 1, 0)
-    yield request.param
-    lib.rma_exp_set_chamfer_path(0, 0)
+    from rma_net_b200 import ext
+    with ext.chamfer_options(path=request.param):      # per-call option of the C ABI (rma_chamfer_opts), no library state
+        yield request.param
 
 CASES = sorted(os.path.basename(p)[8:-4] for p in glob.glob(
     os.path.join(os.path.dirname(__file__), "golden", "chamfer_*.npz")))
@@ -327,10 +325,8 @@ def test_baseline_sizes_bit_exact_and_properties(cuda, cfg):
 
 def _path_stats(B, N, M):
     """(runs_filter_path, [extra row candidates, extra column candidates, row-block rescans]) of the last call."""
-    import ctypes
-    from rma_net_b200 import _lib
-    lib = _lib.load()
-    return lib.rma_exp_chamfer_path_info(B, N, M, None, None, None)
+    from rma_net_b200 import ext
+    return 1 if ext.chamfer_path(B, N, M) == "filter" else 0
 
 
 @pytest.mark.parametrize("case", ["offset", "all_equal", "duplicates", "tiny", "huge", "planar_grid", "two_clusters"])
@@ -374,20 +370,16 @@ def test_filter_guard_adversarial(cuda, case, chamfer_path):
 
 def test_paths_agree_and_auto_dispatch(cuda):
     """The automatic choice (filter below the record cap, exact above) is invisible in the results."""
-    from rma_net_b200 import _lib
+    from rma_net_b200 import ext
     from rma_net_b200.model.loss import chamfer_dist_with_idx
-    lib = _lib.load()
     g = torch.Generator().manual_seed(77)
     x = (torch.rand(3, 2500, 3, generator=g) * 2 - 1).to(cuda)
     y = (torch.rand(3, 1900, 3, generator=g) * 2 - 1).to(cuda)
     outs = []
-    try:
-        for path, cap in ((2, 0), (1, 0), (0, 1 << 30), (0, 1)):     # cap = 1 byte forces the exact path in auto mode
-            lib.rma_exp_set_chamfer_path(path, cap)
-            assert lib.rma_exp_chamfer_path_info(3, 2500, 1900, None, None, None) == (0 if path == 1 or cap == 1 else 1)
+    for path, cap in ((2, 0), (1, 0), (0, 1 << 30), (0, 1)):         # cap = 1 byte forces the exact path in auto mode
+        with ext.chamfer_options(path=path, record_cap_bytes=cap):
+            assert ext.chamfer_path(3, 2500, 1900) == ("exact" if path == 1 or cap == 1 else "filter")
             outs.append([t.cpu() for t in chamfer_dist_with_idx(x, y)])
-    finally:
-        lib.rma_exp_set_chamfer_path(0, 4 << 30)                    # back to the default cap
     for o in outs[1:]:
         for a, b_ in zip(outs[0], o):
             assert torch.equal(a, b_)
@@ -420,9 +412,8 @@ def test_filter_path_fuzz_against_exact_path(cuda):
     (1e-6 .. 1e6), offsets of up to 1000 cloud diameters, anisotropy, clusters, lattices (many exactly equal
     distances), duplicated points and ragged sizes must reproduce the exact difference-form search bit for bit
     (distances AND indices; the exact path itself is pinned to the fp32 C oracle by the tests above)."""
-    from rma_net_b200 import _lib
+    from rma_net_b200 import ext
     from rma_net_b200.model.loss import chamfer_dist_with_idx
-    lib = _lib.load()
     rng = np.random.default_rng(20260101)
     kinds = ["uniform", "normal", "offset", "aniso", "clusters", "lattice", "dups", "surface"]
     try:
@@ -460,12 +451,12 @@ def test_filter_path_fuzz_against_exact_path(cuda):
             xt, yt = torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda)
             outs = []
             for path in (2, 1):
-                lib.rma_exp_set_chamfer_path(path, 0)
-                outs.append([t.cpu() for t in chamfer_dist_with_idx(xt, yt)])
+                with ext.chamfer_options(path=path):
+                    outs.append([t.cpu() for t in chamfer_dist_with_idx(xt, yt)])
             for a, b_ in zip(*outs):
                 assert torch.equal(a, b_), (trial, kind, B, N, M, scale)
     finally:
-        lib.rma_exp_set_chamfer_path(0, 0)
+        pass
 
 
 @pytest.mark.parametrize("kind", ["uniform", "lattice", "dups", "all_equal"])
@@ -474,9 +465,8 @@ def test_filter_long_unit_runs_and_slow_path(cuda, kind):
     partially filled and empty entries, runs that cross row blocks and batch elements.  Tie-heavy clouds (lattice,
     duplicated points, one repeated point) send most items through the slow path, which re-evaluates whole candidate
     entries; the result must still equal the exact path's bit for bit (distances and indices)."""
-    from rma_net_b200 import _lib
+    from rma_net_b200 import ext
     from rma_net_b200.model.loss import chamfer_dist_with_idx
-    lib = _lib.load()
     rng = np.random.default_rng(7)
     B, N, M = 2, 3000, 5003                                      # nT = 79 tiles, 2 CTA row blocks per batch element
 
@@ -492,18 +482,13 @@ def test_filter_long_unit_runs_and_slow_path(cuda, kind):
             p = np.tile(np.array([0.3, -0.2, 0.9]), (B, n, 1))
         return p.astype(np.float32)
     xt, yt = torch.from_numpy(cloud(N)).to(cuda), torch.from_numpy(cloud(M)).to(cuda)
-    try:
-        lib.rma_exp_set_chamfer_path(1, 0)
+    with ext.chamfer_options(path="exact"):
         ref = [t.cpu() for t in chamfer_dist_with_idx(xt, yt)]
-        lib.rma_exp_set_chamfer_path(2, 0)
-        for run in (1, 15, 16, 17, 33, 79, 100, 200):
-            lib.rma_exp_set_search_debug(None, run, 0)
+    for run in (1, 15, 16, 17, 33, 79, 100, 200):
+        with ext.chamfer_options(path="filter", unit_run=run):
             out = [t.cpu() for t in chamfer_dist_with_idx(xt, yt)]
-            for a, b_ in zip(out, ref):
-                assert torch.equal(a, b_), (kind, run)
-    finally:
-        lib.rma_exp_set_search_debug(None, 0, 0)
-        lib.rma_exp_set_chamfer_path(0, 0)
+        for a, b_ in zip(out, ref):
+            assert torch.equal(a, b_), (kind, run)
 
 
 def test_nan_point_does_not_corrupt_anything(cuda, chamfer_path):
@@ -533,9 +518,8 @@ def test_filter_equals_exact_at_large_sizes(cuda, shape, kind):
     """Sizes at which a search CTA's run (chosen automatically) spans several row-direction entries and the resolve reads
     dozens of entries per row; the lattice cloud (41^3 positions, many duplicates) sends a large share of the items through
     the slow path.  Filter path == exact path bit for bit (tools/parity_large.py runs the longer list)."""
-    from rma_net_b200 import _lib
+    from rma_net_b200 import ext
     from rma_net_b200.model.loss import chamfer_dist_with_idx
-    lib = _lib.load()
     B, N, M = shape
     rng = np.random.default_rng(11)
 
@@ -547,11 +531,8 @@ def test_filter_equals_exact_at_large_sizes(cuda, shape, kind):
         return torch.from_numpy(p.astype(np.float32)).to(cuda)
     x, y = cloud(N), cloud(M)
     outs = []
-    try:
-        for path in (2, 1):
-            lib.rma_exp_set_chamfer_path(path, 0)
+    for path in (2, 1):
+        with ext.chamfer_options(path=path):
             outs.append([t.cpu() for t in chamfer_dist_with_idx(x, y)])
-    finally:
-        lib.rma_exp_set_chamfer_path(0, 0)
     for a, b_ in zip(*outs):
         assert torch.equal(a, b_)

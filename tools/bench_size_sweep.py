@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from rma_net_b200 import _lib  # noqa: E402
+from rma_net_b200 import _lib, ext  # noqa: E402
 from rma_net_b200.model.loss import loss_on_cd  # noqa: E402
 
 PEAK_FMA = 148 * 128 * 1.965e9
@@ -38,13 +38,14 @@ for (B, N) in ((64, 1024), (16, 2048), (16, 4096), (16, 8192), (4, 16384), (1, 6
     pairs = B * N * N
     row = {"B": B, "N=M": N, "pairs": pairs}
     for name, path in (("filter", 2), ("exact", 1)):
-        lib.rma_exp_set_chamfer_path(path, 0)
-        wsb = lib.rma_chamfer_workspace_bytes(B, N, N)
+      with ext.chamfer_options(path=path):
+        o = ctypes.byref(_lib.ChamferOpts(path, 0, 0))
+        wsb = lib.rma_chamfer_workspace_bytes(B, N, N, o)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         xs, ys = x.stride(), y.stride()
-        lib.rma_chamfer_prep(P(x), *xs, P(y), *ys, B, N, N, P(ws), wsb, st)
-        t = timed(lambda: lib.rma_chamfer_search(B, N, N, P(ws), wsb, st), 20)
+        lib.rma_chamfer_prep(P(x), *xs, P(y), *ys, B, N, N, P(ws), wsb, o, st)
+        t = timed(lambda: lib.rma_chamfer_search(B, N, N, P(ws), wsb, o, st), 20)
         row[f"{name}_search_us"] = round(t * 1e6, 1)
         row[f"{name}_search_frac_fp32_peak"] = round(6 * pairs / t / PEAK_FMA, 3)
 
@@ -65,5 +66,4 @@ for (B, N) in ((64, 1024), (16, 2048), (16, 4096), (16, 8192), (4, 16384), (1, 6
         row[f"{name}_fwd_bwd_us"] = round(t * 1e6, 1)
         row[f"{name}_fwd_bwd_frac_fp32_peak"] = round(6 * pairs / t / PEAK_FMA, 3)
         row[f"{name}_workspace_MiB"] = round(wsb / 2 ** 20, 1)
-    lib.rma_exp_set_chamfer_path(0, 0)
     print(json.dumps(row), flush=True)

@@ -41,22 +41,20 @@ def main():
     xd, yd = x.to(dev), y.to(dev)
     res = {}
     for name in which:
-        lib = ctypes.CDLL(build_variant(name, VARIANTS[name]))
-        for fn, (rt, at) in list(_lib.SIGNATURES.items()) + list(_lib.EXPERIMENT_SIGNATURES.items()):
-            f = getattr(lib, fn); f.restype = rt; f.argtypes = at
+        lib = _lib.bind(ctypes.CDLL(build_variant(name, VARIANTS[name])))
         P = lambda t: ctypes.c_void_p(t.data_ptr())
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         xs, ys = xd.stride(), yd.stride()
         for run in (0, 7, 14):
-            lib.rma_exp_set_search_debug(None, run, 0)
-            wsb = lib.rma_chamfer_workspace_bytes(B, N, M)
+            o = ctypes.byref(_lib.ChamferOpts(0, run, 0))
+            wsb = lib.rma_chamfer_workspace_bytes(B, N, M, o)
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             times = []
             for it in range(14):
-                lib.rma_chamfer_prep(P(xd), xs[0], xs[1], xs[2], P(yd), ys[0], ys[1], ys[2], B, N, M, P(ws), wsb, st)
+                lib.rma_chamfer_prep(P(xd), xs[0], xs[1], xs[2], P(yd), ys[0], ys[1], ys[2], B, N, M, P(ws), wsb, o, st)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                rc = lib.rma_chamfer_search(B, N, M, P(ws), wsb, st)
+                rc = lib.rma_chamfer_search(B, N, M, P(ws), wsb, o, st)
                 e1.record()
                 torch.cuda.synchronize()
                 assert rc == 0, rc
@@ -65,7 +63,6 @@ def main():
             key = f"{name}/U={run or 'auto'}"
             res[key] = {"us_min": round(min(times), 2), "us_med": round(sorted(times)[len(times) // 2], 2)}
             print(key, json.dumps(res[key]), flush=True)
-        lib.rma_exp_set_search_debug(None, 0, 0)
     with open(os.path.join(ROOT, "gpurun_out", f"fsearch_variants_{wl}.json"), "w") as f:
         json.dump(res, f, indent=1)
 

@@ -22,7 +22,7 @@ def main():
     xd, yd = x.to(dev), y.to(dev)
     lib = _lib.load()
     P = lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr())
-    wsb = lib.rma_chamfer_workspace_bytes(B, N, M)
+    wsb = lib.rma_chamfer_workspace_bytes(B, N, M, None)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     gx = torch.empty(B, N, 3, device=dev); gy = torch.empty(B, M, 3, device=dev)
     sx = torch.empty(B, N, 4, device=dev); sy = torch.empty(B, M, 4, device=dev)
@@ -36,14 +36,14 @@ def main():
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def k_prep():
-        assert lib.rma_chamfer_prep(P(xd), *xs, P(yd), *ys, B, N, M, P(ws), wsb, st()) == 0
+        assert lib.rma_chamfer_prep(P(xd), *xs, P(yd), *ys, B, N, M, P(ws), wsb, None, st()) == 0
 
     def k_search():
-        assert lib.rma_chamfer_search(B, N, M, P(ws), wsb, st()) == 0
+        assert lib.rma_chamfer_search(B, N, M, P(ws), wsb, None, st()) == 0
 
     def k_fwd():
         assert lib.rma_chamfer_cd_forward(P(xd), *xs, P(yd), *ys, B, N, M, P(loss), None, None, None, None,
-                                          P(gx), P(sx), P(gy), P(sy), P(ws), wsb, st()) == 0
+                                          P(gx), P(sx), P(gy), P(sy), P(ws), wsb, None, st()) == 0
 
     def k_bwd():
         assert lib.rma_chamfer_cd_backward(P(gx), P(sx), B * N, P(gy), P(sy), B * M, P(one), P(ox), P(oy), st()) == 0

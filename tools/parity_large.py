@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from rma_net_b200 import _lib  # noqa: E402
+from rma_net_b200 import _lib, ext  # noqa: E402
 from rma_net_b200.model.loss import chamfer_dist_with_idx  # noqa: E402
 
 lib = _lib.load()
@@ -28,9 +28,8 @@ for (B, N, M) in [(16, 8192, 8192), (4, 16384, 12000), (1, 65536, 65536), (2, 30
         x, y = cloud(N), cloud(M)
         outs = []
         for path in (2, 1):
-            lib.rma_exp_set_chamfer_path(path, 0)
-            outs.append(chamfer_dist_with_idx(x, y))
-        lib.rma_exp_set_chamfer_path(0, 0)
+            with ext.chamfer_options(path=path):
+                outs.append(chamfer_dist_with_idx(x, y))
         same = all(torch.equal(a, b) for a, b in zip(*outs))
         print(B, N, M, kind, "identical" if same else "MISMATCH", flush=True)
         ok &= same

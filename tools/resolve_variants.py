@@ -16,9 +16,9 @@ from rma_net_b200 import _lib, build as b  # noqa: E402
 
 VARIANTS = {
     "base": [],
-    "noslow": ["-DRMA_EXP_NO_SLOW"],
-    "noslow_rows": ["-DRMA_EXP_NO_SLOW_ROWS"],
-    "noslow_cols": ["-DRMA_EXP_NO_SLOW_COLS"],
+    "noslow": ["-DRMA_B200_EXPERIMENTS", "-DRMA_EXP_NO_SLOW"],
+    "noslow_rows": ["-DRMA_B200_EXPERIMENTS", "-DRMA_EXP_NO_SLOW_ROWS"],
+    "noslow_cols": ["-DRMA_B200_EXPERIMENTS", "-DRMA_EXP_NO_SLOW_COLS"],
 }
 
 
@@ -52,25 +52,23 @@ def main():
     xd, yd = x.to(dev), y.to(dev)
     res = {}
     for name in which:
-        lib = ctypes.CDLL(build_variant(name, VARIANTS[name]))
-        for fn, (rt, at) in list(_lib.SIGNATURES.items()) + list(_lib.EXPERIMENT_SIGNATURES.items()):
-            f = getattr(lib, fn); f.restype = rt; f.argtypes = at
+        lib = _lib.bind(ctypes.CDLL(build_variant(name, VARIANTS[name])))
         P = lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr())
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         xs, ys = xd.stride(), yd.stride()
-        wsb = lib.rma_chamfer_workspace_bytes(B, N, M)
+        wsb = lib.rma_chamfer_workspace_bytes(B, N, M, None)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         gx = torch.empty(B, N, 3, device=dev); gy = torch.empty(B, M, 3, device=dev)
         sx = torch.empty(B, N, 4, device=dev); sy = torch.empty(B, M, 4, device=dev)
         loss = torch.empty((), device=dev)
 
         def ps():
-            assert lib.rma_chamfer_prep(P(xd), *xs, P(yd), *ys, B, N, M, P(ws), wsb, st) == 0
-            assert lib.rma_chamfer_search(B, N, M, P(ws), wsb, st) == 0
+            assert lib.rma_chamfer_prep(P(xd), *xs, P(yd), *ys, B, N, M, P(ws), wsb, None, st) == 0
+            assert lib.rma_chamfer_search(B, N, M, P(ws), wsb, None, st) == 0
 
         def full():
             assert lib.rma_chamfer_cd_forward(P(xd), *xs, P(yd), *ys, B, N, M, P(loss), None, None, None, None,
-                                              P(gx), P(sx), P(gy), P(sy), P(ws), wsb, st) == 0
+                                              P(gx), P(sx), P(gy), P(sy), P(ws), wsb, None, st) == 0
 
         a = med(ps); f = med(full)
         res[name] = {"prep_search_us": [round(v, 2) for v in a], "cd_forward_us": [round(v, 2) for v in f],

@@ -22,7 +22,7 @@ def main():
     lib = _lib.load()
     P = lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr())
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    wsb = lib.rma_chamfer_workspace_bytes(B, N, M)
+    wsb = lib.rma_chamfer_workspace_bytes(B, N, M, None)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     d1 = torch.empty(B, N, device=dev); d2 = torch.empty(B, M, device=dev)
     i1 = torch.empty(B, N, dtype=torch.int32, device=dev); i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
@@ -34,13 +34,13 @@ def main():
     sx = torch.empty(B, N, 4, device=dev); sy = torch.empty(B, M, 4, device=dev)
     xs, ys = xd.stride(), yd.stride()
     stages = {
-        "prep": lambda: lib.rma_chamfer_prep(P(xd), *xs, P(yd), *ys, B, N, M, P(ws), wsb, st),
-        "search": lambda: lib.rma_chamfer_search(B, N, M, P(ws), wsb, st),
-        "finalize": lambda: lib.rma_chamfer_finalize(B, N, M, P(d1), P(d2), P(i1), P(i2), P(ws), wsb, st),
+        "prep": lambda: lib.rma_chamfer_prep(P(xd), *xs, P(yd), *ys, B, N, M, P(ws), wsb, None, st),
+        "search": lambda: lib.rma_chamfer_search(B, N, M, P(ws), wsb, None, st),
+        "finalize": lambda: lib.rma_chamfer_finalize(B, N, M, P(d1), P(d2), P(i1), P(i2), P(ws), wsb, None, st),
         "backward_generic(memset+scatter)": lambda: lib.rma_chamfer_backward(
             P(xd), *xs, P(yd), *ys, B, N, M, P(g1), P(g2), P(i1), P(i2), P(gx), P(gy), st),
         "cd_forward(fused prep+search+finalize+loss+grads)": lambda: lib.rma_chamfer_cd_forward(
-            P(xd), *xs, P(yd), *ys, B, N, M, P(loss), None, None, None, None, P(gx), P(sx), P(gy), P(sy), P(ws), wsb, st),
+            P(xd), *xs, P(yd), *ys, B, N, M, P(loss), None, None, None, None, P(gx), P(sx), P(gy), P(sy), P(ws), wsb, None, st),
         "cd_backward": lambda: lib.rma_chamfer_cd_backward(P(gx), P(sx), B * N, P(gy), P(sy), B * M, P(one), P(ox), P(oy), st),
     }
     res = {}
