@@ -49,6 +49,11 @@ WORKLOADS = {
     "C2": (16, 4096, 4096, 0, "uniform"),
     "C3": (16, 8192, 8192, 2, "uniform"),
     "C4": (512, 2048, 2048, 3, "uniform"),
+    # small clouds (tools/ only): the size sweep's small rows and the reference's own training shape, T=7 stages x B=4
+    # stacked into one batch (train_sample.py:15-30)
+    "S16x2048": (16, 2048, 2048, 5, "uniform"),
+    "S64x1024": (64, 1024, 1024, 6, "uniform"),
+    "S28x2048": (28, 2048, 2048, 7, "uniform"),
 }
 FLOP_PER_PAIR = 12.0        # 6 FMA: two NN searches x 3 multiply-adds
 METRIC = "chamfer fwd+bwd G point-pairs/s at B=16,N=M=4096; % of FP32 FMA peak"
@@ -813,7 +818,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C2", choices=sorted(k for k in WORKLOADS if k.startswith("C")))
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C3 / C4 / C5 legs of the `secondary` object")

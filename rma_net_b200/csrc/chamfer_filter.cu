@@ -34,21 +34,36 @@ namespace rma {
 
 constexpr int kFRowsPerThread = 16;
 constexpr int kFRowsPerWarp = 32 * kFRowsPerThread;     // 512: one row block
-constexpr int kFWarps = 4;
-constexpr int kFThreads = 32 * kFWarps;
-constexpr int kFRowsPerCta = kFRowsPerWarp * kFWarps;   // 2048
+constexpr int kFWarps = 4;                              // warps per search CTA for clouds of more than 1024 rows: a CTA row
+                                                        // block is 2048 rows.  Smaller clouds run 2- or 1-warp CTAs
+                                                        // (template parameter kW; 1024 / 512 rows per CTA row block), so
+                                                        // that no warp of a CTA is left without rows (64 x 1024 ran at
+                                                        // 33 % of peak with two of four warps idle)
+constexpr int kFThreads = 32 * kFWarps;                 // threads of the largest search CTA (reporting)
+static inline int f_warps_for(int nRB) { return nRB >= 3 ? 4 : nRB; }   // 512-row blocks per batch element -> kW
 constexpr int kFColTile = 32;                           // columns per column-direction tile (= lanes)
 constexpr int kFColTop = 2;                             // packed group minima recorded per column and row block
-constexpr int kFRowTile = 64;                           // columns per row-direction tile minimum
-constexpr int kFSubTiles = 16;                          // tiles per row-direction entry (sub-segment): bounds the
-                                                        // slow path's re-evaluation to 1024 columns per candidate
+constexpr int kFRowTile = 64;                           // columns per work unit (CTA row block x 64 columns)
+// Columns per row-direction tile minimum ("sub-tile", template parameter kSub of the search and the resolve): what the
+// resolve re-evaluates per row.  32 instead of 64 cuts the resolve by a quarter (C2: 13.5 -> 10.3 us, C4: 160 -> 129 us,
+// 16 x 2048: 10.1 -> 7.6 us) for twice the 16-row epilogues in the search (+2-3 %: C2 +1.4 us, C4 +10 us): a net gain
+// while the resolve (linear in N + M) weighs enough against the search (N * M), i.e. for small clouds.
+constexpr int kFSubSmall = 32, kFSubLarge = 64;
+#ifndef RMA_F_SUBSWITCH
+#define RMA_F_SUBSWITCH 4096
+#endif
+constexpr int kFSubSwitch = RMA_F_SUBSWITCH;            // min(N, M) <= this: 32-column sub-tiles (tools/ build A/B variants)
+static inline int f_sub_for(int N, int M) { return (N < M ? N : M) <= kFSubSwitch ? kFSubSmall : kFSubLarge; }
+constexpr int kFSubTiles = 16;                          // 64-column tiles per row-direction entry (sub-segment): bounds
+                                                        // the slow path's re-evaluation to 1024 columns per candidate
 #ifndef RMA_F_CHUNK
 #define RMA_F_CHUNK 1024
 #endif
 #ifndef RMA_F_MINCTAS
 #define RMA_F_MINCTAS 2
 #endif
-constexpr int kFChunk = RMA_F_CHUNK;                     // columns staged in shared memory at a time
+constexpr int kFChunk = RMA_F_CHUNK;                     // columns staged in shared memory at a time by a 4-warp CTA
+                                                         // (kW warps: kFChunk * kW / 4, the same bytes per SM)
 constexpr int kFCbStride = 36;
 constexpr float kFBig = 1e30f;                          // |x|^2 of padded rows / |y|^2 of padded columns
 constexpr float kEps = 5.9604644775390625e-8f;          // 2^-24
@@ -57,7 +72,9 @@ struct FGeometry {
   int B, N, M;
   int nRB;    // 512-row blocks per batch element
   int Npad;   // nRB * 512
-  int nRBC;   // CTA row blocks (2048 rows) per batch element
+  int W;      // warps per search CTA (4, or 2 / 1 for clouds of <= 1024 / 512 rows)
+  int RC;     // rows per CTA row block: 512 * W
+  int nRBC;   // CTA row blocks (RC rows) per batch element
   int nT;     // 64-column tiles per batch element
   int Mp;     // nT * 64
   int U;      // work units (CTA row block x 64-column tile) per search CTA
@@ -89,7 +106,9 @@ static FGeometry f_make_geometry(int B, int N, int M, int slots, int force_run) 
   g.B = B; g.N = N; g.M = M;
   g.nRB = (N + kFRowsPerWarp - 1) / kFRowsPerWarp;
   g.Npad = g.nRB * kFRowsPerWarp;
-  g.nRBC = (g.nRB + kFWarps - 1) / kFWarps;
+  g.W = f_warps_for(g.nRB);
+  g.RC = g.W * kFRowsPerWarp;
+  g.nRBC = (g.nRB + g.W - 1) / g.W;
   g.nT = (M + kFRowTile - 1) / kFRowTile;
   g.Mp = g.nT * kFRowTile;
   g.U = force_run > 0 ? force_run : f_choose_unit_run(g.units(), g.nT, slots);
@@ -106,8 +125,8 @@ struct FWorkspace {
   float4* colpair;   // [B][Mp/2][2]            the same, two columns (c, c+1) interleaved as (q0c, q0c', q1c, q1c')
                      //                         (q2c, q2c', wc, wc'): the search's fp32x2 operands as they are read from
                      //                         shared memory, so a chunk is one contiguous TMA bulk copy
-  float* rowtop;     // [B*nRBC][Smax*P][3][2048] per segment and run of <= 16 tiles in it ("entry"): smallest tile
-                     //                         minimum, its tile, second smallest; unused entries of a segment (inf, 0, inf)
+  float* rowtop;     // [B*nRBC][Smax*P][3][RC] per segment and run of <= 16 tiles in it ("entry"): smallest sub-tile
+                     //                         minimum, its sub-tile, second smallest; unused entries of a segment (inf, 0, inf)
   float* colrec;     // [B][nRB][2][Mp]         two smallest packed group minima of g over the row block
   unsigned* stats;   // [4] rows on the slow path, columns on the slow path, row-block rescans, unused
   size_t bytes;
@@ -121,7 +140,7 @@ static FWorkspace f_carve(const FGeometry& g, void* base) {
   w.rowsoa = (float4*)(p + off);  off += align256((size_t)g.B * g.Npad * sizeof(float4));
   w.colpack = (float4*)(p + off); off += align256((size_t)g.B * g.Mp * sizeof(float4));
   w.colpair = (float4*)(p + off); off += align256((size_t)g.B * g.Mp * sizeof(float4));
-  w.rowtop = (float*)(p + off);   off += align256((size_t)g.B * g.nRBC * g.Smax * g.P * 3 * kFRowsPerCta * sizeof(float));
+  w.rowtop = (float*)(p + off);   off += align256((size_t)g.B * g.nRBC * g.Smax * g.P * 3 * g.RC * sizeof(float));
   w.colrec = (float*)(p + off);   off += align256((size_t)g.B * g.nRB * kFColTop * g.Mp * sizeof(float));
   w.stats = (unsigned*)(p + off); off += 256;
   w.bytes = off;
@@ -198,10 +217,11 @@ __device__ __forceinline__ void top2_insert(float& p1, float& p2, float v) {
 }
 
 // dynamic shared memory: column double buffer, per-warp transpose buffers, per-row running top entries, two mbarriers
-constexpr size_t kFSearchSmemBase =
-    (size_t)2 * (kFChunk + 4) * sizeof(float4) + (size_t)kFWarps * 2 * kFColTile * kFCbStride * sizeof(float);
-constexpr size_t kFSearchSmemTop = kFSearchSmemBase + (size_t)3 * 4 * kFThreads * sizeof(float4);
-constexpr size_t kFSearchSmem = kFSearchSmemTop + 16;
+__host__ __device__ constexpr size_t f_smem_base(int kW) {
+  return (size_t)2 * (kFChunk * kW / 4 + 4) * sizeof(float4) + (size_t)kW * 2 * kFColTile * kFCbStride * sizeof(float);
+}
+__host__ __device__ constexpr size_t f_smem_top(int kW) { return f_smem_base(kW) + (size_t)3 * 4 * (32 * kW) * sizeof(float4); }
+__host__ __device__ constexpr size_t f_smem(int kW) { return f_smem_top(kW) + 16; }
 
 struct FSearchArgs {
   const float4* rowsoa;
@@ -212,14 +232,18 @@ struct FSearchArgs {
   long long units;
 };
 
-__global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kernel(FSearchArgs a) {
+template <int kSub, int kW>
+__global__ void __launch_bounds__(32 * kW, RMA_F_MINCTAS * 4 / kW) chamfer_fsearch_kernel(FSearchArgs a) {
+  static_assert(kSub == kFRowTile || kSub == kFColTile, "row sub-tile is one or two 32-column passes");
+  static_assert(kW == 1 || kW == 2 || kW == 4, "1, 2 or 4 warps per search CTA");
+  constexpr int kThreads = 32 * kW, kRowsPerCta = kFRowsPerWarp * kW, kChunk = kFChunk * kW / 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* scol = reinterpret_cast<float4*>(smem_raw);                                              // [2][kFChunk + 4]
-  float* cball = reinterpret_cast<float*>(smem_raw + (size_t)2 * (kFChunk + 4) * sizeof(float4));   // [warps][2][32][36]
-  u64* mbar = reinterpret_cast<u64*>(smem_raw + kFSearchSmemTop);                                  // [2]
+  float4* scol = reinterpret_cast<float4*>(smem_raw);                                              // [2][kChunk + 4]
+  float* cball = reinterpret_cast<float*>(smem_raw + (size_t)2 * (kChunk + 4) * sizeof(float4));    // [warps][2][32][36]
+  u64* mbar = reinterpret_cast<u64*>(smem_raw + f_smem_top(kW));                                   // [2]
   // per-row running (smallest tile minimum, its tile, second smallest): touched once per 64-column tile, so it lives
   // in shared memory ([plane][q][thread] float4, conflict-free) instead of 48 registers
-  float4* stop = reinterpret_cast<float4*>(smem_raw + kFSearchSmemBase) + threadIdx.x;            // [3][4][kFThreads]
+  float4* stop = reinterpret_cast<float4*>(smem_raw + f_smem_base(kW)) + threadIdx.x;             // [3][4][kThreads]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* cb = cball + warp * (2 * kFColTile * kFCbStride);
@@ -244,7 +268,7 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
     const int ntile = (int)min((long long)(a.nT - tile0), unit_end - unit);
     unit += ntile;
     const int b = brb / a.nRBC, rbc = brb - b * a.nRBC;
-    const int rb = rbc * kFWarps + warp;
+    const int rb = rbc * kW + warp;
     const bool has_rows = rb < a.nRB;   // warp-uniform
     const int seg = blockIdx.x - (int)(((long long)brb * a.nT) / a.U);   // which of the row block's segments
     const int c0 = tile0 * kFRowTile;
@@ -254,7 +278,7 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
     // the segment's first chunk is in flight while the rows are loaded, chunk k+1 while chunk k is computed.  Both
     // buffers are free here: every chunk iteration ends with a __syncthreads.
     const float4* cp = a.colpair + ((size_t)b * a.Mp + c0);
-    if (tid == 0) bulk_load(scol + cur * (kFChunk + 4), cp, (unsigned)min(kFChunk, ncols) * 16u, &mbar[cur]);
+    if (tid == 0) bulk_load(scol + cur * (kChunk + 4), cp, (unsigned)min(kChunk, ncols) * 16u, &mbar[cur]);
 
     u64 px[8], py[8], pz[8], pu[8];
     if (has_rows) {
@@ -270,24 +294,24 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
     }
     // The running (smallest, its tile, second smallest) goes to the segment's next entry every kFSubTiles tiles and at
     // the segment's end, and starts again empty; entries the segment does not fill are written empty.
-    float* top = a.rowtop + ((size_t)(brb * a.Smax + seg) * a.P * 3) * kFRowsPerCta + warp * kFRowsPerWarp +
+    float* top = a.rowtop + ((size_t)(brb * a.Smax + seg) * a.P * 3) * kRowsPerCta + warp * kFRowsPerWarp +
                  lane * kFRowsPerThread;
     int sub_tiles = 0, sub = 0;
     auto reset_top = [&]() {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        stop[q * kFThreads] = make_float4(inf, inf, inf, inf);
-        stop[(4 + q) * kFThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
-        stop[(8 + q) * kFThreads] = make_float4(inf, inf, inf, inf);
+        stop[q * kThreads] = make_float4(inf, inf, inf, inf);
+        stop[(4 + q) * kThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
+        stop[(8 + q) * kThreads] = make_float4(inf, inf, inf, inf);
       }
     };
     auto flush_top = [&]() {
-      float* o = top + (size_t)sub * (3 * kFRowsPerCta);
+      float* o = top + (size_t)sub * (3 * kRowsPerCta);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        reinterpret_cast<float4*>(o)[q] = stop[q * kFThreads];
-        reinterpret_cast<float4*>(o + kFRowsPerCta)[q] = stop[(4 + q) * kFThreads];          // tile ids (int bits)
-        reinterpret_cast<float4*>(o + 2 * kFRowsPerCta)[q] = stop[(8 + q) * kFThreads];
+        reinterpret_cast<float4*>(o)[q] = stop[q * kThreads];
+        reinterpret_cast<float4*>(o + kRowsPerCta)[q] = stop[(4 + q) * kThreads];          // tile ids (int bits)
+        reinterpret_cast<float4*>(o + 2 * kRowsPerCta)[q] = stop[(8 + q) * kThreads];
       }
       ++sub;
       sub_tiles = 0;
@@ -302,26 +326,27 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
     int pend_col = -1;   // column offset (relative to c0) of the tile whose reduce is pending; warp-uniform
     int parity = 0;
 
-    for (int cs = 0; cs < ncols; cs += kFChunk) {
-      const int nc = min(kFChunk, ncols - cs);
+    for (int cs = 0; cs < ncols; cs += kChunk) {
+      const int nc = min(kChunk, ncols - cs);
       // two columns (c, c+1) lie interleaved as (q0c, q0c', q1c, q1c') (q2c, q2c', wc, wc'): an LDS.128 delivers two
       // ready-made fp32x2 operands of the column pair
-      if (tid == 0 && cs + kFChunk < ncols)
-        bulk_load(scol + (cur ^ 1) * (kFChunk + 4), cp + cs + kFChunk,
-                  (unsigned)min(kFChunk, ncols - cs - kFChunk) * 16u, &mbar[cur ^ 1]);
+      if (tid == 0 && cs + kChunk < ncols)
+        bulk_load(scol + (cur ^ 1) * (kChunk + 4), cp + cs + kChunk,
+                  (unsigned)min(kChunk, ncols - cs - kChunk) * 16u, &mbar[cur ^ 1]);
       mbar_wait(&mbar[cur], (phases >> cur) & 1u);
       phases ^= 1u << cur;
-      const float4* schunk = scol + cur * (kFChunk + 4);
+      const float4* schunk = scol + cur * (kChunk + 4);
       cur ^= 1;
 
 #pragma unroll 1
       for (int t0 = 0; has_rows && t0 < nc; t0 += kFRowTile) {
         float tm[kFRowsPerThread];
-#pragma unroll
-        for (int r = 0; r < kFRowsPerThread; ++r) tm[r] = inf;
-
 #pragma unroll 1
         for (int h = 0; h < kFRowTile; h += kFColTile) {
+          if (kSub == kFColTile || h == 0) {
+#pragma unroll
+            for (int r = 0; r < kFRowsPerThread; ++r) tm[r] = inf;
+          }
           const float4* sp = schunk + t0 + h;
           float* cbw = cb + parity * (kFColTile * kFCbStride) + lane;
           const float4* cbr = reinterpret_cast<const float4*>(cb + (parity ^ 1) * (kFColTile * kFCbStride) +
@@ -402,24 +427,26 @@ __global__ void __launch_bounds__(kFThreads, RMA_F_MINCTAS) chamfer_fsearch_kern
           pend_col = cs + t0 + h;
           parity ^= 1;
           __syncwarp();   // this tile's partial minima visible to all lanes; previous buffer free for reuse
-        }
 
-        // Row direction: the tile's 16 filter minima are folded into the running (smallest, its tile, second
-        // smallest) of the segment.  (A per-tile record in global memory - B*N*M/16 bytes, read only when a guard fails -
-        // cost 2.8 us of the 83 us C2 step in stores that evict dirty L2 lines; the slow path re-evaluates the
-        // candidate SEGMENTS instead.)
-        const int tile = tile0 + (cs + t0) / kFRowTile;
-        const float tilef = __int_as_float(tile);
+          // Row direction: the sub-tile's 16 filter minima are folded into the running (smallest, its sub-tile, second
+          // smallest) of the segment.  (A per-tile record in global memory - B*N*M/16 bytes, read only when a guard
+          // fails - cost 2.8 us of the 83 us C2 step in stores that evict dirty L2 lines; the slow path re-evaluates
+          // the candidate SEGMENTS instead.)
+          if (kSub == kFColTile || h + kFColTile == kFRowTile) {
+            const int tile = tile0 * (kFRowTile / kSub) + (cs + t0 + h) / kSub;
+            const float tilef = __int_as_float(tile);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float4 m1 = stop[q * kFThreads], t1 = stop[(4 + q) * kFThreads], m2 = stop[(8 + q) * kFThreads];
-          m2.x = fminf(m2.x, fmaxf(m1.x, tm[4 * q]));     t1.x = tm[4 * q] < m1.x ? tilef : t1.x;
-          m2.y = fminf(m2.y, fmaxf(m1.y, tm[4 * q + 1])); t1.y = tm[4 * q + 1] < m1.y ? tilef : t1.y;
-          m2.z = fminf(m2.z, fmaxf(m1.z, tm[4 * q + 2])); t1.z = tm[4 * q + 2] < m1.z ? tilef : t1.z;
-          m2.w = fminf(m2.w, fmaxf(m1.w, tm[4 * q + 3])); t1.w = tm[4 * q + 3] < m1.w ? tilef : t1.w;
-          m1.x = fminf(m1.x, tm[4 * q]); m1.y = fminf(m1.y, tm[4 * q + 1]);
-          m1.z = fminf(m1.z, tm[4 * q + 2]); m1.w = fminf(m1.w, tm[4 * q + 3]);
-          stop[q * kFThreads] = m1; stop[(4 + q) * kFThreads] = t1; stop[(8 + q) * kFThreads] = m2;
+            for (int q = 0; q < 4; ++q) {
+              float4 m1 = stop[q * kThreads], t1 = stop[(4 + q) * kThreads], m2 = stop[(8 + q) * kThreads];
+              m2.x = fminf(m2.x, fmaxf(m1.x, tm[4 * q]));     t1.x = tm[4 * q] < m1.x ? tilef : t1.x;
+              m2.y = fminf(m2.y, fmaxf(m1.y, tm[4 * q + 1])); t1.y = tm[4 * q + 1] < m1.y ? tilef : t1.y;
+              m2.z = fminf(m2.z, fmaxf(m1.z, tm[4 * q + 2])); t1.z = tm[4 * q + 2] < m1.z ? tilef : t1.z;
+              m2.w = fminf(m2.w, fmaxf(m1.w, tm[4 * q + 3])); t1.w = tm[4 * q + 3] < m1.w ? tilef : t1.w;
+              m1.x = fminf(m1.x, tm[4 * q]); m1.y = fminf(m1.y, tm[4 * q + 1]);
+              m1.z = fminf(m1.z, tm[4 * q + 2]); m1.w = fminf(m1.w, tm[4 * q + 3]);
+              stop[q * kThreads] = m1; stop[(4 + q) * kThreads] = t1; stop[(8 + q) * kThreads] = m2;
+            }
+          }
         }
         if (++sub_tiles == kFSubTiles) flush_top();
       }
@@ -473,10 +500,11 @@ __device__ __forceinline__ float sqdist_q(float x, float y, float z, const float
   return d;
 }
 
-// (distance bits, index) lexicographic minimum over the 8 lanes of an aligned lane group.
-__device__ __forceinline__ void group8_min(unsigned& d, unsigned& idx) {
+// (distance bits, index) lexicographic minimum over the kLanes lanes of an aligned lane group.
+template <int kLanes>
+__device__ __forceinline__ void group_min(unsigned& d, unsigned& idx) {
 #pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
+  for (int o = 1; o < kLanes; o <<= 1) {
     const unsigned od = __shfl_xor_sync(0xffffffffu, d, o);
     const unsigned oi = __shfl_xor_sync(0xffffffffu, idx, o);
     const bool take = od < d || (od == d && oi < idx);
@@ -485,20 +513,22 @@ __device__ __forceinline__ void group8_min(unsigned& d, unsigned& idx) {
   }
 }
 
-// Result of one fast-path round for owner lane (round*4 + k): the (distance, index) minimum of 8-lane group k.
-// Usually exactly one lane of a group holds a survivor, then a ballot finds it and two SHFL fetch it; otherwise the
-// 3-step butterfly runs.  Warp-uniform control flow.
+// Result of one fast-path round for owner lane (round * kItems + k): the (distance, index) minimum of lane group k
+// (kLanes lanes per item, kItems = 32 / kLanes items per round).  Usually exactly one lane of a group holds a
+// survivor, then a ballot finds it and two SHFL fetch it; otherwise the butterfly runs.  Warp-uniform control flow.
+template <int kLanes>
 __device__ __forceinline__ void round_result(unsigned d, unsigned idx, unsigned& rd, unsigned& ri) {
+  constexpr unsigned kItems = 32u / kLanes, gmask = (1u << kLanes) - 1u;
   const unsigned full = 0xffffffffu, lane = lane_id();
   const unsigned hit = __ballot_sync(full, d != 0xffffffffu);
-  const unsigned gb = (hit >> (lane & 24u)) & 0xffu;                 // my own group's survivors
-  if (__all_sync(full, (gb & (gb - 1u)) == 0u)) {                    // every group has at most one
-    const unsigned k = lane & 3u, gk = (hit >> (k * 8u)) & 0xffu;
-    const int src = (int)(k * 8u) + (gk ? __ffs(gk) - 1 : 0);
+  const unsigned gb = (hit >> (lane & ~(unsigned)(kLanes - 1))) & gmask;   // my own group's survivors
+  if (__all_sync(full, (gb & (gb - 1u)) == 0u)) {                            // every group has at most one
+    const unsigned k = lane % kItems, gk = (hit >> (k * kLanes)) & gmask;
+    const int src = (int)(k * kLanes) + (gk ? __ffs(gk) - 1 : 0);
     rd = __shfl_sync(full, d, src); ri = __shfl_sync(full, idx, src);
   } else {
-    group8_min(d, idx);
-    rd = __shfl_sync(full, d, (lane & 3) * 8); ri = __shfl_sync(full, idx, (lane & 3) * 8);
+    group_min<kLanes>(d, idx);
+    rd = __shfl_sync(full, d, (lane % kItems) * kLanes); ri = __shfl_sync(full, idx, (lane % kItems) * kLanes);
   }
 }
 
@@ -507,7 +537,13 @@ __device__ __forceinline__ void round_result(unsigned d, unsigned idx, unsigned&
 // SMs x 4 resident CTAs, so every SM carries the same load wherever the block scheduler (or an early programmatic
 // launch behind the search's tail) places the CTAs: with one CTA per 8 items, 512 CTAs on 148 SMs leave some SMs with
 // 4 x 8 items against an average of 27.7.
+//
+// Lanes per item in the fast path: kSub / 8 lanes re-evaluate one row's candidate sub-tile (8 columns each) or one
+// column's candidate group of 16 rows; a round handles kItems = 32 / kLanes items.
+template <int kSub>
 __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGeometry g, FWorkspace w, FinalizeArgs f) {
+  constexpr int kLanes = kSub / 8, kItems = 32 / kLanes, kRounds = 32 / kItems;
+  constexpr int kGroupRows = kFRowsPerThread / kLanes;      // rows of a 16-row group per lane
   __shared__ double lsum[kFinWarps];
   // per-warp staging of the 32 items' broadcast data: a round reads its 4 items with two LDS.128 (one address per
   // 8-lane group, conflict-free) instead of seven SHFL
@@ -518,7 +554,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
   const unsigned nrow = (unsigned)g.B * (unsigned)g.N, ncol = (unsigned)g.B * (unsigned)g.M;
   const unsigned row_warps = (nrow + 31u) / 32u;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
-  const int grp = lane >> 3, sub = lane & 7;
+  const int grp = lane / kLanes, sub = lane % kLanes;
   const unsigned total_warps = row_warps + (ncol + 31u) / 32u;
   const unsigned w_begin = (unsigned)(((u64)blockIdx.x * total_warps) / gridDim.x);
   const unsigned w_end = (unsigned)(((u64)(blockIdx.x + 1) * total_warps) / gridDim.x);
@@ -543,10 +579,10 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
     if (valid) {
       b = (int)(t / (unsigned)g.N); i = (int)(t - (unsigned)b * (unsigned)g.N);
       rp = w.rowpack[(size_t)b * g.Npad + i];
-      const int rbc = i / kFRowsPerCta, brb = b * g.nRBC + rbc;
+      const int rbc = i / g.RC, brb = b * g.nRBC + rbc;
       const int kfirst = (int)(((unsigned)brb * (unsigned)g.nT) / (unsigned)g.U);
       const int klast = (int)((((unsigned)brb + 1u) * (unsigned)g.nT - 1u) / (unsigned)g.U);
-      const float* top = w.rowtop + ((size_t)brb * g.Smax * g.P * 3) * kFRowsPerCta + (i - rbc * kFRowsPerCta);
+      const float* top = w.rowtop + ((size_t)brb * g.Smax * g.P * 3) * g.RC + (i - rbc * g.RC);
       const int nseg = (klast - kfirst + 1) * g.P;  // entries: P per segment, consecutive
       constexpr int kSegBatch = 12;                 // up to 12 entries in flight: one latency for C2 (10)
       for (int s0 = 0; s0 < nseg; s0 += kSegBatch) {
@@ -555,10 +591,10 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
 #pragma unroll
         for (int k = 0; k < kSegBatch; ++k) {
           const bool on = s0 + k < nseg;
-          const float* tp = top + (size_t)(on ? s0 + k : s0) * (3 * kFRowsPerCta);
+          const float* tp = top + (size_t)(on ? s0 + k : s0) * (3 * g.RC);
           a1[k] = on ? tp[0] : inf;
-          at[k] = __float_as_int(tp[kFRowsPerCta]);
-          a2[k] = on ? tp[2 * kFRowsPerCta] : inf;
+          at[k] = __float_as_int(tp[g.RC]);
+          a2[k] = on ? tp[2 * g.RC] : inf;
         }
 #pragma unroll
         for (int k = 0; k < kSegBatch; ++k) {
@@ -575,38 +611,43 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
 #endif
     unsigned best_d = 0xffffffffu, best_j = 0;
 
-    // Fast path (one candidate tile): 8 lanes per row, 8 columns per lane, 4 rows per round.  Inside the tile the
-    // same guard applies per COLUMN: every exact minimiser has f_j <= thr, so each column is first re-filtered with
-    // the search's own 3-FFMA chain (bit-identical f; padded columns carry |y|^2 = 1e30 and never pass) and only the
-    // survivors - typically one per row - are evaluated in the exact difference form.
+    // Fast path (one candidate sub-tile of kSub columns): kLanes lanes per row, 8 columns per lane, kItems rows per
+    // round.  Inside the sub-tile the same guard applies per COLUMN: every exact minimiser has f_j <= thr, so each
+    // column is first re-filtered with the search's own 3-FFMA chain (bit-identical f; padded columns carry
+    // |y|^2 = 1e30 and never pass) and only the survivors - typically one per row - are evaluated in the exact
+    // difference form; the pass bits are collected branch-free and the exact evaluations sit under one branch.
     sA[warp][lane] = make_float4(rp.x, rp.y, rp.z, thr);
     sB[warp][lane] = make_int4(b, T1, fast ? 1 : 0, 0);
     __syncwarp();
 #pragma unroll 1
-    for (int round = 0; round < 8; ++round) {
-      const int src = round * 4 + grp;
+    for (int round = 0; round < kRounds; ++round) {
+      const int src = round * kItems + grp;
       const float4 sa = sA[warp][src];
       const int4 sb4 = sB[warp][src];
       const float x = sa.x, y = sa.y, z = sa.z, sthr = sa.w;
       unsigned d = 0xffffffffu, dj = 0xffffffffu;
       if (sb4.z) {
-        const int j0 = sb4.y * kFRowTile + sub;
+        const int j0 = sb4.y * kSub + sub;
         const float4* cq = w.colpack + (size_t)sb4.x * g.Mp + j0;
         float4 q[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) q[c] = cq[8 * c];
+        for (int c = 0; c < 8; ++c) q[c] = cq[kLanes * c];
+        unsigned pass = 0u;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float fj = __fmaf_rn(x, q[c].x, __fmaf_rn(y, q[c].y, __fmaf_rn(z, q[c].z, q[c].w)));
-          if (fj <= sthr) {
-            const unsigned dc = __float_as_uint(sqdist_q(x, y, z, q[c]));
-            if (dc < d) { d = dc; dj = (unsigned)(j0 + 8 * c); }   // ascending columns: strict '<' keeps the first
-          }
+          pass |= fj <= sthr ? 1u << c : 0u;
+        }
+        while (pass) {                                     // ascending columns: strict '<' keeps the first
+          const int c = __ffs(pass) - 1;
+          pass &= pass - 1u;
+          const unsigned dc = __float_as_uint(sqdist_q(x, y, z, cq[kLanes * c]));
+          if (dc < d) { d = dc; dj = (unsigned)(j0 + kLanes * c); }
         }
       }
       unsigned rd, rj;
-      round_result(d, dj, rd, rj);
-      if ((lane >> 2) == round) { best_d = rd; best_j = rj; }
+      round_result<kLanes>(d, dj, rd, rj);
+      if (lane / kItems == round) { best_d = rd; best_j = rj; }
     }
 
     // Slow path (guard failed: several tiles within the rounding error of the smallest).  Every candidate tile lies in
@@ -620,25 +661,25 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       const int sb = __shfl_sync(full, b, src), si = __shfl_sync(full, i, src);
       const float sthr = __shfl_sync(full, thr, src);
       const float x = __shfl_sync(full, rp.x, src), y = __shfl_sync(full, rp.y, src), z = __shfl_sync(full, rp.z, src);
-      const int srbc = si / kFRowsPerCta;
+      const int srbc = si / g.RC;
       const unsigned sbrb = (unsigned)(sb * g.nRBC + srbc);
       const unsigned u0 = sbrb * (unsigned)g.nT, u1 = u0 + (unsigned)g.nT;       // the row block's units [u0, u1)
       const unsigned kfirst = u0 / (unsigned)g.U, klast = (u1 - 1u) / (unsigned)g.U;
-      const float* top = w.rowtop + ((size_t)sbrb * g.Smax * g.P * 3) * kFRowsPerCta + (si - srbc * kFRowsPerCta);
+      const float* top = w.rowtop + ((size_t)sbrb * g.Smax * g.P * 3) * g.RC + (si - srbc * g.RC);
       const float4* cq = w.colpack + (size_t)sb * g.Mp;
       unsigned bd = 0xffffffffu, bj = 0xffffffffu;
-      // One tile for this lane's 8-lane group: the fast path's re-filter (f_j <= thr, bit-identical to the search's
+      // One sub-tile for this lane's group: the fast path's re-filter (f_j <= thr, bit-identical to the search's
       // chain; padded columns never pass) in front of the exact evaluation, 8 loads in flight per lane.
       auto eval_tile = [&](unsigned tile) {
-        const int j0 = (int)tile * kFRowTile + sub;
+        const int j0 = (int)tile * kSub + sub;
         float4 q[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) q[c] = cq[j0 + 8 * c];
+        for (int c = 0; c < 8; ++c) q[c] = cq[j0 + kLanes * c];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float fj = __fmaf_rn(x, q[c].x, __fmaf_rn(y, q[c].y, __fmaf_rn(z, q[c].z, q[c].w)));
           if (fj <= sthr) {
-            const unsigned d = __float_as_uint(sqdist_q(x, y, z, q[c])), jc = (unsigned)(j0 + 8 * c);
+            const unsigned d = __float_as_uint(sqdist_q(x, y, z, q[c])), jc = (unsigned)(j0 + kLanes * c);
             if (d < bd || (d == bd && jc < bj)) { bd = d; bj = jc; }
           }
         }
@@ -647,30 +688,31 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       for (unsigned base = 0; base < nent; base += 32u) {
         // one entry per lane, all in flight; empty entries hold inf
         const unsigned e = base + (unsigned)lane;
-        const float* tp = top + (size_t)(e < nent ? e : base) * (3 * kFRowsPerCta);
+        const float* tp = top + (size_t)(e < nent ? e : base) * (3 * g.RC);
         const float a1 = e < nent ? tp[0] : inf;
-        const unsigned t1 = (unsigned)__float_as_int(tp[kFRowsPerCta]);
-        const float a2 = e < nent ? tp[2 * kFRowsPerCta] : inf;
+        const unsigned t1 = (unsigned)__float_as_int(tp[g.RC]);
+        const float a2 = e < nent ? tp[2 * g.RC] : inf;
         const bool hit = a1 <= sthr;
         // An entry whose SECOND smallest tile minimum is above the threshold has one candidate tile, the recorded one:
         // the usual case (two near-tied tiles in two entries) then costs a single round.
         const unsigned singles = __ballot_sync(full, hit && !(a2 <= sthr));
         unsigned wholes = __ballot_sync(full, hit && a2 <= sthr);
         const int nsingle = __popc(singles);
-        for (int r = 0; r < nsingle; r += 4) {            // four tiles per round, one per 8-lane group
+        for (int r = 0; r < nsingle; r += kItems) {       // kItems sub-tiles per round, one per lane group
           const int idx = r + grp;
           const unsigned from = idx < nsingle ? __fns(singles, 0, idx + 1) : 0u;
           const unsigned tile = __shfl_sync(full, t1, (int)from);
           if (idx < nsingle) eval_tile(tile);
         }
-        while (wholes) {                                  // every tile of the entry
+        while (wholes) {                                  // every sub-tile of the entry
           const unsigned he = base + (unsigned)__ffs(wholes) - 1u; wholes &= wholes - 1u;
           const unsigned k = kfirst + he / (unsigned)g.P, pe = he % (unsigned)g.P;
           const unsigned ua = max(k * (unsigned)g.U, u0), ub = min((k + 1u) * (unsigned)g.U, u1);   // the segment's units
-          const unsigned ta = ua - u0 + pe * kFSubTiles;              // first tile of the entry, within the row block
+          const unsigned ta = ua - u0 + pe * kFSubTiles;              // first 64-column tile of the entry, within the row block
           const unsigned tb = min(ta + kFSubTiles, ub - u0);          // the entry's tiles [ta, tb)
-          for (unsigned tr = ta; tr < tb; tr += 4u)
-            if (tr + (unsigned)grp < tb) eval_tile(tr + (unsigned)grp);
+          constexpr unsigned kPer = kFRowTile / kSub;                  // sub-tiles per tile
+          for (unsigned tr = ta * kPer; tr < tb * kPer; tr += (unsigned)kItems)
+            if (tr + (unsigned)grp < tb * kPer) eval_tile(tr + (unsigned)grp);
         }
       }
       const unsigned mn = __reduce_min_sync(full, bd);
@@ -736,34 +778,43 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
     const int G1 = (R1 * 32 + (int)(__float_as_uint(M1) & 31u)) * kFRowsPerThread;   // first row of the candidate group
     unsigned best_d = 0xffffffffu, best_i = 0;
 
-    // Fast path (one candidate group of 16 rows): 8 lanes per column, 2 rows per lane, 4 columns per round.
+    // Fast path (one candidate group of 16 rows): kLanes lanes per column, kGroupRows rows per lane, kItems columns per
+    // round.  As for the rows: inside the candidate group the guard applies per ROW (g_i = fl(f + |x_i|^2) <= thr for
+    // every exact minimiser; padded rows carry |x|^2 = 1e30), so the 16 rows are re-filtered with the search's chain
+    // and only the survivors are evaluated exactly.
     sA[warp][lane] = make_float4(cq.x, cq.y, cq.z, cq.w);
     sB[warp][lane] = make_int4(b, G1, fast ? 1 : 0, __float_as_int(thr));
     __syncwarp();
-    // As for the rows: inside the candidate group the guard applies per ROW (g_i = fl(f + |x_i|^2) <= thr for every
-    // exact minimiser; padded rows carry |x|^2 = 1e30), so the 16 rows are re-filtered with the search's chain and
-    // only the survivors are evaluated exactly.
-#pragma unroll 2
-    for (int round = 0; round < 8; ++round) {
-      const int src = round * 4 + grp;
+#pragma unroll 1
+    for (int round = 0; round < kRounds; ++round) {
+      const int src = round * kItems + grp;
       const float4 q = sA[warp][src];
       const int4 sb4 = sB[warp][src];
       const float sthr = __int_as_float(sb4.w);
       unsigned d = 0xffffffffu, di = 0xffffffffu;
       if (sb4.z) {
         const int r0 = sb4.y + sub;
-        const float4 pa = w.rowpack[(size_t)sb4.x * g.Npad + r0], pb = w.rowpack[(size_t)sb4.x * g.Npad + r0 + 8];
-        const float ga = __fadd_rn(__fmaf_rn(pa.x, q.x, __fmaf_rn(pa.y, q.y, __fmaf_rn(pa.z, q.z, q.w))), pa.w);
-        const float gb = __fadd_rn(__fmaf_rn(pb.x, q.x, __fmaf_rn(pb.y, q.y, __fmaf_rn(pb.z, q.z, q.w))), pb.w);
-        if (ga <= sthr) { d = __float_as_uint(sqdist_q(pa.x, pa.y, pa.z, q)); di = (unsigned)r0; }
-        if (gb <= sthr) {
-          const unsigned d1 = __float_as_uint(sqdist_q(pb.x, pb.y, pb.z, q));
-          if (d1 < d) { d = d1; di = (unsigned)(r0 + 8); }
+        const float4* rq = w.rowpack + (size_t)sb4.x * g.Npad + r0;
+        float4 pr[kGroupRows];
+#pragma unroll
+        for (int k = 0; k < kGroupRows; ++k) pr[k] = rq[kLanes * k];
+        unsigned pass = 0u;
+#pragma unroll
+        for (int k = 0; k < kGroupRows; ++k) {
+          const float gk = __fadd_rn(__fmaf_rn(pr[k].x, q.x, __fmaf_rn(pr[k].y, q.y, __fmaf_rn(pr[k].z, q.z, q.w))), pr[k].w);
+          pass |= gk <= sthr ? 1u << k : 0u;
+        }
+        while (pass) {                                     // ascending rows: strict '<' keeps the first
+          const int k = __ffs(pass) - 1;
+          pass &= pass - 1u;
+          const float4 pk = rq[kLanes * k];
+          const unsigned dk = __float_as_uint(sqdist_q(pk.x, pk.y, pk.z, q));
+          if (dk < d) { d = dk; di = (unsigned)(r0 + kLanes * k); }
         }
       }
       unsigned rd, ri;
-      round_result(d, di, rd, ri);
-      if ((lane >> 2) == round) { best_d = rd; best_i = ri; }
+      round_result<kLanes>(d, di, rd, ri);
+      if (lane / kItems == round) { best_d = rd; best_i = ri; }
     }
 
     // Slow path: every row block's smallest entry within the guard is a candidate group; a second-smallest entry
@@ -876,9 +927,18 @@ static int f_caps(int* sms, int* occ) {
     if (m) { *sms = (int)(m >> 8); *occ = (int)(m & 0xffu); return 0; }
   }
   RMA_CUDA_TRY(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
-  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)kFSearchSmem));
-  RMA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, chamfer_fsearch_kernel, kFThreads, kFSearchSmem));
+  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<kFSubLarge, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)f_smem(4)));
+  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<kFSubSmall, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)f_smem(4)));
+  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<kFSubSmall, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)f_smem(2)));
+  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<kFSubSmall, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)f_smem(1)));
+  // occupancy of the 4-warp CTA; the 2- and 1-warp CTAs use half / a quarter of its registers and shared memory and
+  // are launch-bounded to 2x / 4x as many resident CTAs (the same warps per SM)
+  RMA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, chamfer_fsearch_kernel<kFSubLarge, 4>, kFThreads,
+                                                             f_smem(4)));
   if (*occ < 1) *occ = 1;
   if (*occ > 255) *occ = 255;
   if (dev >= 0 && dev < 64) memo[dev].store(((unsigned)*sms << 8) | (unsigned)*occ, std::memory_order_release);
@@ -890,6 +950,8 @@ static int f_caps(int* sms, int* occ) {
 static int f_geometry(int B, int N, int M, int unit_run, FGeometry* g, int* occ_out) {
   int sms = 0, occ = 0;
   if (int e = f_caps(&sms, &occ)) return e;
+  const int W = f_warps_for((N + kFRowsPerWarp - 1) / kFRowsPerWarp);
+  occ *= kFWarps / W;                       // resident CTAs per SM for this CTA shape
   *g = f_make_geometry(B, N, M, sms * occ, unit_run);
   if (occ_out) *occ_out = occ;
   return 0;
@@ -931,7 +993,7 @@ int f_search_config(int B, int N, int M, int unit_run, int* ctas, int* threads, 
   int occ = 0;
   if (int e = f_geometry(B, N, M, unit_run, &g, &occ)) return e;
   if (ctas) *ctas = (int)((g.units() + g.U - 1) / g.U);
-  if (threads) *threads = kFThreads;
+  if (threads) *threads = 32 * g.W;
   if (splits) *splits = g.U;          // for this path: 64-column tiles per CTA
   if (ctas_per_sm) *ctas_per_sm = occ;
   return RMA_OK;
@@ -946,8 +1008,17 @@ int f_launch_search(int B, int N, int M, int unit_run, void* workspace, size_t w
   a.U = g.U; a.Smax = g.Smax; a.P = g.P; a.units = g.units();
   const long long ctas = (a.units + g.U - 1) / g.U;
   if (ctas > 0x7fffffffLL) return RMA_E_BADARG;
-  RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel, (unsigned)ctas, (unsigned)kFThreads, kFSearchSmem,
-                          (cudaStream_t)stream_, a));
+  const bool small = f_sub_for(N, M) == kFSubSmall;
+  cudaStream_t st = (cudaStream_t)stream_;
+  // clouds of <= 1024 rows always take 32-column sub-tiles (f_sub_for: min(N, M) <= 4096)
+  if (g.W == 4 && !small)
+    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<kFSubLarge, 4>, (unsigned)ctas, 128u, f_smem(4), st, a));
+  else if (g.W == 4)
+    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<kFSubSmall, 4>, (unsigned)ctas, 128u, f_smem(4), st, a));
+  else if (g.W == 2)
+    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<kFSubSmall, 2>, (unsigned)ctas, 64u, f_smem(2), st, a));
+  else
+    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<kFSubSmall, 1>, (unsigned)ctas, 32u, f_smem(1), st, a));
   return RMA_OK;
 }
 
@@ -961,8 +1032,12 @@ int f_launch_resolve(int B, int N, int M, int unit_run, const FinalizeArgs& f, v
   long long grid = grid_for(warps, kFinWarps);            // one CTA per 8 items when that is more than one wave
   const long long wave = (long long)sms * 4;              // resident resolve CTAs (launch bounds: 4 per SM)
   if (grid <= wave) grid = warps < wave ? warps : wave;   // single wave: the same number of CTAs on every SM
-  RMA_CUDA_TRY(launch_dep(pdl_site(4), chamfer_fresolve_kernel, (unsigned)grid, (unsigned)(kFinWarps * 32), 0,
-                          (cudaStream_t)stream_, g, w, f));
+  if (f_sub_for(N, M) == kFSubSmall)
+    RMA_CUDA_TRY(launch_dep(pdl_site(4), chamfer_fresolve_kernel<kFSubSmall>, (unsigned)grid,
+                            (unsigned)(kFinWarps * 32), 0, (cudaStream_t)stream_, g, w, f));
+  else
+    RMA_CUDA_TRY(launch_dep(pdl_site(4), chamfer_fresolve_kernel<kFSubLarge>, (unsigned)grid,
+                            (unsigned)(kFinWarps * 32), 0, (cudaStream_t)stream_, g, w, f));
   return RMA_OK;
 }
 
