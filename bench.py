@@ -55,6 +55,8 @@ WORKLOADS = {
     "S64x1024": (64, 1024, 1024, 6, "uniform"),
     "S28x2048": (28, 2048, 2048, 7, "uniform"),
 }
+GATE_CYCLES = 40_000_000    # ~20 ms at 1.9 GHz: see the headline leg in run_ours
+L2_BYTES = 126 << 20        # B200 L2 (guides/B200_PROFILING.md)
 FLOP_PER_PAIR = 12.0        # 6 FMA: two NN searches x 3 multiply-adds
 METRIC = "chamfer fwd+bwd G point-pairs/s at B=16,N=M=4096; % of FP32 FMA peak"
 UNIT = "G point-pairs/s"
@@ -413,7 +415,6 @@ def run_ours(args):
     x_pin, y_pin = x_host.pin_memory(), y_host.pin_memory()
     xd = x_host.to(dev).requires_grad_(True)
     yd = y_host.to(dev).requires_grad_(True)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def step():
         xd.grad = None
@@ -442,16 +443,76 @@ def run_ours(args):
     else:
         run = step
 
-    for _ in range(max(args.warmup, 3)):
+    # ---- headline leg: K steps back to back over ROTATING input sets larger than L2 ----------------------------
+    # A step's inputs are 1.5 MiB, L2-resident by nature if the same pair were replayed.  So the timed steps walk
+    # through R distinct device-resident input sets (own clouds, own gradient tensors, own CUDA graph with its own
+    # memory pool, so every set also has its own scratch workspace: nothing a step touches was touched by the previous
+    # R - 1 steps) whose total size is > 2 x L2: every timed step reads inputs that are not in L2, and there is no host
+    # work, event or flush kernel between the steps - the way a training loop issues them.  One event pair around
+    # exactly K steps.
+    W = max(args.warmup, 3)
+    set_bytes = 4 * (xd.numel() + yd.numel()) * 2               # clouds + their gradients
+    R = max(2, int(2.2 * L2_BYTES // set_bytes) + 1)
+    sets = []
+    gen = torch.Generator().manual_seed(1234 + rank)
+    for r in range(R):
+        if r == 0:
+            xr_, yr_ = xd, yd
+        else:       # the same distribution as the workload (uniform cube), different points
+            xr_ = (torch.rand(B, N, 3, generator=gen) * 2 - 1).to(dev).requires_grad_(True)
+            yr_ = (torch.rand(B, M, 3, generator=gen) * 2 - 1).to(dev).requires_grad_(True)
+
+        def step_r(xr_=xr_, yr_=yr_):
+            xr_.grad = None
+            yr_.grad = None
+            loss_r = loss_on_cd(xr_, yr_)
+            loss_r.backward()
+            return loss_r
+        for _ in range(2):
+            step_r()
+        if use_graph:
+            torch.cuda.synchronize()
+            g_r = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_r):
+                step_r()
+            sets.append(g_r.replay)
+        else:
+            sets.append(step_r)
+    barrier()
+    for r in range(R):            # the first launch of a graph uploads it: replay every set once, in order, untimed
+        sets[r]()
+    barrier()
+    for k in range(W):            # warm-up steps; set W was last touched R - W steps (> 2 x L2 of traffic) ago
+        sets[k % R]()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    region_ms = []
+    for rep in range(5):          # region 0 is THE measurement (exactly K steps); the others give its spread
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # A ~20 ms spin kernel in front of the start event: the host enqueues all K launches while it runs, so the K
+        # steps execute back to back on the device whatever the host does meanwhile (the clock sampler's NVML
+        # queries stall launches for milliseconds: without the gate a region now and then measured such a stall)
+        torch.cuda._sleep(GATE_CYCLES)
+        ev0.record()
+        for k in range(args.steps):
+            sets[(W + rep * args.steps + k) % R]()
+        ev1.record()
+        barrier()
+        region_ms.append(ev0.elapsed_time(ev1) / args.steps)
+    ms = region_ms[0]
+
+    # ---- flushed leg (the round-1 protocol, kept for comparison): one input set, a 256 MiB memset between the steps,
+    # one event pair per step.  It adds the idle gap between an event record and the first kernel of a graph launch
+    # and the write-back of the memset's dirty lines to every step.
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    for _ in range(W):
         flush.zero_()
         run()
     barrier()
-
-    sampler = ClockSampler(local)
-    sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                 # L2 flush between timed iterations (outside the per-step event bracket)
@@ -460,8 +521,8 @@ def run_ours(args):
         ends[k].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    ms = sum(step_ms) / len(step_ms)
+    step_ms = [s_.elapsed_time(e_) for s_, e_ in zip(starts, ends)]
+    flushed_ms = sum(step_ms) / len(step_ms)
 
     # ---- roofline leg: the dominant kernel alone, events around the rma_chamfer_search stage -------------------
     lib = _lib.load()
@@ -730,10 +791,12 @@ def run_ours(args):
             torch.cuda.empty_cache()
 
     # ---- aggregate over ranks (max time) ------------------------------------------------------------------------
-    t = torch.tensor([ms, e2e_ms, search_ms, e2e_serial_ms, e2e_sync_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_ms, search_ms, e2e_serial_ms, e2e_sync_ms, flushed_ms] + region_ms, dtype=torch.float64,
+                     device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, search_ms, e2e_serial_ms, e2e_sync_ms = (float(v) for v in t.cpu())
+    ms, e2e_ms, search_ms, e2e_serial_ms, e2e_sync_ms, flushed_ms = (float(v) for v in t.cpu()[:6])
+    region_ms = [float(v) for v in t.cpu()[6:]]
     value = world * pairs / (ms * 1e-3) / 1e9
     e2e_value = world * pairs / (e2e_ms * 1e-3) / 1e9
 
@@ -750,7 +813,11 @@ def run_ours(args):
         "config": {"workload": f"{name}: chamfer fwd+bwd of loss_on_cd, B={B} per GPU, N=M={N}, uniform cube, "
                                f"seed {WORKLOADS[name][3]} (SURVEY.md §8d)",
                    "global_batch": B * world, "parallelism": f"batch-sharded x{world}, no collective",
-                   "l2": "256 MiB flush between timed steps (inputs are 1.5 MiB, L2-resident by nature)",
+                   "l2": f"inputs larger than L2: the timed steps rotate through {R} device-resident input sets "
+                         f"({R * set_bytes / 2**20:.0f} MiB of clouds + gradients > 2 x 126 MiB L2), replayed back to back "
+                         f"with one event pair around the K steps; flushed_step = the round-1 protocol (one set, 256 "
+                         f"MiB memset + one event pair per step) for comparison",
+                   "input_sets": R,
                    "cuda_graph": bool(use_graph),
                    "search_launch": {"kernel": search_kernel, "ctas": ctas.value, "threads": thr.value,
                                      ("tiles64_per_cta" if filt == 1 else "column_splits"): spl.value,
@@ -766,6 +833,7 @@ def run_ours(args):
                      # the north-star quantity: the same algorithmic FLOP over the WHOLE fwd+bwd step (prep + search +
                      # resolve + backward), L2 flushed before every step
                      "step_frac": FLOP_PER_PAIR * pairs / (ms * 1e-3) / 1e12 / peak_tflops,
+                     "step_frac_flushed_protocol": FLOP_PER_PAIR * pairs / (flushed_ms * 1e-3) / 1e12 / peak_tflops,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch cannot be measured inside
                      # this run (it needs ncu): taken from the committed ncu --set full capture named in
                      # traffic_source, for this workload and search kernel only
@@ -789,8 +857,10 @@ def run_ours(args):
         "gpu_launches": 4 * args.steps,      # prep + search + resolve/finalize(+loss,+grads) + cd_backward per step
         "secondary": secondary,
         "clocks": clocks,
-        "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
-        "step_ms_min_max": [min(step_ms), max(step_ms)],
+        "region_ms_per_step": region_ms,      # [0] is ms_per_step; four more regions of K steps show the spread
+        "flushed_step": {"ms_per_step": flushed_ms, "step_ms_min_max": [min(step_ms), max(step_ms)],
+                         "value": world * pairs / (flushed_ms * 1e-3) / 1e9,
+                         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3},
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -26,6 +26,7 @@
 //   beta = a + sqrt(1.0001 D_jf) by the triangle inequality, and D_jf <= 1.001 (f_jf + u_i)^+ + 1e-5 u_i.
 //   guard_row / guard_col below evaluate these bounds with >= 1% slack plus an absolute 1e-30 for underflow.
 #include <atomic>
+#include <type_traits>
 
 #include "chamfer_common.cuh"
 #include "../../include/rma_b200.h"
@@ -43,19 +44,36 @@ constexpr int kFThreads = 32 * kFWarps;                 // threads of the larges
 static inline int f_warps_for(int nRB) { return nRB >= 3 ? 4 : nRB; }   // 512-row blocks per batch element -> kW
 constexpr int kFColTile = 32;                           // columns per column-direction tile (= lanes)
 constexpr int kFColTop = 2;                             // packed group minima recorded per column and row block
-constexpr int kFRowTile = 64;                           // columns per work unit (CTA row block x 64 columns)
-// Columns per row-direction tile minimum ("sub-tile", template parameter kSub of the search and the resolve): what the
-// resolve re-evaluates per row.  32 instead of 64 cuts the resolve by a quarter (C2: 13.5 -> 10.3 us, C4: 160 -> 129 us,
-// 16 x 2048: 10.1 -> 7.6 us) for twice the 16-row epilogues in the search (+2-3 %: C2 +1.4 us, C4 +10 us): a net gain
-// while the resolve (linear in N + M) weighs enough against the search (N * M), i.e. for small clouds.
-constexpr int kFSubSmall = 32, kFSubLarge = 64;
-#ifndef RMA_F_SUBSWITCH
-#define RMA_F_SUBSWITCH 4096
-#endif
-constexpr int kFSubSwitch = RMA_F_SUBSWITCH;            // min(N, M) <= this: 32-column sub-tiles (tools/ build A/B variants)
-static inline int f_sub_for(int N, int M) { return (N < M ? N : M) <= kFSubSwitch ? kFSubSmall : kFSubLarge; }
+constexpr int kFRowTile = 64;                           // columns per work unit (CTA row block x 64 columns) = row-direction tile
+// Row direction: per row the minimum of f over each GROUP of 16 columns carries the group's position inside its
+// 64-column tile in the two low mantissa bits; per tile the two smallest tagged group minima are kept (registers), per
+// search segment the running (smallest, its tile, second smallest) over the tiles (shared memory).  The resolve then
+// re-evaluates the 16 columns of ONE group per row (256 bytes) instead of a whole tile.
+constexpr int kFGroup = 16;
+constexpr int kFGroupsPerTile = kFRowTile / kFGroup;    // 4: two tag bits
+constexpr unsigned kFRowTagMask = (unsigned)kFGroupsPerTile - 1u;
 constexpr int kFSubTiles = 16;                          // 64-column tiles per row-direction entry (sub-segment): bounds
                                                         // the slow path's re-evaluation to 1024 columns per candidate
+#ifndef RMA_F_FENCE_KIND
+#define RMA_F_FENCE_KIND 2
+#endif
+#if RMA_F_FENCE_KIND == 0
+#define RMA_F_FENCE() ((void)0)
+#elif RMA_F_FENCE_KIND == 1
+#define RMA_F_FENCE() __syncwarp()
+#elif RMA_F_FENCE_KIND == 2
+#define RMA_F_FENCE() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#elif RMA_F_FENCE_KIND == 3
+#define RMA_F_FENCE() asm volatile("bar.warp.sync 0xffffffff;" ::: "memory")
+#elif RMA_F_FENCE_KIND == 4
+#define RMA_F_FENCE() do { unsigned c_; asm volatile("mov.u32 %0, %%clock;" : "=r"(c_) :: "memory"); } while (0)
+#elif RMA_F_FENCE_KIND == 5
+#define RMA_F_FENCE() asm volatile("pmevent 0;" ::: "memory")
+#elif RMA_F_FENCE_KIND == 6
+#define RMA_F_FENCE() asm volatile("nanosleep.u32 0;" ::: "memory")
+#elif RMA_F_FENCE_KIND == 7
+#define RMA_F_FENCE() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
+#endif
 #ifndef RMA_F_CHUNK
 #define RMA_F_CHUNK 1024
 #endif
@@ -67,6 +85,23 @@ constexpr int kFChunk = RMA_F_CHUNK;                     // columns staged in sh
 constexpr int kFCbStride = 36;
 constexpr float kFBig = 1e30f;                          // |x|^2 of padded rows / |y|^2 of padded columns
 constexpr float kEps = 5.9604644775390625e-8f;          // 2^-24
+
+// Timeline instrumentation for tools/ builds (-DRMA_B200_TIMELINE): per kernel phase the earliest and latest
+// %globaltimer over all CTAs, kept behind the guard statistics.  Not compiled into the product library.
+#ifdef RMA_B200_TIMELINE
+__device__ __forceinline__ void tl_mark(unsigned* stats, int slot) {
+  if (threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(stats + 8) + 2 * slot;
+    atomicMin(p, t);
+    atomicMax(p + 1, t);
+  }
+}
+#define RMA_TL(stats, slot) tl_mark(stats, slot)
+#else
+#define RMA_TL(stats, slot) ((void)0)
+#endif
 
 struct FGeometry {
   int B, N, M;
@@ -80,6 +115,8 @@ struct FGeometry {
   int U;      // work units (CTA row block x 64-column tile) per search CTA
   int Smax;   // max segments (CTAs) that share one CTA row block
   int P;      // row-direction entries per segment: ceil(U / kFSubTiles)
+  unsigned magicN, magicM, magicU;   // ceil(2^32 / d) (clipped to 2^32 - 1): fast exact division in the resolve (fdiv)
+  int rc_shift;                      // log2(RC)
   long long units() const { return (long long)B * nRBC * nT; }
 };
 
@@ -114,6 +151,9 @@ static FGeometry f_make_geometry(int B, int N, int M, int slots, int force_run) 
   g.U = force_run > 0 ? force_run : f_choose_unit_run(g.units(), g.nT, slots);
   g.Smax = (g.nT + g.U - 1) / g.U + 1;
   g.P = ((g.U < g.nT ? g.U : g.nT) + kFSubTiles - 1) / kFSubTiles;
+  auto magic = [](unsigned d) { const unsigned long long m = ((1ull << 32) + d - 1) / d; return (unsigned)(m > 0xffffffffull ? 0xffffffffull : m); };
+  g.magicN = magic((unsigned)N); g.magicM = magic((unsigned)M); g.magicU = magic((unsigned)g.U);
+  g.rc_shift = g.W == 4 ? 11 : g.W == 2 ? 10 : 9;
   return g;
 }
 
@@ -127,7 +167,8 @@ struct FWorkspace {
                      //                         shared memory, so a chunk is one contiguous TMA bulk copy
   float* rowtop;     // [B*nRBC][Smax*P][3][RC] per segment and run of <= 16 tiles in it ("entry"): smallest sub-tile
                      //                         minimum, its sub-tile, second smallest; unused entries of a segment (inf, 0, inf)
-  float* colrec;     // [B][nRB][2][Mp]         two smallest packed group minima of g over the row block
+  float* colrec;     // [B][nRB][Mp][2]         two smallest packed group minima of g over the row block, interleaved
+                     //                         per column: one 8-byte store in the search, one 8-byte load in the resolve
   unsigned* stats;   // [4] rows on the slow path, columns on the slow path, row-block rescans, unused
   size_t bytes;
 };
@@ -163,6 +204,7 @@ __global__ void __launch_bounds__(256) chamfer_fprep_kernel(
   const long long ncol = (long long)g.B * g.Mp;
   pdl_wait();
   pdl_launch_dependents();   // let the search grid's launch overlap this kernel; its CTAs wait for our completion
+  RMA_TL(w.stats, 0);
   if (blockIdx.x == 0 && threadIdx.x < 4) w.stats[threadIdx.x] = 0u;
   if (zero_loss && blockIdx.x == 0 && threadIdx.x == 0) *zero_loss = 0.f;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nrow + ncol;
@@ -204,6 +246,7 @@ __global__ void __launch_bounds__(256) chamfer_fprep_kernel(
       w.colpair[u] = odd ? make_float4(r0, v.z, r1, v.w) : make_float4(v.x, r0, v.y, r1);
     }
   }
+  RMA_TL(w.stats, 1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -228,13 +271,13 @@ struct FSearchArgs {
   const float4* colpair;
   float* rowtop;
   float* colrec;
+  unsigned* stats;
   int N, M, nRB, Npad, nRBC, nT, Mp, U, Smax, P;
   long long units;
 };
 
-template <int kSub, int kW>
+template <int kW>
 __global__ void __launch_bounds__(32 * kW, RMA_F_MINCTAS * 4 / kW) chamfer_fsearch_kernel(FSearchArgs a) {
-  static_assert(kSub == kFRowTile || kSub == kFColTile, "row sub-tile is one or two 32-column passes");
   static_assert(kW == 1 || kW == 2 || kW == 4, "1, 2 or 4 warps per search CTA");
   constexpr int kThreads = 32 * kW, kRowsPerCta = kFRowsPerWarp * kW, kChunk = kFChunk * kW / 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -251,6 +294,8 @@ __global__ void __launch_bounds__(32 * kW, RMA_F_MINCTAS * 4 / kW) chamfer_fsear
   const unsigned lane_tag = (unsigned)lane;
   unsigned tag_mask = ~31u;                                    // kept in a register: (bits & mask) | tag is then ONE LOP3
   asm volatile("" : "+r"(tag_mask));
+  unsigned rtag_mask = ~kFRowTagMask;
+  asm volatile("" : "+r"(rtag_mask));
 
   long long unit = (long long)blockIdx.x * a.U;
   const long long unit_end = min(unit + a.U, a.units);
@@ -260,6 +305,7 @@ __global__ void __launch_bounds__(32 * kW, RMA_F_MINCTAS * 4 / kW) chamfer_fsear
   unsigned phases = 0;   // bit s: parity the next wait on buffer s expects
   pdl_wait();
   pdl_launch_dependents();   // the resolve grid may be launched (it blocks in its own pdl_wait until we are done)
+  RMA_TL(a.stats, 2);
 
   while (unit < unit_end) {
     // ---- one segment: a run of `ntile` 64-column tiles of one CTA row block ----
@@ -319,10 +365,10 @@ __global__ void __launch_bounds__(32 * kW, RMA_F_MINCTAS * 4 / kW) chamfer_fsear
     };
     reset_top();
 
-    float* crec = a.colrec + ((size_t)(b * a.nRB + rb) * kFColTop) * a.Mp + c0 + lane;
+    float2* crec = reinterpret_cast<float2*>(a.colrec) + (size_t)(b * a.nRB + rb) * a.Mp + c0 + lane;
 
     // Column direction, software-pipelined: while tile t is computed, lane l folds column l of tile t-1 (32 per-lane
-    // packed partial minima in the other half of the double buffer) into its running top-3, four values per body.
+    // packed partial minima in the other half of the double buffer) into its running top-2, four values per body.
     int pend_col = -1;   // column offset (relative to c0) of the tile whose reduce is pending; warp-uniform
     int parity = 0;
 
@@ -340,60 +386,77 @@ __global__ void __launch_bounds__(32 * kW, RMA_F_MINCTAS * 4 / kW) chamfer_fsear
 
 #pragma unroll 1
       for (int t0 = 0; has_rows && t0 < nc; t0 += kFRowTile) {
-        float tm[kFRowsPerThread];
+        // tile-level (smallest, second smallest) tagged group minimum per row
+        float tm[kFRowsPerThread], ts[kFRowsPerThread];
+#pragma unroll
+        for (int r = 0; r < kFRowsPerThread; ++r) tm[r] = ts[r] = inf;
 #pragma unroll 1
         for (int h = 0; h < kFRowTile; h += kFColTile) {
-          if (kSub == kFColTile || h == 0) {
-#pragma unroll
-            for (int r = 0; r < kFRowsPerThread; ++r) tm[r] = inf;
-          }
           const float4* sp = schunk + t0 + h;
           float* cbw = cb + parity * (kFColTile * kFCbStride) + lane;
           const float4* cbr = reinterpret_cast<const float4*>(cb + (parity ^ 1) * (kFColTile * kFCbStride) +
                                                               lane * kFCbStride);
           float p1 = inf, p2 = inf;
+          float gm[kFRowsPerThread];       // running minimum of f over the current 16-column group
 
           // Four columns against the 16 rows, plus four pending values of the previous tile's column reduce.
-          auto body = [&](const float4& q0, const float4& q1, const float4& q2, const float4& q3, int jj) {
+          // kFirst: the group's first body starts the group minima (no reset instructions, a 2-input minimum).
+          auto body = [&](const float4& q0, const float4& q1, const float4& q2, const float4& q3, int jj, auto first_tag) {
+            constexpr bool kFirst = decltype(first_tag)::value;
             const float4 pv = cbr[jj >> 2];          // 4 packed partial minima of the pending tile
             // fp32x2 lanes = two COLUMNS, the row value is the broadcast scalar.  The operand that stays fixed over
             // the 16-row inner loop is then the 64-bit column pair, which the operand-reuse cache keeps (2 register
             // words saved per FFMA2 instead of 1): FFMA2 acc, Qpair.reuse, x_row.F32, acc.
             float cm[4];
+            // The 96 FFMA2 of the body (two column pairs x three chain steps x 16 rows) are issued as six runs of 16
+            // that share their 64-bit column operand (operand-reuse latch: an FFMA2 whose column pair comes from the
+            // latch reads 3 register words = 2 issue cycles, otherwise 5 words = 3 cycles), then the minima.  Left to
+            // itself ptxas alternates FFMA2 and FMNMX3 one to one, which loses the latch on every FFMA2; RMA_F_FENCE()
+            // keeps the two groups apart.
+            u64 acc[2][16];
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
               const float4 A = h2 ? q2 : q0, Bq = h2 ? q3 : q1;
               const u64 Q0 = pack2(A.x, A.y), Q1 = pack2(A.z, A.w), Q2 = pack2(Bq.x, Bq.y), WW = pack2(Bq.z, Bq.w);
-              // chain step by step over the 16 rows (ptxas re-schedules this freely; forcing the order with
-              // basic-block fences so that the 64-bit column operand is reused 16 times in a row was measured: no gain)
-              u64 acc[16];
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 float za, zb;
                 unpack2(pz[k], za, zb);
-                acc[2 * k] = fma2(Q2, pack2(za, za), WW); acc[2 * k + 1] = fma2(Q2, pack2(zb, zb), WW);
+                acc[h2][2 * k] = fma2(Q2, pack2(za, za), WW); acc[h2][2 * k + 1] = fma2(Q2, pack2(zb, zb), WW);
               }
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 float ya, yb;
                 unpack2(py[k], ya, yb);
-                acc[2 * k] = fma2(Q1, pack2(ya, ya), acc[2 * k]); acc[2 * k + 1] = fma2(Q1, pack2(yb, yb), acc[2 * k + 1]);
+                acc[h2][2 * k] = fma2(Q1, pack2(ya, ya), acc[h2][2 * k]);
+                acc[h2][2 * k + 1] = fma2(Q1, pack2(yb, yb), acc[h2][2 * k + 1]);
               }
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 float xa, xb;
                 unpack2(px[k], xa, xb);
-                acc[2 * k] = fma2(Q0, pack2(xa, xa), acc[2 * k]); acc[2 * k + 1] = fma2(Q0, pack2(xb, xb), acc[2 * k + 1]);
+                acc[h2][2 * k] = fma2(Q0, pack2(xa, xa), acc[h2][2 * k]);
+                acc[h2][2 * k + 1] = fma2(Q0, pack2(xb, xb), acc[h2][2 * k + 1]);
               }
+            }
+            RMA_F_FENCE();
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
               float cl = inf, ch = inf;
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 float ua, ub, al, ah, bl, bh;
                 unpack2(pu[k], ua, ub);
-                unpack2(acc[2 * k], al, ah); unpack2(acc[2 * k + 1], bl, bh);
-                tm[2 * k] = min3(tm[2 * k], al, ah);
-                tm[2 * k + 1] = min3(tm[2 * k + 1], bl, bh);
-                unpack2(add2(acc[2 * k], pack2(ua, ua)), al, ah); unpack2(add2(acc[2 * k + 1], pack2(ub, ub)), bl, bh);
+                unpack2(acc[h2][2 * k], al, ah); unpack2(acc[h2][2 * k + 1], bl, bh);
+                if (kFirst && h2 == 0) {
+                  gm[2 * k] = fminf(al, ah);
+                  gm[2 * k + 1] = fminf(bl, bh);
+                } else {
+                  gm[2 * k] = min3(gm[2 * k], al, ah);
+                  gm[2 * k + 1] = min3(gm[2 * k + 1], bl, bh);
+                }
+                unpack2(add2(acc[h2][2 * k], pack2(ua, ua)), al, ah);
+                unpack2(add2(acc[h2][2 * k + 1], pack2(ub, ub)), bl, bh);
                 cl = min3(cl, al, bl);
                 ch = min3(ch, ah, bh);
               }
@@ -406,46 +469,61 @@ __global__ void __launch_bounds__(32 * kW, RMA_F_MINCTAS * 4 / kW) chamfer_fsear
             top2_insert(p1, p2, pv.y);
             top2_insert(p1, p2, pv.z);
             top2_insert(p1, p2, pv.w);
+#ifndef RMA_F_NO_TAIL_FENCE
+            RMA_F_FENCE();
+#endif
           };
 
-          // Operands are prefetched one body ahead into the OTHER register set (ping-pong, unrolled by two) so that no
-          // register copies are needed: a MOV/IMAD.MOV here queues behind the saturated FMA pipe and stalls the warp.
-          // The last prefetch of a chunk reads the 4-column pad behind the staged data and is never used.
+          // One 16-column group per trip (four bodies).  Operands are prefetched one body ahead into the OTHER register
+          // set (ping-pong) so that no register copies are needed: a MOV/IMAD.MOV here queues behind the saturated FMA
+          // pipe and stalls the warp.  The last prefetch of a chunk reads the 4-column pad behind the staged data and is
+          // never used.
           float4 a0 = sp[0], a1 = sp[1], a2 = sp[2], a3 = sp[3];
+          unsigned gid = (unsigned)(h / kFGroup);                   // group position inside the 64-column tile
 #pragma unroll 1
-          for (int jj = 0; jj < kFColTile; jj += 8) {
-            const float4 b0 = sp[jj + 4], b1 = sp[jj + 5], b2 = sp[jj + 6], b3 = sp[jj + 7];
-            body(a0, a1, a2, a3, jj);
+          for (int jj = 0; jj < kFColTile; jj += kFGroup, ++gid) {
+            float4 b0 = sp[jj + 4], b1 = sp[jj + 5], b2 = sp[jj + 6], b3 = sp[jj + 7];
+            body(a0, a1, a2, a3, jj, std::true_type{});
             a0 = sp[jj + 8]; a1 = sp[jj + 9]; a2 = sp[jj + 10]; a3 = sp[jj + 11];
-            body(b0, b1, b2, b3, jj + 4);
+            body(b0, b1, b2, b3, jj + 4, std::false_type{});
+            b0 = sp[jj + 12]; b1 = sp[jj + 13]; b2 = sp[jj + 14]; b3 = sp[jj + 15];
+            body(a0, a1, a2, a3, jj + 8, std::false_type{});
+            a0 = sp[jj + 16]; a1 = sp[jj + 17]; a2 = sp[jj + 18]; a3 = sp[jj + 19];
+            body(b0, b1, b2, b3, jj + 12, std::false_type{});
+            // fold the group's tagged minima into the tile's two smallest (3 FMNMX + 1 LOP3 per row and group)
+#pragma unroll
+            for (int r = 0; r < kFRowsPerThread; ++r) {
+              const float v = __uint_as_float((__float_as_uint(gm[r]) & rtag_mask) | gid);
+              ts[r] = fminf(ts[r], fmaxf(tm[r], v));
+              tm[r] = fminf(tm[r], v);
+            }
           }
 
           if (pend_col >= 0) {
-            float* o = crec + pend_col;
-            o[0] = p1; o[a.Mp] = p2;
+            crec[pend_col] = make_float2(p1, p2);
           }
           pend_col = cs + t0 + h;
           parity ^= 1;
           __syncwarp();   // this tile's partial minima visible to all lanes; previous buffer free for reuse
+        }
 
-          // Row direction: the sub-tile's 16 filter minima are folded into the running (smallest, its sub-tile, second
-          // smallest) of the segment.  (A per-tile record in global memory - B*N*M/16 bytes, read only when a guard
-          // fails - cost 2.8 us of the 83 us C2 step in stores that evict dirty L2 lines; the slow path re-evaluates
-          // the candidate SEGMENTS instead.)
-          if (kSub == kFColTile || h + kFColTile == kFRowTile) {
-            const int tile = tile0 * (kFRowTile / kSub) + (cs + t0 + h) / kSub;
-            const float tilef = __int_as_float(tile);
+        // Row direction: the tile's two smallest tagged group minima are folded into the running (smallest, its tile,
+        // second smallest) of the segment.  (A per-tile record in global memory - B*N*M/16 bytes, read only when a
+        // guard fails - cost 2.8 us of the 83 us C2 step in stores that evict dirty L2 lines; the slow path
+        // re-evaluates the candidate SEGMENTS instead.)
+        {
+          const int tile = tile0 + (cs + t0) / kFRowTile;
+          const float tilef = __int_as_float(tile);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4 m1 = stop[q * kThreads], t1 = stop[(4 + q) * kThreads], m2 = stop[(8 + q) * kThreads];
-              m2.x = fminf(m2.x, fmaxf(m1.x, tm[4 * q]));     t1.x = tm[4 * q] < m1.x ? tilef : t1.x;
-              m2.y = fminf(m2.y, fmaxf(m1.y, tm[4 * q + 1])); t1.y = tm[4 * q + 1] < m1.y ? tilef : t1.y;
-              m2.z = fminf(m2.z, fmaxf(m1.z, tm[4 * q + 2])); t1.z = tm[4 * q + 2] < m1.z ? tilef : t1.z;
-              m2.w = fminf(m2.w, fmaxf(m1.w, tm[4 * q + 3])); t1.w = tm[4 * q + 3] < m1.w ? tilef : t1.w;
-              m1.x = fminf(m1.x, tm[4 * q]); m1.y = fminf(m1.y, tm[4 * q + 1]);
-              m1.z = fminf(m1.z, tm[4 * q + 2]); m1.w = fminf(m1.w, tm[4 * q + 3]);
-              stop[q * kThreads] = m1; stop[(4 + q) * kThreads] = t1; stop[(8 + q) * kThreads] = m2;
-            }
+          for (int q = 0; q < 4; ++q) {
+            float4 m1 = stop[q * kThreads], t1 = stop[(4 + q) * kThreads], m2 = stop[(8 + q) * kThreads];
+            m2.x = min3(m2.x, ts[4 * q], fmaxf(m1.x, tm[4 * q]));         t1.x = tm[4 * q] < m1.x ? tilef : t1.x;
+            m2.y = min3(m2.y, ts[4 * q + 1], fmaxf(m1.y, tm[4 * q + 1])); t1.y = tm[4 * q + 1] < m1.y ? tilef : t1.y;
+            m2.z = min3(m2.z, ts[4 * q + 2], fmaxf(m1.z, tm[4 * q + 2])); t1.z = tm[4 * q + 2] < m1.z ? tilef : t1.z;
+            m2.w = min3(m2.w, ts[4 * q + 3], fmaxf(m1.w, tm[4 * q + 3])); t1.w = tm[4 * q + 3] < m1.w ? tilef : t1.w;
+            m1.x = fminf(m1.x, tm[4 * q]); m1.y = fminf(m1.y, tm[4 * q + 1]);
+            m1.z = fminf(m1.z, tm[4 * q + 2]); m1.w = fminf(m1.w, tm[4 * q + 3]);
+            stop[q * kThreads] = m1; stop[(4 + q) * kThreads] = t1; stop[(8 + q) * kThreads] = m2;
           }
         }
         if (++sub_tiles == kFSubTiles) flush_top();
@@ -459,33 +537,41 @@ __global__ void __launch_bounds__(32 * kW, RMA_F_MINCTAS * 4 / kW) chamfer_fsear
         float p1 = inf, p2 = inf;
 #pragma unroll
         for (int k = 0; k < 32; ++k) top2_insert(p1, p2, col[k]);
-        float* o = crec + pend_col;
-        o[0] = p1; o[a.Mp] = p2;
+        crec[pend_col] = make_float2(p1, p2);
       }
       if (sub_tiles > 0) flush_top();
       while (sub < a.P) flush_top();   // empty entries
       __syncwarp();   // the next segment reuses the transpose buffers
     }
   }
+  RMA_TL(a.stats, 3);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // resolve
 // ---------------------------------------------------------------------------------------------------------------
+// sqrt.approx (one MUFU instruction, <= 2 ulp; 0 -> 0, inf -> inf) instead of the IEEE sqrtf (~12 instructions and a
+// divergent slow path for denormals): the guards multiply every square root by 1.0001, which covers 2 ulp = 2.4e-7.
+__device__ __forceinline__ float sqrt_fast(float v) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 // Rigorous guards (derivation in the file header).  u = fl(|x_i|^2), mt = smallest filter value f of the row.
 __device__ __forceinline__ float guard_row(float u, float mt) {
   const float D0 = fmaxf(mt + u, 0.f);
   const float Dub = 1.001f * D0 + 1e-5f * u;
-  const float a = sqrtf(u) * 1.0001f;
-  const float beta = a + sqrtf(Dub) * 1.0001f;
+  const float a = sqrt_fast(u) * 1.0001f;
+  const float beta = a + sqrt_fast(Dub) * 1.0001f;
   return (12.3f * beta * (beta + a) + 10.3f * Dub) * (kEps * 1.01f) + 1e-30f;
 }
 // wj = fl(|y_j|^2), mt = smallest (packed, truncated) value of g for the column, i.e. an estimate of the distance.
 __device__ __forceinline__ float guard_col(float wj, float mt) {
   const float D0 = fmaxf(mt, 0.f);
   const float Dub = 1.001f * D0 + 1e-5f * wj;
-  const float bn = sqrtf(wj) * 1.0001f;
-  const float alpha = bn + sqrtf(Dub) * 1.0001f;
+  const float bn = sqrt_fast(wj) * 1.0001f;
+  const float alpha = bn + sqrt_fast(Dub) * 1.0001f;
   return (12.3f * bn * (bn + alpha) + 6.3f * alpha * alpha + 12.5f * Dub) * (kEps * 1.01f) +
          Dub * 7.8e-6f /* 2^-17 * 1.02 */ + 1e-30f;
 }
@@ -500,64 +586,285 @@ __device__ __forceinline__ float sqdist_q(float x, float y, float z, const float
   return d;
 }
 
-// (distance bits, index) lexicographic minimum over the kLanes lanes of an aligned lane group.
-template <int kLanes>
-__device__ __forceinline__ void group_min(unsigned& d, unsigned& idx) {
+// t / d for t < 2^31 with m = min(ceil(2^32 / d), 2^32 - 1): umulhi(t, m) is off by at most one either way (the
+// estimate t m / 2^32 lies in [t/d - t/2^32, t/d + t/2^32)), so one multiply-back and two selects make it exact - six
+// instructions against ~20 for the emulated 32-bit division (the resolve had five of them per lane).
+__device__ __forceinline__ unsigned fdiv(unsigned t, unsigned d, unsigned m) {
+  unsigned q = __umulhi(t, m);
+  const int r = (int)(t - q * d);
+  q = r < 0 ? q - 1u : q;
+  q = r >= (int)d ? q + 1u : q;
+  return q;
+}
+
+// Tagged row-direction values: a group minimum v is stored as t(v) = (bits(v) & ~3) | group, |t(v) - v| < 4 ulp(v)
+// <= 2^-21 |v|.  With M1 the smallest TAGGED group minimum of a row, every group that holds an exact minimiser has
+// t(gm) <= M1 + G (1 + 2^-21) + 2.02 * 2^-21 |M1| = M1 + ... + 0.97e-6 |M1| (the 1.2e-6 below also covers the rounding of the final sum; G = guard_row at the true filter minimum; guard_row's own slack in
+// its distance estimate, 1e-5 u + 1e-3 D, covers the 2^-21 (u + D) by which M1 may differ from it).
+__device__ __forceinline__ float row_threshold(float u, float M1) {
+  return M1 + (guard_row(u, M1) * 1.0001f + 1.2e-6f * fabsf(M1));
+}
+
+// Fast-path evaluation of the 32 items of a warp, 16 candidates each (a row's candidate group of 16 columns / a
+// column's candidate group of 16 rows: 256 contiguous bytes of colpack / rowpack).
+//   phase 1  two items per round, one candidate per lane (a half-warp reads its item's 256 bytes as one coalesced
+//            LDG.128): the candidate is re-filtered with the search's own chain (bit-identical f / g; padding carries
+//            1e30 and never passes) against the item's threshold; a ballot hands every item's 16 pass bits to its owner
+//            lane.  All loads of eight rounds are in flight together.
+//   phase 2  lane <-> item: the owner evaluates its survivors - usually one - in the exact difference form, ascending,
+//            strict '<' (torch.min's first index).
+// sA[item] = the item's broadcast data, sB[item] = (first candidate's index in `cand`, fast flag, threshold bits, -).
+template <bool kColumns>
+__device__ __forceinline__ void fast_items(const float4* __restrict__ cand, const float4* sA, const int2* sB, float4* sQ,
+                                           int lane, unsigned& best_d, unsigned& best_k, float4& best_c) {
+  const int half = lane >> 4;
+  const unsigned c = (unsigned)lane & 15u, sh = ((unsigned)lane & 1u) * 16u;
+  unsigned mymask = 0u;
+  // Rounds of two items.  Loads run two batches of four rounds ahead of the arithmetic (32 registers in flight), so the
+  // sixteen loads cost little more than one L2 round trip.  A candidate that passes is also dropped into its item's
+  // shared-memory slot: with exactly one survivor - the usual case - the owner lane evaluates it from there without a
+  // second dependent trip to L2.
+  auto load4 = [&](int r0, float4 (&v)[4]) {
 #pragma unroll
-  for (int o = 1; o < kLanes; o <<= 1) {
-    const unsigned od = __shfl_xor_sync(0xffffffffu, d, o);
-    const unsigned oi = __shfl_xor_sync(0xffffffffu, idx, o);
-    const bool take = od < d || (od == d && oi < idx);
-    d = take ? od : d;
-    idx = take ? oi : idx;
+    for (int k = 0; k < 4; ++k)          // unconditional: an item off the fast path has base 0 and threshold -inf
+      v[k] = cand[(unsigned)sB[2 * (r0 + k) + half].x + c];
+  };
+  auto eval4 = [&](int r0, const float4 (&v)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int item = 2 * (r0 + k) + half;
+      const float4 it = sA[item];
+      const float thr = __int_as_float(sB[item].y);
+      float fv;
+      if (kColumns)   // it = the column (q0, q1, q2, w), v = a row (x, y, z, u):  g = fl(f + u)
+        fv = __fadd_rn(__fmaf_rn(v[k].x, it.x, __fmaf_rn(v[k].y, it.y, __fmaf_rn(v[k].z, it.z, it.w))), v[k].w);
+      else            // it = the row (x, y, z, .), v = a column (q0, q1, q2, w)
+        fv = __fmaf_rn(it.x, v[k].x, __fmaf_rn(it.y, v[k].y, __fmaf_rn(it.z, v[k].z, v[k].w)));
+      const bool pass = fv <= thr;
+      if (pass) sQ[item] = v[k];
+      const unsigned bal = __ballot_sync(0xffffffffu, pass);
+      if ((lane >> 1) == r0 + k) mymask = (bal >> sh) & 0xffffu;
+    }
+  };
+  float4 va[4], vb[4];
+  load4(0, va);
+  load4(4, vb);
+  eval4(0, va);
+  load4(8, va);
+  eval4(4, vb);
+  load4(12, vb);
+  eval4(8, va);
+  eval4(12, vb);
+  __syncwarp();
+  const float4 me = sA[lane];
+  const unsigned base = (unsigned)sB[lane].x;
+  if (mymask != 0u && (mymask & (mymask - 1u)) == 0u) {     // one survivor: its data is in the item's slot
+    const float4 cv = sQ[lane];
+    best_d = __float_as_uint(kColumns ? sqdist_q(cv.x, cv.y, cv.z, me) : sqdist_q(me.x, me.y, me.z, cv));
+    best_k = base + (unsigned)(__ffs(mymask) - 1);
+    best_c = cv;
+    mymask = 0u;
+  }
+  while (mymask) {                                          // several survivors: ascending, strict '<' keeps the first
+    const int k = __ffs(mymask) - 1;
+    mymask &= mymask - 1u;
+    const float4 cv = cand[base + (unsigned)k];
+    const unsigned d = __float_as_uint(kColumns ? sqdist_q(cv.x, cv.y, cv.z, me) : sqdist_q(me.x, me.y, me.z, cv));
+    if (d < best_d) { best_d = d; best_k = base + (unsigned)k; best_c = cv; }
   }
 }
 
-// Result of one fast-path round for owner lane (round * kItems + k): the (distance, index) minimum of lane group k
-// (kLanes lanes per item, kItems = 32 / kLanes items per round).  Usually exactly one lane of a group holds a
-// survivor, then a ballot finds it and two SHFL fetch it; otherwise the butterfly runs.  Warp-uniform control flow.
-template <int kLanes>
-__device__ __forceinline__ void round_result(unsigned d, unsigned idx, unsigned& rd, unsigned& ri) {
-  constexpr unsigned kItems = 32u / kLanes, gmask = (1u << kLanes) - 1u;
-  const unsigned full = 0xffffffffu, lane = lane_id();
-  const unsigned hit = __ballot_sync(full, d != 0xffffffffu);
-  const unsigned gb = (hit >> (lane & ~(unsigned)(kLanes - 1))) & gmask;   // my own group's survivors
-  if (__all_sync(full, (gb & (gb - 1u)) == 0u)) {                            // every group has at most one
-    const unsigned k = lane % kItems, gk = (hit >> (k * kLanes)) & gmask;
-    const int src = (int)(k * kLanes) + (gk ? __ffs(gk) - 1 : 0);
-    rd = __shfl_sync(full, d, src); ri = __shfl_sync(full, idx, src);
-  } else {
-    group_min<kLanes>(d, idx);
-    rd = __shfl_sync(full, d, (lane % kItems) * kLanes); ri = __shfl_sync(full, idx, (lane % kItems) * kLanes);
+// Row-direction records of one row: the smallest tagged group minimum over the row block's entries, its tile, and the
+// second smallest.  kRC = rows per CTA row block (compile-time: the three planes of an entry then sit at immediate
+// offsets from one running pointer).
+template <int kRC>
+__device__ __forceinline__ void scan_row_entries(const float* top, int nseg, float& M1, int& T1, float& M2) {
+  const float inf = __int_as_float(0x7f800000);
+  constexpr int kSegBatch = 12;                 // up to 12 entries in flight: one latency for C2 (10)
+  for (int s0 = 0; s0 < nseg; s0 += kSegBatch) {
+    float a1[kSegBatch], a2[kSegBatch];
+    int at[kSegBatch];
+    const float* tp = top + (size_t)s0 * (3 * kRC);
+#pragma unroll
+    for (int k = 0; k < kSegBatch; ++k) {
+      const bool on = s0 + k < nseg;
+      const float* q = on ? tp + k * (3 * kRC) : tp;
+      a1[k] = q[0]; at[k] = __float_as_int(q[kRC]); a2[k] = q[2 * kRC];
+      a1[k] = on ? a1[k] : inf;
+      a2[k] = on ? a2[k] : inf;
+    }
+#pragma unroll
+    for (int k = 0; k < kSegBatch; ++k) {
+      M2 = fminf(fminf(M2, a2[k]), fmaxf(M1, a1[k]));
+      if (a1[k] < M1) { M1 = a1[k]; T1 = at[k]; }
+    }
   }
 }
 
-// Work distribution: the ceil(B*N/32) + ceil(B*M/32) warp items are dealt out evenly over the grid (CTA c takes items
-// [c*total/grid, (c+1)*total/grid), at most one per warp).  For a single-wave problem the grid is exactly
+// Slow path of ONE row (out of line: its registers must not weigh on the fast path, which runs at the kernel's 64-register
+// cap).  Every candidate group lies in an entry (a run of up to 16 tiles of one search segment) whose smallest group
+// minimum is within the guard: an entry whose second smallest is not contributes its one recorded group, otherwise all
+// of its columns.  The lowest column among the lanes that hold the minimum = torch.min's first index.
+__device__ __noinline__ void row_slow_item(const float* __restrict__ rowtop, const float4* __restrict__ colpack, int RC,
+                                           int nRBC, int nT, int U, int Smax, int P, int Mp, int sb, int si, float sthr,
+                                           float x, float y, float z, unsigned& out_d, unsigned& out_j, float4& out_q) {
+  const unsigned full = 0xffffffffu;
+  const float inf = __int_as_float(0x7f800000);
+  const int lane = lane_id(), half = lane >> 4, hl = lane & 15;
+  const int srbc = si / RC;
+  const unsigned sbrb = (unsigned)(sb * nRBC + srbc);
+  const unsigned u0 = sbrb * (unsigned)nT, u1 = u0 + (unsigned)nT;       // the row block's units [u0, u1)
+  const unsigned kfirst = u0 / (unsigned)U, klast = (u1 - 1u) / (unsigned)U;
+  const float* top = rowtop + ((size_t)sbrb * Smax * P * 3) * RC + (si - srbc * RC);
+  const float4* scq = colpack + (size_t)sb * Mp;
+  unsigned bd = 0xffffffffu, bj = 0xffffffffu;
+  float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+  // Latency matters more than work here: a warp with a slow item is the last to finish, and the kernel is as long
+  // as its slowest warp.  So the candidates of a slow item are loaded in batches (every load of a batch in flight
+  // together) and only then evaluated: one L2 round trip per batch of 8 groups / 128 columns.
+  auto eval_col = [&](const float4 q, unsigned jc) {
+    const float fj = __fmaf_rn(x, q.x, __fmaf_rn(y, q.y, __fmaf_rn(z, q.z, q.w)));
+    if (fj <= sthr) {
+      const unsigned d = __float_as_uint(sqdist_q(x, y, z, q));
+      if (d < bd || (d == bd && jc < bj)) { bd = d; bj = jc; bq = q; }
+    }
+  };
+  const unsigned nent = (klast - kfirst + 1u) * (unsigned)P;
+  for (unsigned base = 0; base < nent; base += 32u) {
+    // one entry per lane, all in flight; empty entries hold inf
+    const unsigned e = base + (unsigned)lane;
+    const float* tp = top + (size_t)(e < nent ? e : base) * (3 * RC);
+    const float a1 = e < nent ? tp[0] : inf;
+    const unsigned g1 = (unsigned)__float_as_int(tp[RC]) * kFGroupsPerTile + (__float_as_uint(a1) & kFRowTagMask);
+    const float a2 = e < nent ? tp[2 * RC] : inf;
+    const bool hit = a1 <= sthr;
+    const unsigned singles = __ballot_sync(full, hit && !(a2 <= sthr));
+    unsigned wholes = __ballot_sync(full, hit && a2 <= sthr);
+    const int nsingle = __popc(singles);
+    for (int r = 0; r < nsingle; r += 8) {            // eight groups per batch: half-warp <-> group, lane <-> column
+      float4 q[4];
+      unsigned jc[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = min(r + 2 * k + half, nsingle - 1);       // clamped: re-evaluating a candidate is harmless
+        const unsigned from = __fns(singles, 0, idx + 1);
+        jc[k] = __shfl_sync(full, g1, (int)from) * kFGroup + (unsigned)hl;
+        q[k] = scq[jc[k]];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) eval_col(q[k], jc[k]);
+    }
+    while (wholes) {                                  // every column of the entry: 128 per batch, lane <-> 4 columns
+      const unsigned he = base + (unsigned)__ffs(wholes) - 1u; wholes &= wholes - 1u;
+      const unsigned k = kfirst + he / (unsigned)P, pe = he % (unsigned)P;
+      const unsigned ua = max(k * (unsigned)U, u0), ub = min((k + 1u) * (unsigned)U, u1);   // the segment's units
+      const unsigned ta = ua - u0 + pe * kFSubTiles;              // first 64-column tile of the entry, within the row block
+      const unsigned tb = min(ta + kFSubTiles, ub - u0);          // the entry's tiles [ta, tb)
+      const unsigned c_lo = ta * kFRowTile, c_hi = tb * kFRowTile;
+#pragma unroll 1
+      for (unsigned cb0 = c_lo; cb0 < c_hi; cb0 += 128u) {
+        float4 q[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) q[kk] = scq[min(cb0 + (unsigned)lane + 32u * kk, c_hi - 1u)];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) eval_col(q[kk], min(cb0 + (unsigned)lane + 32u * kk, c_hi - 1u));
+      }
+    }
+  }
+  const unsigned mn = __reduce_min_sync(full, bd);
+  const unsigned jm = __reduce_min_sync(full, bd == mn ? bj : 0xffffffffu);
+  const int owner = __ffs(__ballot_sync(full, bd == mn && bj == jm)) - 1;
+  const float qx = __shfl_sync(full, bq.x, owner), qy = __shfl_sync(full, bq.y, owner);
+  const float qz = __shfl_sync(full, bq.z, owner);
+  out_d = mn; out_j = jm; out_q = make_float4(qx, qy, qz, 0.f);
+}
+
+// Slow path of ONE column (out of line, see row_slow_item): every row block's first record within the guard is a
+// candidate group of 16 rows; a SECOND record within the guard means the row block may hold more than the recorded two,
+// so all of its 512 rows are re-evaluated.
+__device__ __noinline__ void col_slow_item(const float* __restrict__ colrec, const float4* __restrict__ rowpack,
+                                           unsigned* stats, int nRB, int Mp, int Npad, int N, int sb, int sj, float sthr,
+                                           float qx, float qy, float qz, unsigned& out_d, unsigned& out_i) {
+  const unsigned full = 0xffffffffu;
+  const float inf = __int_as_float(0x7f800000);
+  const int lane = lane_id(), half = lane >> 4, hl = lane & 15;
+  const float4 q = make_float4(qx, qy, qz, 0.f);
+  const float* rec = colrec + ((size_t)sb * nRB * Mp + sj) * kFColTop;   // record e of this column: rec[(e / 2) * 2 Mp + e % 2]
+  unsigned bd = 0xffffffffu, bi = 0xffffffffu;
+  const float4* srp = rowpack + (size_t)sb * Npad;
+  auto eval_row = [&](const float4 pr, unsigned row) {            // padded rows sit at the origin: excluded by index
+    if (row < (unsigned)N) {
+      const unsigned d = __float_as_uint(sqdist_q(pr.x, pr.y, pr.z, q));
+      if (d < bd || (d == bd && row < bi)) { bd = d; bi = row; }
+    }
+  };
+  const int nE = nRB * kFColTop;
+  for (int base = 0; base < nE; base += 32) {
+    const int e = base + lane;                                     // entry e = row block e / 2, record e % 2
+    const float p = e < nE ? rec[(size_t)(e >> 1) * (kFColTop * Mp) + (e & 1)] : inf;
+    const unsigned hits = __ballot_sync(full, p <= sthr);
+    // a row block whose SECOND record is within the guard may hold more candidates than the two recorded: rescan it
+    unsigned blocks = hits & 0xaaaaaaaau;
+    unsigned groups = hits & 0x55555555u & ~(blocks >> 1);        // first records of the other row blocks
+    const unsigned first_row = ((unsigned)(e >> 1) * 32u + (__float_as_uint(p) & 31u)) * kFRowsPerThread;
+    const int ngroup = __popc(groups);
+    for (int r = 0; r < ngroup; r += 8) {            // eight 16-row groups per batch: half-warp <-> group, lane <-> row
+      float4 pr[4];
+      unsigned row[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = min(r + 2 * k + half, ngroup - 1);
+        const unsigned from = __fns(groups, 0, idx + 1);
+        row[k] = __shfl_sync(full, first_row, (int)from) + (unsigned)hl;
+        pr[k] = srp[row[k]];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) eval_row(pr[k], row[k]);
+    }
+    while (blocks) {                                  // all 512 rows of the block: 128 per batch
+      const unsigned hrb = (unsigned)(base + __ffs(blocks) - 1) >> 1; blocks &= blocks - 1u;
+      if (lane == 0) atomicAdd(stats + 2, 1u);
+#pragma unroll 1
+      for (unsigned r0 = hrb * kFRowsPerWarp; r0 < (hrb + 1u) * kFRowsPerWarp; r0 += 128u) {
+        float4 pr[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) pr[kk] = srp[r0 + (unsigned)lane + 32u * kk];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) eval_row(pr[kk], r0 + (unsigned)lane + 32u * kk);
+      }
+    }
+  }
+  {
+    const unsigned mn = __reduce_min_sync(full, bd);
+    const unsigned ii = __reduce_min_sync(full, bd == mn ? bi : 0xffffffffu);
+    bd = mn; bi = ii;
+  }
+  out_d = bd; out_i = bi;
+}
+
+// Work distribution: the ceil(B*N/32) + ceil(B*M/32) warp items are dealt out evenly over the grid (CTA c takes
+// total/grid items, the first total%grid CTAs one more; at most one per warp).  For a single-wave problem the grid is exactly
 // SMs x 4 resident CTAs, so every SM carries the same load wherever the block scheduler (or an early programmatic
 // launch behind the search's tail) places the CTAs: with one CTA per 8 items, 512 CTAs on 148 SMs leave some SMs with
 // 4 x 8 items against an average of 27.7.
-//
-// Lanes per item in the fast path: kSub / 8 lanes re-evaluate one row's candidate sub-tile (8 columns each) or one
-// column's candidate group of 16 rows; a round handles kItems = 32 / kLanes items.
-template <int kSub>
-__global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGeometry g, FWorkspace w, FinalizeArgs f) {
-  constexpr int kLanes = kSub / 8, kItems = 32 / kLanes, kRounds = 32 / kItems;
-  constexpr int kGroupRows = kFRowsPerThread / kLanes;      // rows of a 16-row group per lane
+__global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGeometry g, FWorkspace w, FinalizeArgs f,
+                                                                             unsigned wbase, unsigned wrem) {
   __shared__ double lsum[kFinWarps];
-  // per-warp staging of the 32 items' broadcast data: a round reads its 4 items with two LDS.128 (one address per
-  // 8-lane group, conflict-free) instead of seven SHFL
+  // per-warp staging of the 32 items' broadcast data
   __shared__ float4 sA[kFinWarps][32];
-  __shared__ int4 sB[kFinWarps][32];
+  __shared__ int2 sB[kFinWarps][32];
+  __shared__ float4 sQ[kFinWarps][32];      // per item: the candidate that passed the re-filter (fast_items)
   // 32-bit index math throughout: B*Npad, B*Mp and the unit count are < 2^31 (f_sizes_ok); a 64-bit division
   // costs ~80 emulated instructions per lane and there were five of them
   const unsigned nrow = (unsigned)g.B * (unsigned)g.N, ncol = (unsigned)g.B * (unsigned)g.M;
   const unsigned row_warps = (nrow + 31u) / 32u;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
-  const int grp = lane / kLanes, sub = lane % kLanes;
+  const int half = lane >> 4, hl = lane & 15;
   const unsigned total_warps = row_warps + (ncol + 31u) / 32u;
-  const unsigned w_begin = (unsigned)(((u64)blockIdx.x * total_warps) / gridDim.x);
-  const unsigned w_end = (unsigned)(((u64)(blockIdx.x + 1) * total_warps) / gridDim.x);
+  // CTA c takes wbase = total / grid items, the first wrem = total % grid CTAs one more (computed on the host: a 64-bit
+  // division here costs ~100 instructions per thread)
+  const unsigned w_begin = blockIdx.x * wbase + min(blockIdx.x, wrem);
+  const unsigned w_end = w_begin + wbase + (blockIdx.x < wrem ? 1u : 0u);
   // warps beyond the CTA's share take the out-of-range item (valid == false on every lane)
   const unsigned wi = w_begin + (unsigned)warp < w_end ? w_begin + (unsigned)warp : total_warps;
   const float coef_grad = 2.f * f.coef_loss;
@@ -565,165 +872,77 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
   const float inf = __int_as_float(0x7f800000);
   float myd = 0.f, wb = 1.f;
   bool valid = false;
+  RMA_TL(w.stats, 4);
   pdl_wait();
   pdl_launch_dependents();   // the backward combine may queue behind us (it waits for our completion itself)
+  RMA_TL(w.stats, 5);
 
-  if (wi < row_warps) {
-    // ---------------------------------------------------------------- rows: lane <-> row, candidates = 64-column tiles
-    const unsigned t = wi * 32u + lane;
+  // Row items and column items alternate over the warp index (row warps read ~10 records per item, column warps
+  // 2 per row block: interleaved, every CTA - and so every SM - carries the same mix and they finish together).
+  const unsigned col_warps = total_warps - row_warps, both = 2u * min(row_warps, col_warps);
+  const bool is_row = wi < both ? (wi & 1u) == 0u : row_warps > col_warps;
+  const unsigned widx = wi < both ? wi >> 1 : wi - (both >> 1);
+  if (is_row) {
+    // ------------------------------------------------------------ rows: lane <-> row, candidates = 16-column groups
+    const unsigned t = widx * 32u + lane;
     valid = t < nrow;
     int b = 0, i = 0;
     float4 rp = make_float4(0.f, 0.f, 0.f, 0.f);
     float M1 = inf, M2 = inf;
     int T1 = 0;
     if (valid) {
-      b = (int)(t / (unsigned)g.N); i = (int)(t - (unsigned)b * (unsigned)g.N);
+      b = (int)fdiv(t, (unsigned)g.N, g.magicN); i = (int)(t - (unsigned)b * (unsigned)g.N);
       rp = w.rowpack[(size_t)b * g.Npad + i];
-      const int rbc = i / g.RC, brb = b * g.nRBC + rbc;
-      const int kfirst = (int)(((unsigned)brb * (unsigned)g.nT) / (unsigned)g.U);
-      const int klast = (int)((((unsigned)brb + 1u) * (unsigned)g.nT - 1u) / (unsigned)g.U);
+      const int rbc = i >> g.rc_shift, brb = b * g.nRBC + rbc;
+      const int kfirst = (int)fdiv((unsigned)brb * (unsigned)g.nT, (unsigned)g.U, g.magicU);
+      const int klast = (int)fdiv(((unsigned)brb + 1u) * (unsigned)g.nT - 1u, (unsigned)g.U, g.magicU);
       const float* top = w.rowtop + ((size_t)brb * g.Smax * g.P * 3) * g.RC + (i - rbc * g.RC);
       const int nseg = (klast - kfirst + 1) * g.P;  // entries: P per segment, consecutive
-      constexpr int kSegBatch = 12;                 // up to 12 entries in flight: one latency for C2 (10)
-      for (int s0 = 0; s0 < nseg; s0 += kSegBatch) {
-        float a1[kSegBatch], a2[kSegBatch];
-        int at[kSegBatch];
-#pragma unroll
-        for (int k = 0; k < kSegBatch; ++k) {
-          const bool on = s0 + k < nseg;
-          const float* tp = top + (size_t)(on ? s0 + k : s0) * (3 * g.RC);
-          a1[k] = on ? tp[0] : inf;
-          at[k] = __float_as_int(tp[g.RC]);
-          a2[k] = on ? tp[2 * g.RC] : inf;
-        }
-#pragma unroll
-        for (int k = 0; k < kSegBatch; ++k) {
-          M2 = fminf(fminf(M2, a2[k]), fmaxf(M1, a1[k]));
-          if (a1[k] < M1) { M1 = a1[k]; T1 = at[k]; }
-        }
-      }
+      if (g.W == 4) scan_row_entries<4 * kFRowsPerWarp>(top, nseg, M1, T1, M2);
+      else if (g.W == 2) scan_row_entries<2 * kFRowsPerWarp>(top, nseg, M1, T1, M2);
+      else scan_row_entries<kFRowsPerWarp>(top, nseg, M1, T1, M2);
     }
-    const float thr = M1 + guard_row(rp.w, M1);
+    const float thr = row_threshold(rp.w, M1);
 #if defined(RMA_B200_EXPERIMENTS) && (defined(RMA_EXP_NO_SLOW) || defined(RMA_EXP_NO_SLOW_ROWS))   // timing experiment only (tools/resolve_variants.py): wrong results for the slow-path items
     const bool fast = valid;
 #else
     const bool fast = valid && M2 > thr;
 #endif
     unsigned best_d = 0xffffffffu, best_j = 0;
+    float4 best_q = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* cq = w.colpack + (size_t)b * g.Mp;
 
-    // Fast path (one candidate sub-tile of kSub columns): kLanes lanes per row, 8 columns per lane, kItems rows per
-    // round.  Inside the sub-tile the same guard applies per COLUMN: every exact minimiser has f_j <= thr, so each
-    // column is first re-filtered with the search's own 3-FFMA chain (bit-identical f; padded columns carry
-    // |y|^2 = 1e30 and never pass) and only the survivors - typically one per row - are evaluated in the exact
-    // difference form; the pass bits are collected branch-free and the exact evaluations sit under one branch.
-    sA[warp][lane] = make_float4(rp.x, rp.y, rp.z, thr);
-    sB[warp][lane] = make_int4(b, T1, fast ? 1 : 0, 0);
+    // Fast path: the one candidate group (tile T1, position in the two tag bits of M1)
+    sA[warp][lane] = make_float4(rp.x, rp.y, rp.z, 0.f);
+    sB[warp][lane] = fast ? make_int2(b * g.Mp + T1 * kFRowTile + (int)(__float_as_uint(M1) & kFRowTagMask) * kFGroup,
+                                      __float_as_int(thr))
+                          : make_int2(0, (int)0xff800000u);
     __syncwarp();
-#pragma unroll 1
-    for (int round = 0; round < kRounds; ++round) {
-      const int src = round * kItems + grp;
-      const float4 sa = sA[warp][src];
-      const int4 sb4 = sB[warp][src];
-      const float x = sa.x, y = sa.y, z = sa.z, sthr = sa.w;
-      unsigned d = 0xffffffffu, dj = 0xffffffffu;
-      if (sb4.z) {
-        const int j0 = sb4.y * kSub + sub;
-        const float4* cq = w.colpack + (size_t)sb4.x * g.Mp + j0;
-        float4 q[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) q[c] = cq[kLanes * c];
-        unsigned pass = 0u;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float fj = __fmaf_rn(x, q[c].x, __fmaf_rn(y, q[c].y, __fmaf_rn(z, q[c].z, q[c].w)));
-          pass |= fj <= sthr ? 1u << c : 0u;
-        }
-        while (pass) {                                     // ascending columns: strict '<' keeps the first
-          const int c = __ffs(pass) - 1;
-          pass &= pass - 1u;
-          const unsigned dc = __float_as_uint(sqdist_q(x, y, z, cq[kLanes * c]));
-          if (dc < d) { d = dc; dj = (unsigned)(j0 + kLanes * c); }
-        }
-      }
-      unsigned rd, rj;
-      round_result<kLanes>(d, dj, rd, rj);
-      if (lane / kItems == round) { best_d = rd; best_j = rj; }
-    }
+    fast_items<false>(w.colpack, sA[warp], sB[warp], sQ[warp], lane, best_d, best_j, best_q);
+    best_j -= (unsigned)(b * g.Mp);
 
-    // Slow path (guard failed: several tiles within the rounding error of the smallest).  Every candidate tile lies in
-    // an entry (a run of up to 16 tiles of one search segment) whose smallest tile minimum is within the guard, so the
-    // warp re-evaluates those entries' tiles; the lowest column among the lanes that hold the minimum = torch.min's
-    // first index.
+    // Slow path (guard failed: several groups within the rounding error of the smallest).  Every candidate group lies
+    // in an entry (a run of up to 16 tiles of one search segment) whose smallest group minimum is within the guard: an
+    // entry whose second smallest is not contributes its one recorded group, otherwise all of its groups; a half-warp
+    // re-filters and evaluates one group per round.  The lowest column among the lanes that hold the minimum =
+    // torch.min's first index.
     unsigned slow = __ballot_sync(full, valid && !fast);
     if (slow && lane == 0) atomicAdd(w.stats + 0, (unsigned)__popc(slow));
     while (slow) {
       const int src = __ffs(slow) - 1; slow &= slow - 1;
-      const int sb = __shfl_sync(full, b, src), si = __shfl_sync(full, i, src);
-      const float sthr = __shfl_sync(full, thr, src);
-      const float x = __shfl_sync(full, rp.x, src), y = __shfl_sync(full, rp.y, src), z = __shfl_sync(full, rp.z, src);
-      const int srbc = si / g.RC;
-      const unsigned sbrb = (unsigned)(sb * g.nRBC + srbc);
-      const unsigned u0 = sbrb * (unsigned)g.nT, u1 = u0 + (unsigned)g.nT;       // the row block's units [u0, u1)
-      const unsigned kfirst = u0 / (unsigned)g.U, klast = (u1 - 1u) / (unsigned)g.U;
-      const float* top = w.rowtop + ((size_t)sbrb * g.Smax * g.P * 3) * g.RC + (si - srbc * g.RC);
-      const float4* cq = w.colpack + (size_t)sb * g.Mp;
-      unsigned bd = 0xffffffffu, bj = 0xffffffffu;
-      // One sub-tile for this lane's group: the fast path's re-filter (f_j <= thr, bit-identical to the search's
-      // chain; padded columns never pass) in front of the exact evaluation, 8 loads in flight per lane.
-      auto eval_tile = [&](unsigned tile) {
-        const int j0 = (int)tile * kSub + sub;
-        float4 q[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) q[c] = cq[j0 + kLanes * c];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float fj = __fmaf_rn(x, q[c].x, __fmaf_rn(y, q[c].y, __fmaf_rn(z, q[c].z, q[c].w)));
-          if (fj <= sthr) {
-            const unsigned d = __float_as_uint(sqdist_q(x, y, z, q[c])), jc = (unsigned)(j0 + kLanes * c);
-            if (d < bd || (d == bd && jc < bj)) { bd = d; bj = jc; }
-          }
-        }
-      };
-      const unsigned nent = (klast - kfirst + 1u) * (unsigned)g.P;
-      for (unsigned base = 0; base < nent; base += 32u) {
-        // one entry per lane, all in flight; empty entries hold inf
-        const unsigned e = base + (unsigned)lane;
-        const float* tp = top + (size_t)(e < nent ? e : base) * (3 * g.RC);
-        const float a1 = e < nent ? tp[0] : inf;
-        const unsigned t1 = (unsigned)__float_as_int(tp[g.RC]);
-        const float a2 = e < nent ? tp[2 * g.RC] : inf;
-        const bool hit = a1 <= sthr;
-        // An entry whose SECOND smallest tile minimum is above the threshold has one candidate tile, the recorded one:
-        // the usual case (two near-tied tiles in two entries) then costs a single round.
-        const unsigned singles = __ballot_sync(full, hit && !(a2 <= sthr));
-        unsigned wholes = __ballot_sync(full, hit && a2 <= sthr);
-        const int nsingle = __popc(singles);
-        for (int r = 0; r < nsingle; r += kItems) {       // kItems sub-tiles per round, one per lane group
-          const int idx = r + grp;
-          const unsigned from = idx < nsingle ? __fns(singles, 0, idx + 1) : 0u;
-          const unsigned tile = __shfl_sync(full, t1, (int)from);
-          if (idx < nsingle) eval_tile(tile);
-        }
-        while (wholes) {                                  // every sub-tile of the entry
-          const unsigned he = base + (unsigned)__ffs(wholes) - 1u; wholes &= wholes - 1u;
-          const unsigned k = kfirst + he / (unsigned)g.P, pe = he % (unsigned)g.P;
-          const unsigned ua = max(k * (unsigned)g.U, u0), ub = min((k + 1u) * (unsigned)g.U, u1);   // the segment's units
-          const unsigned ta = ua - u0 + pe * kFSubTiles;              // first 64-column tile of the entry, within the row block
-          const unsigned tb = min(ta + kFSubTiles, ub - u0);          // the entry's tiles [ta, tb)
-          constexpr unsigned kPer = kFRowTile / kSub;                  // sub-tiles per tile
-          for (unsigned tr = ta * kPer; tr < tb * kPer; tr += (unsigned)kItems)
-            if (tr + (unsigned)grp < tb * kPer) eval_tile(tr + (unsigned)grp);
-        }
-      }
-      const unsigned mn = __reduce_min_sync(full, bd);
-      const unsigned jm = __reduce_min_sync(full, bd == mn ? bj : 0xffffffffu);
-      if (lane == src) { best_d = mn; best_j = jm; }
+      unsigned sd, sj;
+      float4 sq;
+      row_slow_item(w.rowtop, w.colpack, g.RC, g.nRBC, g.nT, g.U, g.Smax, g.P, g.Mp, __shfl_sync(full, b, src),
+                    __shfl_sync(full, i, src), __shfl_sync(full, thr, src), __shfl_sync(full, rp.x, src),
+                    __shfl_sync(full, rp.y, src), __shfl_sync(full, rp.z, src), sd, sj, sq);
+      if (lane == src) { best_d = sd; best_j = sj; best_q = sq; }
     }
 
     myd = __uint_as_float(best_d);
     wb = (valid && f.batch_weight) ? f.batch_weight[b] : 1.f;
     // no candidate at all happens only for NaN coordinates (every comparison fails): NaN distance, index 0
-    const int j = best_d == 0xffffffffu ? 0 : (int)best_j;
+    const bool none = best_d == 0xffffffffu;
+    const int j = none ? 0 : (int)best_j;
     if (valid) {
       if (f.dist1) f.dist1[t] = myd;
       if (f.idx1) f.idx1[t] = j;
@@ -731,7 +950,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
     if (f.own_x || f.scat_y) {
       float vx = 0.f, vy = 0.f, vz = 0.f;
       if (valid) {
-        const float4 q = w.colpack[(size_t)b * g.Mp + j];
+        const float4 q = none ? cq[0] : best_q;
         const float cg = coef_grad * wb;
         vx = cg * __fmaf_rn(0.5f, q.x, rp.x);
         vy = cg * __fmaf_rn(0.5f, q.y, rp.y);
@@ -742,30 +961,31 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
     }
   } else {
     // ------------------------------------------------------------- columns: lane <-> column, candidates = 16-row groups
-    const unsigned t = (wi - row_warps) * 32u + lane;
+    const unsigned t = widx * 32u + lane;
     valid = t < ncol;
     int b = 0, j = 0;
     float4 cq = make_float4(0.f, 0.f, 0.f, 0.f);
     float M1 = inf, M2 = inf;
     int R1 = 0;
     if (valid) {
-      b = (int)(t / (unsigned)g.M); j = (int)(t - (unsigned)b * (unsigned)g.M);
+      b = (int)fdiv(t, (unsigned)g.M, g.magicM); j = (int)(t - (unsigned)b * (unsigned)g.M);
       cq = w.colpack[(size_t)b * g.Mp + j];
-      const float* rec = w.colrec + (size_t)b * g.nRB * kFColTop * g.Mp + j;
+      const float2* rec = reinterpret_cast<const float2*>(w.colrec) + (size_t)b * g.nRB * g.Mp + j;
       constexpr int kRbBatch = 8;                   // records of 8 row blocks in flight (C2: all of them)
       for (int r0 = 0; r0 < g.nRB; r0 += kRbBatch) {
-        float a1[kRbBatch], a2[kRbBatch];
+        float2 a[kRbBatch];
+        const float2* rp_ = rec + (size_t)r0 * g.Mp;
 #pragma unroll
         for (int k = 0; k < kRbBatch; ++k) {
           const bool on = r0 + k < g.nRB;
-          const float* rp_ = rec + (size_t)(on ? r0 + k : r0) * kFColTop * g.Mp;
-          a1[k] = on ? rp_[0] : inf;
-          a2[k] = on ? rp_[g.Mp] : inf;
+          a[k] = *(on ? rp_ : rec);
+          a[k] = on ? a[k] : make_float2(inf, inf);
+          rp_ += g.Mp;
         }
 #pragma unroll
         for (int k = 0; k < kRbBatch; ++k) {
-          M2 = fminf(fminf(M2, a2[k]), fmaxf(M1, a1[k]));
-          if (a1[k] < M1) { M1 = a1[k]; R1 = r0 + k; }
+          M2 = fminf(fminf(M2, a[k].y), fmaxf(M1, a[k].x));
+          if (a[k].x < M1) { M1 = a[k].x; R1 = r0 + k; }
         }
       }
     }
@@ -777,45 +997,15 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
 #endif
     const int G1 = (R1 * 32 + (int)(__float_as_uint(M1) & 31u)) * kFRowsPerThread;   // first row of the candidate group
     unsigned best_d = 0xffffffffu, best_i = 0;
+    float4 best_p = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // Fast path (one candidate group of 16 rows): kLanes lanes per column, kGroupRows rows per lane, kItems columns per
-    // round.  As for the rows: inside the candidate group the guard applies per ROW (g_i = fl(f + |x_i|^2) <= thr for
-    // every exact minimiser; padded rows carry |x|^2 = 1e30), so the 16 rows are re-filtered with the search's chain
-    // and only the survivors are evaluated exactly.
-    sA[warp][lane] = make_float4(cq.x, cq.y, cq.z, cq.w);
-    sB[warp][lane] = make_int4(b, G1, fast ? 1 : 0, __float_as_int(thr));
+    // Fast path (one candidate group of 16 rows).  As for the rows: inside the candidate group the guard applies per
+    // ROW (g_i = fl(f + |x_i|^2) <= thr for every exact minimiser; padded rows carry |x|^2 = 1e30).
+    sA[warp][lane] = cq;
+    sB[warp][lane] = fast ? make_int2(b * g.Npad + G1, __float_as_int(thr)) : make_int2(0, (int)0xff800000u);
     __syncwarp();
-#pragma unroll 1
-    for (int round = 0; round < kRounds; ++round) {
-      const int src = round * kItems + grp;
-      const float4 q = sA[warp][src];
-      const int4 sb4 = sB[warp][src];
-      const float sthr = __int_as_float(sb4.w);
-      unsigned d = 0xffffffffu, di = 0xffffffffu;
-      if (sb4.z) {
-        const int r0 = sb4.y + sub;
-        const float4* rq = w.rowpack + (size_t)sb4.x * g.Npad + r0;
-        float4 pr[kGroupRows];
-#pragma unroll
-        for (int k = 0; k < kGroupRows; ++k) pr[k] = rq[kLanes * k];
-        unsigned pass = 0u;
-#pragma unroll
-        for (int k = 0; k < kGroupRows; ++k) {
-          const float gk = __fadd_rn(__fmaf_rn(pr[k].x, q.x, __fmaf_rn(pr[k].y, q.y, __fmaf_rn(pr[k].z, q.z, q.w))), pr[k].w);
-          pass |= gk <= sthr ? 1u << k : 0u;
-        }
-        while (pass) {                                     // ascending rows: strict '<' keeps the first
-          const int k = __ffs(pass) - 1;
-          pass &= pass - 1u;
-          const float4 pk = rq[kLanes * k];
-          const unsigned dk = __float_as_uint(sqdist_q(pk.x, pk.y, pk.z, q));
-          if (dk < d) { d = dk; di = (unsigned)(r0 + kLanes * k); }
-        }
-      }
-      unsigned rd, ri;
-      round_result<kLanes>(d, di, rd, ri);
-      if (lane / kItems == round) { best_d = rd; best_i = ri; }
-    }
+    fast_items<true>(w.rowpack, sA[warp], sB[warp], sQ[warp], lane, best_d, best_i, best_p);
+    best_i -= (unsigned)(b * g.Npad);
 
     // Slow path: every row block's smallest entry within the guard is a candidate group; a second-smallest entry
     // within the guard means the row block may hold more than the recorded two, so all of its 512 rows are re-evaluated.
@@ -823,44 +1013,20 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
     if (slow && lane == 0) atomicAdd(w.stats + 1, (unsigned)__popc(slow));
     while (slow) {
       const int src = __ffs(slow) - 1; slow &= slow - 1;
-      const int sb = __shfl_sync(full, b, src), sj = __shfl_sync(full, j, src);
-      const float sthr = __shfl_sync(full, thr, src);
-      const float4 q = make_float4(__shfl_sync(full, cq.x, src), __shfl_sync(full, cq.y, src),
-                                   __shfl_sync(full, cq.z, src), 0.f);
-      const float* rec = w.colrec + (size_t)sb * g.nRB * kFColTop * g.Mp + sj;
-      unsigned bd = 0xffffffffu, bi = 0xffffffffu;
-      const int nE = g.nRB * kFColTop;
-      for (int base = 0; base < nE; base += 32) {
-        const int e = base + lane;
-        const float p = e < nE ? rec[(size_t)e * g.Mp] : inf;
-        unsigned hits = __ballot_sync(full, p <= sthr);
-        while (hits) {
-          const int hl = __ffs(hits) - 1; hits &= hits - 1;
-          const int he = base + hl, hrb = he / kFColTop, hk = he - hrb * kFColTop;
-          const unsigned pbits = __float_as_uint(__shfl_sync(full, p, hl));
-          int first, n;
-          if (hk < kFColTop - 1) { first = (hrb * 32 + (int)(pbits & 31u)) * kFRowsPerThread; n = kFRowsPerThread; }
-          else { first = hrb * kFRowsPerWarp; n = kFRowsPerWarp; if (lane == 0) atomicAdd(w.stats + 2, 1u); }
-          unsigned dm = 0xffffffffu, im = 0xffffffffu;
-          for (int o = lane; o < n; o += 32) {
-            const int row = first + o;
-            if (row < g.N) {
-              const float4 pr = w.rowpack[(size_t)sb * g.Npad + row];
-              const unsigned d = __float_as_uint(sqdist_q(pr.x, pr.y, pr.z, q));
-              if (d < dm) { dm = d; im = (unsigned)row; }
-            }
-          }
-          const unsigned mn = __reduce_min_sync(full, dm);
-          const unsigned ii = __reduce_min_sync(full, dm == mn ? im : 0xffffffffu);
-          if (mn < bd || (mn == bd && ii < bi)) { bd = mn; bi = ii; }
-        }
+      unsigned sd, si_;
+      col_slow_item(w.colrec, w.rowpack, w.stats, g.nRB, g.Mp, g.Npad, g.N, __shfl_sync(full, b, src),
+                    __shfl_sync(full, j, src), __shfl_sync(full, thr, src), __shfl_sync(full, cq.x, src),
+                    __shfl_sync(full, cq.y, src), __shfl_sync(full, cq.z, src), sd, si_);
+      if (lane == src) {
+        best_d = sd; best_i = si_;
+        if (sd != 0xffffffffu) best_p = w.rowpack[(size_t)b * g.Npad + si_];
       }
-      if (lane == src) { best_d = bd; best_i = bi; }
     }
 
     myd = __uint_as_float(best_d);
     wb = (valid && f.batch_weight) ? f.batch_weight[b] : 1.f;
-    const int i = best_d == 0xffffffffu ? 0 : (int)best_i;
+    const bool none = best_d == 0xffffffffu;
+    const int i = none ? 0 : (int)best_i;
     if (valid) {
       if (f.dist2) f.dist2[t] = myd;
       if (f.idx2) f.idx2[t] = i;
@@ -868,7 +1034,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
     if (f.own_y || f.scat_x) {
       float vx = 0.f, vy = 0.f, vz = 0.f;
       if (valid) {
-        const float4 p = w.rowpack[(size_t)b * g.Npad + i];
+        const float4 p = none ? w.rowpack[(size_t)b * g.Npad] : best_p;
         // d/dy_j |y_j - x_i|^2 = 2 (y_j - x_i) = -2 (x_i - y_j)
         const float cg = coef_grad * wb;
         vx = -cg * __fmaf_rn(0.5f, cq.x, p.x);
@@ -893,6 +1059,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       atomicAdd(f.loss, (float)(tot * (double)f.coef_loss));
     }
   }
+  RMA_TL(w.stats, 6);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -927,18 +1094,12 @@ static int f_caps(int* sms, int* occ) {
     if (m) { *sms = (int)(m >> 8); *occ = (int)(m & 0xffu); return 0; }
   }
   RMA_CUDA_TRY(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
-  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<kFSubLarge, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)f_smem(4)));
-  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<kFSubSmall, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)f_smem(4)));
-  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<kFSubSmall, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)f_smem(2)));
-  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<kFSubSmall, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)f_smem(1)));
+  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem(4)));
+  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem(2)));
+  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem(1)));
   // occupancy of the 4-warp CTA; the 2- and 1-warp CTAs use half / a quarter of its registers and shared memory and
   // are launch-bounded to 2x / 4x as many resident CTAs (the same warps per SM)
-  RMA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, chamfer_fsearch_kernel<kFSubLarge, 4>, kFThreads,
-                                                             f_smem(4)));
+  RMA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, chamfer_fsearch_kernel<4>, kFThreads, f_smem(4)));
   if (*occ < 1) *occ = 1;
   if (*occ > 255) *occ = 255;
   if (dev >= 0 && dev < 64) memo[dev].store(((unsigned)*sms << 8) | (unsigned)*occ, std::memory_order_release);
@@ -1003,22 +1164,18 @@ int f_launch_search(int B, int N, int M, int unit_run, void* workspace, size_t w
   FGeometry g; FWorkspace w;
   if (int e = f_setup(B, N, M, unit_run, workspace, workspace_bytes, &g, &w)) return e;
   FSearchArgs a;
-  a.rowsoa = w.rowsoa; a.colpair = w.colpair; a.rowtop = w.rowtop; a.colrec = w.colrec;
+  a.rowsoa = w.rowsoa; a.colpair = w.colpair; a.rowtop = w.rowtop; a.colrec = w.colrec; a.stats = w.stats;
   a.N = N; a.M = M; a.nRB = g.nRB; a.Npad = g.Npad; a.nRBC = g.nRBC; a.nT = g.nT; a.Mp = g.Mp;
   a.U = g.U; a.Smax = g.Smax; a.P = g.P; a.units = g.units();
   const long long ctas = (a.units + g.U - 1) / g.U;
   if (ctas > 0x7fffffffLL) return RMA_E_BADARG;
-  const bool small = f_sub_for(N, M) == kFSubSmall;
   cudaStream_t st = (cudaStream_t)stream_;
-  // clouds of <= 1024 rows always take 32-column sub-tiles (f_sub_for: min(N, M) <= 4096)
-  if (g.W == 4 && !small)
-    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<kFSubLarge, 4>, (unsigned)ctas, 128u, f_smem(4), st, a));
-  else if (g.W == 4)
-    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<kFSubSmall, 4>, (unsigned)ctas, 128u, f_smem(4), st, a));
+  if (g.W == 4)
+    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<4>, (unsigned)ctas, 128u, f_smem(4), st, a));
   else if (g.W == 2)
-    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<kFSubSmall, 2>, (unsigned)ctas, 64u, f_smem(2), st, a));
+    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<2>, (unsigned)ctas, 64u, f_smem(2), st, a));
   else
-    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<kFSubSmall, 1>, (unsigned)ctas, 32u, f_smem(1), st, a));
+    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<1>, (unsigned)ctas, 32u, f_smem(1), st, a));
   return RMA_OK;
 }
 
@@ -1032,12 +1189,8 @@ int f_launch_resolve(int B, int N, int M, int unit_run, const FinalizeArgs& f, v
   long long grid = grid_for(warps, kFinWarps);            // one CTA per 8 items when that is more than one wave
   const long long wave = (long long)sms * 4;              // resident resolve CTAs (launch bounds: 4 per SM)
   if (grid <= wave) grid = warps < wave ? warps : wave;   // single wave: the same number of CTAs on every SM
-  if (f_sub_for(N, M) == kFSubSmall)
-    RMA_CUDA_TRY(launch_dep(pdl_site(4), chamfer_fresolve_kernel<kFSubSmall>, (unsigned)grid,
-                            (unsigned)(kFinWarps * 32), 0, (cudaStream_t)stream_, g, w, f));
-  else
-    RMA_CUDA_TRY(launch_dep(pdl_site(4), chamfer_fresolve_kernel<kFSubLarge>, (unsigned)grid,
-                            (unsigned)(kFinWarps * 32), 0, (cudaStream_t)stream_, g, w, f));
+  RMA_CUDA_TRY(launch_dep(pdl_site(4), chamfer_fresolve_kernel, (unsigned)grid, (unsigned)(kFinWarps * 32), 0,
+                          (cudaStream_t)stream_, g, w, f, (unsigned)(warps / grid), (unsigned)(warps % grid)));
   return RMA_OK;
 }
 
@@ -1051,4 +1204,27 @@ int f_read_stats(void* workspace, int B, int N, int M, int unit_run, unsigned* o
   return RMA_OK;
 }
 
+#ifdef RMA_B200_TIMELINE
+// tools/ only: copy the 8 (min, max) timestamp pairs to the host and reset them
+int f_timeline_read(void* workspace, int B, int N, int M, int unit_run, unsigned long long* out16_host, void* stream_) {
+  FGeometry g;
+  if (int e = f_geometry(B, N, M, unit_run, &g, nullptr)) return e;
+  FWorkspace w = f_carve(g, workspace);
+  cudaStream_t st = (cudaStream_t)stream_;
+  RMA_CUDA_TRY(cudaMemcpyAsync(out16_host, w.stats + 8, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  RMA_CUDA_TRY(cudaStreamSynchronize(st));
+  unsigned long long init[16];
+  for (int k = 0; k < 8; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
+  RMA_CUDA_TRY(cudaMemcpyAsync(w.stats + 8, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  RMA_CUDA_TRY(cudaStreamSynchronize(st));
+  return RMA_OK;
+}
+#endif
+
 }  // namespace rma
+
+#ifdef RMA_B200_TIMELINE
+extern "C" int rma_debug_timeline_read(void* workspace, int B, int N, int M, unsigned long long* out16_host, void* stream) {
+  return rma::f_timeline_read(workspace, B, N, M, 0, out16_host, stream);
+}
+#endif

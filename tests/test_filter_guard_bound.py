@@ -33,12 +33,15 @@ def filter_f(x, y):                    # x [..,3], y [..,3] broadcastable, fp32
     return fma32(x[..., 0], q[..., 0], fma32(x[..., 1], q[..., 1], fma32(x[..., 2], q[..., 2], w)))
 
 
+SQRT_LO = F(1.0 - 3e-7)                # the device uses sqrt.approx (<= 2 ulp): model its worst case from below
+
+
 def guard_row(u, mt):                  # chamfer_filter.cu guard_row, fp32 arithmetic
     u, mt = u.astype(F), mt.astype(F)
     D0 = np.maximum(mt + u, F(0))
     Dub = F(1.001) * D0 + F(1e-5) * u
-    a = np.sqrt(u) * F(1.0001)
-    beta = a + np.sqrt(Dub) * F(1.0001)
+    a = np.sqrt(u) * SQRT_LO * F(1.0001)
+    beta = a + np.sqrt(Dub) * SQRT_LO * F(1.0001)
     return (F(12.3) * beta * (beta + a) + F(10.3) * Dub) * F(EPS * 1.01) + F(1e-30)
 
 
@@ -46,8 +49,8 @@ def guard_col(w, mt):                  # chamfer_filter.cu guard_col
     w, mt = w.astype(F), mt.astype(F)
     D0 = np.maximum(mt, F(0))
     Dub = F(1.001) * D0 + F(1e-5) * w
-    bn = np.sqrt(w) * F(1.0001)
-    alpha = bn + np.sqrt(Dub) * F(1.0001)
+    bn = np.sqrt(w) * SQRT_LO * F(1.0001)
+    alpha = bn + np.sqrt(Dub) * SQRT_LO * F(1.0001)
     return (F(12.3) * bn * (bn + alpha) + F(6.3) * alpha * alpha + F(12.5) * Dub) * F(EPS * 1.01) + Dub * F(7.8e-6) + F(1e-30)
 
 
@@ -108,3 +111,39 @@ def test_exact_minimisers_are_always_candidates():
             thr = f.min(1) + guard_row(norm2_rn(x), f.min(1))
             exact_min = d == d.min(1, keepdims=True)
             assert np.all(f[exact_min] <= np.broadcast_to(thr[:, None], f.shape)[exact_min])
+
+
+def row_threshold(u, M1):              # chamfer_filter.cu row_threshold, fp32 arithmetic
+    u, M1 = u.astype(F), M1.astype(F)
+    return (M1 + (guard_row(u, M1) * F(1.0001) + F(1.2e-6) * np.abs(M1))).astype(F)
+
+
+def test_tagged_group_minima_keep_every_exact_minimiser():
+    """Row direction as the search records it: the minimum of f over each 16-column group carries the group's position
+    in its 64-column tile in the two low mantissa bits, M1 = the smallest TAGGED group minimum, thr = row_threshold(u, M1).
+    Every exact minimiser j* must (a) sit in a group whose tagged minimum is <= thr (so the resolve's candidate test on
+    the recorded values finds the group) and (b) pass the per-column re-filter f_j* <= thr."""
+    rng = np.random.default_rng(11)
+    for kind, scale in (("cube", 1.0), ("offset", 1.0), ("near", 1e3), ("cube", 1e-5), ("skewed", 1.0), ("cube", 1e4)):
+        for _ in range(25):
+            n, m = 48, 2048
+            x, _ = _pairs(rng, n, kind, scale)
+            if kind == "near":
+                y = (x[rng.integers(0, n, m)].astype(np.float64) + rng.normal(size=(m, 3)) * 1e-6 * scale).astype(F)
+            else:
+                _, y = _pairs(rng, m, kind, scale)
+            f = filter_f(x[:, None, :], y[None, :, :])                       # [n, m]
+            gm = f.reshape(n, m // 16, 16).min(2)                            # group minima
+            gid = (np.arange(m // 16) % 4).astype(np.uint32)
+            tagged = ((gm.view(np.uint32) & np.uint32(0xFFFFFFFC)) | gid[None, :]).view(F)
+            M1 = tagged.min(1)
+            thr = row_threshold(norm2_rn(x), M1)
+            dx = (x[:, None, :] - y[None, :, :]).astype(F)
+            d = fma32(dx[..., 2], dx[..., 2], fma32(dx[..., 1], dx[..., 1], (dx[..., 0] * dx[..., 0]).astype(F)))
+            exact_min = d == d.min(1, keepdims=True)
+            thr_b = np.broadcast_to(thr[:, None], f.shape)
+            assert np.all(f[exact_min] <= thr_b[exact_min])
+            tagged_of_col = np.repeat(tagged, 16, axis=1)
+            assert np.all(tagged_of_col[exact_min] <= thr_b[exact_min])
+            # the tag moves a value by less than 4 ulp
+            assert np.all(np.abs(tagged.astype(np.float64) - gm.astype(np.float64)) <= 2.0 ** -21 * np.abs(gm.astype(np.float64)))

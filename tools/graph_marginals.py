@@ -45,6 +45,12 @@ def main():
         assert lib.rma_chamfer_cd_forward(P(xd), *xs, P(yd), *ys, B, N, M, P(loss), None, None, None, None,
                                           P(gx), P(sx), P(gy), P(sy), P(ws), wsb, None, st()) == 0
 
+    d1 = torch.empty(B, N, device=dev); d2 = torch.empty(B, M, device=dev)
+    i1 = torch.empty(B, N, dtype=torch.int32, device=dev); i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
+
+    def k_fin():
+        assert lib.rma_chamfer_finalize(B, N, M, P(d1), P(d2), P(i1), P(i2), P(ws), wsb, None, st()) == 0
+
     def k_bwd():
         assert lib.rma_chamfer_cd_backward(P(gx), P(sx), B * N, P(gy), P(sy), B * M, P(one), P(ox), P(oy), st()) == 0
 
@@ -58,6 +64,8 @@ def main():
         "prep+search+resolve (cd_forward)": [k_fwd],
         "cd_forward+cd_backward": [k_fwd, k_bwd],
         "public API step (adds autograd's seed fill)": [k_step],
+        "prep+search+finalize (dist, idx; no gradients)": [k_prep, k_search, k_fin],
+        "finalize x8 (same records)": [k_fin] * 8,
         "prep": [k_prep],
         "cd_backward": [k_bwd],
     }

@@ -16,8 +16,6 @@ from rma_net_b200 import _lib, build as b  # noqa: E402
 
 VARIANTS = {
     "base": [],
-    "sub64": ["-DRMA_F_SUBSWITCH=0"],                 # 64-column row sub-tiles at every size
-    "sub32": ["-DRMA_F_SUBSWITCH=1073741824"],        # 32-column row sub-tiles at every size
     "noslow": ["-DRMA_B200_EXPERIMENTS", "-DRMA_EXP_NO_SLOW"],
     "noslow_rows": ["-DRMA_B200_EXPERIMENTS", "-DRMA_EXP_NO_SLOW_ROWS"],
     "noslow_cols": ["-DRMA_B200_EXPERIMENTS", "-DRMA_EXP_NO_SLOW_COLS"],
