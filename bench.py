@@ -452,8 +452,8 @@ def run_ours(args):
     # exactly K steps.
     W = max(args.warmup, 3)
     set_bytes = 4 * (xd.numel() + yd.numel()) * 2               # clouds + their gradients
-    R = max(2, int(2.2 * L2_BYTES // set_bytes) + 1)
-    sets = []
+    R = args.sets if args.sets > 0 else max(2, int(2.2 * L2_BYTES // set_bytes) + 1)
+    sets, keep_alive = [], []
     gen = torch.Generator().manual_seed(1234 + rank)
     for r in range(R):
         if r == 0:
@@ -468,6 +468,7 @@ def run_ours(args):
             loss_r = loss_on_cd(xr_, yr_)
             loss_r.backward()
             return loss_r
+        keep_alive.append((xr_, yr_))          # a graph holds raw pointers: its inputs must outlive the closure
         for _ in range(2):
             step_r()
         if use_graph:
@@ -820,7 +821,7 @@ def run_ours(args):
                    "input_sets": R,
                    "cuda_graph": bool(use_graph),
                    "search_launch": {"kernel": search_kernel, "ctas": ctas.value, "threads": thr.value,
-                                     ("tiles64_per_cta" if filt == 1 else "column_splits"): spl.value,
+                                     ("units32_per_cta" if filt == 1 else "column_splits"): spl.value,
                                      "ctas_per_sm": occ.value},
                    "search_path": ("filter (expanded form, 3 FFMA + 1 FADD per pair) + exact difference-form resolve"
                                    if filt == 1 else "exact difference form (6 FP32 ops per pair)"),
@@ -889,6 +890,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(k for k in WORKLOADS if k.startswith("C")))
+    ap.add_argument("--sets", type=int, default=0, help="rotating input sets of the headline leg (default: enough for "
+                    "2.2 x L2; a small number only for profiler runs, whose line is not a bench value)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C3 / C4 / C5 legs of the `secondary` object")

@@ -45,7 +45,7 @@ def main():
         P = lambda t: ctypes.c_void_p(t.data_ptr())
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         xs, ys = xd.stride(), yd.stride()
-        for run in (0, 7, 14):
+        for run in (0, 14, 28):
             o = ctypes.byref(_lib.ChamferOpts(0, run, 0))
             wsb = lib.rma_chamfer_workspace_bytes(B, N, M, o)
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
