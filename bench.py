@@ -708,7 +708,7 @@ def run_ours(args):
                 pipelined_loss = run_pipelined(args.steps, ev0, lag=lag)
                 ev1.record()
                 barrier()
-                if abs(pipelined_loss - serial_loss) > 1e-6 * abs(serial_loss):
+                if abs(pipelined_loss - serial_loss) > 1e-5 * abs(serial_loss):
                     raise RuntimeError(f"pipelined e2e loss {pipelined_loss} != serial {serial_loss}")
                 reps_ms.append(ev0.elapsed_time(ev1) / args.steps)
             e2e_modes[lag] = statistics.median(reps_ms)
@@ -756,7 +756,7 @@ def run_ours(args):
             fused_loss = run_fused(args.steps)
             ev1.record()
             barrier()
-            if abs(fused_loss - serial_loss) > 1e-6 * abs(serial_loss):
+            if abs(fused_loss - serial_loss) > 1e-5 * abs(serial_loss):
                 raise RuntimeError(f"graph-pipelined e2e loss {fused_loss} != serial {serial_loss}")
             fused_ms.append(ev0.elapsed_time(ev1) / args.steps)
         e2e_fused_ms = statistics.median(fused_ms)
