@@ -56,25 +56,15 @@ constexpr int kFGroupsPerTile = kFRowTile / kFGroup;    // 4: two tag bits
 constexpr unsigned kFRowTagMask = (unsigned)kFGroupsPerTile - 1u;
 constexpr int kFSubTiles = 16;                          // 64-column tiles per row-direction entry (sub-segment): bounds
                                                         // the slow path's re-evaluation to 1024 columns per candidate
-#ifndef RMA_F_FENCE_KIND
-#define RMA_F_FENCE_KIND 2
-#endif
-#if RMA_F_FENCE_KIND == 0
+// Scheduling fence between the FFMA2 runs and the minima of a loop body: an instruction
+// ptxas does not move arithmetic across.  griddepcontrol.launch_dependents (SASS PREEXIT) is one - a repeated call is a
+// no-op for the launch logic - and the cheapest of those tried (pmevent also fences but stalls longer; __syncwarp,
+// %clock reads, nanosleep and fence.proxy.async do not stop the scheduler).  -DRMA_F_NO_FENCE builds the unfenced loop
+// (tools/ A/B).
+#ifdef RMA_F_NO_FENCE
 #define RMA_F_FENCE() ((void)0)
-#elif RMA_F_FENCE_KIND == 1
-#define RMA_F_FENCE() __syncwarp()
-#elif RMA_F_FENCE_KIND == 2
+#else
 #define RMA_F_FENCE() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
-#elif RMA_F_FENCE_KIND == 3
-#define RMA_F_FENCE() asm volatile("bar.warp.sync 0xffffffff;" ::: "memory")
-#elif RMA_F_FENCE_KIND == 4
-#define RMA_F_FENCE() do { unsigned c_; asm volatile("mov.u32 %0, %%clock;" : "=r"(c_) :: "memory"); } while (0)
-#elif RMA_F_FENCE_KIND == 5
-#define RMA_F_FENCE() asm volatile("pmevent 0;" ::: "memory")
-#elif RMA_F_FENCE_KIND == 6
-#define RMA_F_FENCE() asm volatile("nanosleep.u32 0;" ::: "memory")
-#elif RMA_F_FENCE_KIND == 7
-#define RMA_F_FENCE() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
 #endif
 #ifndef RMA_F_CHUNK
 #define RMA_F_CHUNK 1024
@@ -472,9 +462,7 @@ __global__ void __launch_bounds__(32 * kW, RMA_F_MINCTAS * 4 / kW) chamfer_fsear
           top2_insert(p1, p2, pv.y);
           top2_insert(p1, p2, pv.z);
           top2_insert(p1, p2, pv.w);
-#ifndef RMA_F_NO_TAIL_FENCE
           RMA_F_FENCE();
-#endif
         };
 
         // One 16-column group per trip (four bodies).  Operands are prefetched one body ahead into the OTHER register

@@ -15,6 +15,7 @@ from rma_net_b200 import _lib, build as b  # noqa: E402
 
 VARIANTS = {
     "base": [],
+    "nofence": ["-DRMA_F_NO_FENCE"],              # the loop as ptxas schedules it by itself (FFMA2 / FMNMX3 alternating)
     "occ3": ["-DRMA_F_MINCTAS=3", "-DRMA_F_CHUNK=512"],
     "chunk512": ["-DRMA_F_CHUNK=512"],
 }
