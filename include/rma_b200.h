@@ -63,7 +63,7 @@ int rma_b200_device_info(int* sm_count, int* clock_khz, int* cc_major, int* cc_m
 #define RMA_CHAMFER_PATH_FILTER 2
 typedef struct rma_chamfer_opts {
   int32_t path;               /* RMA_CHAMFER_PATH_*: force one search implementation (parity tests, A/B timing) */
-  int32_t unit_run;           /* > 0: 64-column tiles per search CTA (filter path) / column splits (exact path) */
+  int32_t unit_run;           /* > 0: 32-column work units per search CTA (filter path) / column splits (exact path) */
   int64_t record_cap_bytes;   /* > 0: switch-over size of the automatic choice */
 } rma_chamfer_opts;
 size_t rma_chamfer_workspace_bytes(int B, int N, int M, const rma_chamfer_opts* opts);

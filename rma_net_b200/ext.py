@@ -63,7 +63,7 @@ def _opts():
 @contextlib.contextmanager
 def chamfer_options(path=None, unit_run: int = 0, record_cap_bytes: int = 0):
     """Run the chamfer calls of this block (and this thread) with explicit options: path "auto" | "exact" | "filter"
-    (both give identical results; parity tests and A/B timing force one), unit_run (tiles per search CTA) and the
+    (both give identical results; parity tests and A/B timing force one), unit_run (32-column work units per search CTA) and the
     record cap of the automatic choice.  Backward passes of ops created inside the block do not depend on it."""
     prev = getattr(_tls, "opts", None)
     _tls.opts = _lib.ChamferOpts(_PATHS[path], int(unit_run), int(record_cap_bytes))

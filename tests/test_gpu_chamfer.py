@@ -461,7 +461,7 @@ def test_filter_path_fuzz_against_exact_path(cuda):
 
 @pytest.mark.parametrize("kind", ["uniform", "lattice", "dups", "all_equal"])
 def test_filter_long_unit_runs_and_slow_path(cuda, kind):
-    """Forced unit runs of 1 .. 200 tiles per search CTA: segments with several row-direction entries (one per 16 tiles),
+    """Forced unit runs of 1 .. 200 32-column units per search CTA: segments with several row-direction entries (one per 16 tiles),
     partially filled and empty entries, runs that cross row blocks and batch elements.  Tie-heavy clouds (lattice,
     duplicated points, one repeated point) send most items through the slow path, which re-evaluates whole candidate
     entries; the result must still equal the exact path's bit for bit (distances and indices)."""
@@ -484,7 +484,7 @@ def test_filter_long_unit_runs_and_slow_path(cuda, kind):
     xt, yt = torch.from_numpy(cloud(N)).to(cuda), torch.from_numpy(cloud(M)).to(cuda)
     with ext.chamfer_options(path="exact"):
         ref = [t.cpu() for t in chamfer_dist_with_idx(xt, yt)]
-    for run in (1, 15, 16, 17, 33, 79, 100, 200):
+    for run in (1, 2, 15, 17, 31, 32, 33, 65, 79, 100, 158, 200, 400):   # odd starts split tiles between segments
         with ext.chamfer_options(path="filter", unit_run=run):
             out = [t.cpu() for t in chamfer_dist_with_idx(xt, yt)]
         for a, b_ in zip(out, ref):
