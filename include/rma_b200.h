@@ -110,7 +110,10 @@ int rma_chamfer_cd_forward(const float* x, int64_t xsb, int64_t xsn, int64_t xsc
 /* The same with per-batch-element weights (device array [B] or NULL = 1) and an explicit coefficient:
  *   *loss = coef * sum_b batch_weight[b] * (sum dist1[b] + sum dist2[b]),   gradients scaled accordingly.
  * This is the stage loop of Loss.forward (loss.py:260-267) as ONE call: stack the T stage outputs as a [T*B,N,3] batch,
- * repeat the target, batch_weight[t*B + b] = weight_cd * gamma^(T-t-1), coef = 0.5 / B. */
+ * repeat the target, batch_weight[t*B + b] = weight_cd * gamma^(T-t-1), coef = 0.5 / B.
+ * coef and every batch_weight[b] must be >= 0 (stage weights are): coef < 0 is RMA_E_BADARG, a negative weight makes
+ * *loss NaN (the value is published as the largest rounded prefix of a sum of non-negative terms - repeated calls on
+ * the same inputs then agree bit for bit without a completion ticket; csrc/chamfer_common.cuh, loss_commit). */
 int rma_chamfer_cd_forward_weighted(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
                                     const float* y, int64_t ysb, int64_t ysn, int64_t ysc,
                                     int B, int N, int M, const float* batch_weight, float coef, float* loss,

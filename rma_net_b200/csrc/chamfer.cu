@@ -59,6 +59,7 @@ struct Workspace {
   float4* colpack;  // [B][Mp] float4          : (-x, -y, -z, 0)
   u64* rowbest;     // [B][Npad]               : (dist bits << 32) | tile start column
   u64* colbest;     // [B][Mp]                 : (dist bits << 32) | 16-row group id
+  double* lossacc;  // [1]                     : fused loss summed in double (loss_commit, chamfer_common.cuh)
   size_t bytes;
 };
 
@@ -70,6 +71,7 @@ static Workspace carve(const Geometry& g, void* base) {
   w.colpack = (float4*)(p + off); off += align256(g.colpack_float4() * sizeof(float4));
   w.rowbest = (u64*)(p + off);    off += align256((size_t)g.B * g.Npad * sizeof(u64));
   w.colbest = (u64*)(p + off);    off += align256((size_t)g.B * g.Mp * sizeof(u64));
+  w.lossacc = (double*)(p + off); off += align256(sizeof(double));
   w.bytes = off;
   return w;
 }
@@ -85,7 +87,10 @@ __global__ void __launch_bounds__(256) chamfer_prep_kernel(
   const long long nrow = (long long)g.B * g.Npad;
   const long long ncol = (long long)g.B * g.Mp;
   pdl_wait();
-  if (zero_loss && blockIdx.x == 0 && threadIdx.x == 0) *zero_loss = 0.f;
+  if (zero_loss && blockIdx.x == 0 && threadIdx.x == 0) {
+    *zero_loss = 0.f;
+    w.lossacc[0] = 0.0;
+  }
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nrow + ncol;
        t += (long long)gridDim.x * blockDim.x) {
     if (t < nrow) {
@@ -371,6 +376,9 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
     __syncwarp();
     const unsigned myhit = hits[warp][lane];
     const int j = jt + (myhit ? __ffs(myhit) - 1 : 0);
+    // no candidate reproduces the winning value: only with NaN coordinates (every comparison fails).  NaN distance,
+    // index 0 - the same contract as the filter path's resolve.
+    if (valid && !myhit) myd = __int_as_float(0x7fc00000);
     wb = (valid && f.batch_weight) ? f.batch_weight[b] : 1.f;
     if (valid) {
       if (f.dist1) f.dist1[t] = myd;
@@ -422,6 +430,7 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
     __syncwarp();
     const unsigned myhit = hits[warp][lane];
     const int myi = myhit ? __ffs(myhit) - 1 : 0;
+    if (valid && !myhit) myd = __int_as_float(0x7fc00000);   // NaN coordinates, as above
     const int i = grp * kRowsPerThread + myi;
     wb = (valid && f.batch_weight) ? f.batch_weight[b] : 1.f;
     if (valid) {
@@ -443,17 +452,8 @@ __global__ void __launch_bounds__(kFinWarps * 32) chamfer_finalize_kernel(Geomet
   }
 
   if (f.loss) {
-    double sd = valid ? (double)myd * (double)wb : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
-    if (lane == 0) lsum[warp] = sd;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double tot = 0.0;
-#pragma unroll
-      for (int k = 0; k < kFinWarps; ++k) tot += lsum[k];
-      atomicAdd(f.loss, (float)(tot * (double)f.coef_loss));
-    }
+    const double tot = loss_partial<kFinWarps>(valid, myd, wb, f.coef_loss, lsum);
+    if (threadIdx.x == 0) loss_commit(w.lossacc, tot, f.loss);
   }
 }
 
@@ -812,7 +812,7 @@ int rma_chamfer_cd_forward_weighted(const float* x, int64_t xsb, int64_t xsn, in
                                     float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* own_x,
                                     float* scat_x, float* own_y, float* scat_y, void* workspace,
                                     size_t workspace_bytes, const rma_chamfer_opts* opts, void* stream) {
-  if (!loss) return RMA_E_BADARG;
+  if (!loss || !(coef >= 0.f)) return RMA_E_BADARG;
   const ChamferOpts o = make_opts(opts);
   if ((own_x == nullptr) != (scat_x == nullptr) || (own_y == nullptr) != (scat_y == nullptr)) return RMA_E_BADARG;
   if ((((uintptr_t)scat_x) | ((uintptr_t)scat_y)) & 15u) return RMA_E_BADARG;

@@ -84,5 +84,37 @@ struct FinalizeArgs {
 
 constexpr int kFinWarps = 8;
 
+// Fused loss value.  Every CTA adds its share - summed in DOUBLE - to a double accumulator in the workspace (zeroed by
+// prep) with ONE value-returning atomic and publishes fl32(previous + own) with an integer atomicMax on the caller's
+// float: the terms are non-negative (squared distances, weights >= 0), so the prefix sums only grow, their float
+// roundings are monotone, and the largest one is the rounding of the total.  The order of the double additions moves the
+// total by ~1e-16 relative, i.e. repeated runs agree to the last bit in practice, and no CTA has to know that it is the
+// last one: a "last CTA rounds the sum" ticket (atomic, fence, atomic, and fence + load + store on the last CTA) cost
+// 2.3 us at the tail of a 77 us step, float atomics are free but differ by ~1e-6 between runs.
+// A negative weight breaks the monotonicity, so it poisons the sum instead: NaN, which as an integer is larger than every
+// finite value and sticks (NaN / inf distances propagate the same way, as they do in the reference's torch.mean).
+template <int kWarps>
+__device__ __forceinline__ double loss_partial(bool valid, float d, float wb, float coef, double* lsum) {
+  double sd = valid ? (double)d * (double)wb : 0.0;
+  if (valid && wb < 0.f) sd = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+  if (lane_id() == 0) lsum[threadIdx.x >> 5] = sd;
+  __syncthreads();
+  double tot = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < kWarps; ++k) tot += lsum[k];
+    tot *= (double)coef;
+  }
+  return tot;   // valid on thread 0
+}
+
+__device__ __forceinline__ void loss_commit(double* acc, double tot, float* loss) {
+  const double prev = atomicAdd(acc, tot);
+  const float r = (float)(prev + tot);
+  atomicMax(reinterpret_cast<int*>(loss), r == r ? __float_as_int(r) : 0x7fc00000);
+}
+
 
 }  // namespace rma

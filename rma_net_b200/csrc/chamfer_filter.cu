@@ -162,7 +162,7 @@ struct FWorkspace {
   float* colrec;     // [B][nRB][Mp][2]         two smallest packed group minima of g over the row block, interleaved
                      //                         per column: one 8-byte store in the search, one 8-byte load in the resolve
   unsigned* stats;   // [64]: [0..3] rows on the slow path, columns on the slow path, row-block rescans, unused;
-                     //       [8..39] timeline marks (tools/ builds only); [48..49] the loss accumulator (double), [50] its ticket
+                     //       [8..39] timeline marks (tools/ builds only); [48..49] the loss accumulator (double; loss_commit)
   size_t bytes;
 };
 
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) chamfer_fprep_kernel(
   pdl_launch_dependents();   // let the search grid's launch overlap this kernel; its CTAs wait for our completion
   RMA_TL(w.stats, 0);
   if (blockIdx.x == 0 && threadIdx.x < 4) w.stats[threadIdx.x] = 0u;
-  if (blockIdx.x == 0 && threadIdx.x >= 48 && threadIdx.x < 52) w.stats[threadIdx.x] = 0u;   // loss accumulator (double) + ticket
+  if (blockIdx.x == 0 && threadIdx.x >= 48 && threadIdx.x < 50) w.stats[threadIdx.x] = 0u;   // loss accumulator (double)
   if (zero_loss && blockIdx.x == 0 && threadIdx.x == 0) *zero_loss = 0.f;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nrow + ncol;
        t += (long long)gridDim.x * blockDim.x) {
@@ -1042,26 +1042,13 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
   }
 
   if (f.loss) {
-    double sd = valid ? (double)myd * (double)wb : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
-    if (lane == 0) lsum[warp] = sd;
-    __syncthreads();
+    const double tot = loss_partial<kFinWarps>(valid, myd, wb, f.coef_loss, lsum);
     if (threadIdx.x == 0) {
-      double tot = 0.0;
-#pragma unroll
-      for (int k = 0; k < kFinWarps; ++k) tot += lsum[k];
-      // The loss is summed in DOUBLE (workspace scratch behind the statistics) and the last CTA rounds it to the
-      // caller's float once: the order of the atomics then changes the result by ~1e-16 relative instead of ~1e-6
-      // (592 float atomics at C2), so two runs on the same inputs agree to the last bit in practice.
-      double* acc = reinterpret_cast<double*>(w.stats + 48);
-      atomicAdd(acc, tot * (double)f.coef_loss);
-      __threadfence();
-      const unsigned ticket = atomicAdd(w.stats + 50, 1u);
-      if (ticket == gridDim.x - 1u) {
-        __threadfence();
-        *f.loss = (float)*reinterpret_cast<volatile double*>(acc);
-      }
+#ifdef RMA_LOSS_FLOAT_ATOMIC   // tools/ A/B only: the round-1 float atomics (run-to-run differences of ~1e-6 relative)
+      atomicAdd(f.loss, (float)tot);
+#else
+      loss_commit(reinterpret_cast<double*>(w.stats + 48), tot, f.loss);
+#endif
     }
   }
   RMA_TL(w.stats, 6);

@@ -493,8 +493,8 @@ def test_filter_long_unit_runs_and_slow_path(cuda, kind):
 
 def test_nan_point_does_not_corrupt_anything(cuda, chamfer_path):
     """NaN coordinates are outside the contract, but they must not send an index out of range (the
-    gradient scatter would write there): every index stays inside [0, M) / [0, N); on the filter path the NaN point's own
-    distance is NaN."""
+    gradient scatter would write there): every index stays inside [0, M) / [0, N), and on both paths the NaN point's own
+    distance is NaN (the other points skip it as a candidate)."""
     from rma_net_b200.model.loss import chamfer_dist_with_idx, loss_on_cd
     g = torch.Generator().manual_seed(5)
     x = (torch.rand(2, 700, 3, generator=g) * 2 - 1)
@@ -504,8 +504,8 @@ def test_nan_point_does_not_corrupt_anything(cuda, chamfer_path):
     xd, yd = x.to(cuda).requires_grad_(True), y.to(cuda).requires_grad_(True)
     d1, d2, i1, i2 = chamfer_dist_with_idx(xd, yd)
     torch.cuda.synchronize()
-    if chamfer_path == "filter":                       # the exact path's minimum skips NaN candidates instead
-        assert torch.isnan(d1[0, 13]) and torch.isnan(d2[1, 77])
+    assert torch.isnan(d1[0, 13]) and torch.isnan(d2[1, 77])
+    assert int(torch.isnan(d1).sum()) == 1 and int(torch.isnan(d2).sum()) == 1
     assert int(i1.min()) >= 0 and int(i1.max()) < 900 and int(i2.min()) >= 0 and int(i2.max()) < 700
     loss_on_cd(xd, yd).backward()
     torch.cuda.synchronize()
@@ -536,3 +536,46 @@ def test_filter_equals_exact_at_large_sizes(cuda, shape, kind):
             outs.append([t.cpu() for t in chamfer_dist_with_idx(x, y)])
     for a, b_ in zip(*outs):
         assert torch.equal(a, b_)
+
+
+def test_fused_loss_is_reproducible_and_matches_the_sum(cuda):
+    """The fused loss is accumulated in double and published as the largest rounded prefix sum (csrc/chamfer_common.cuh,
+    loss_commit), so repeated runs on the same inputs agree bit for bit and the value equals the fp64 sum of the returned
+    distances to fp32 rounding; the metric variant returns exactly the distances chamfer_dist returns."""
+    from rma_net_b200.model.exfunc.functions import ChamferCDMetricsFunction
+    from rma_net_b200.model.loss import chamfer_dist, loss_on_cd
+    g = torch.Generator().manual_seed(21)
+    B, N, M = 16, 4096, 4096
+    x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(cuda)
+    y = (torch.rand(B, M, 3, generator=g) * 2 - 1).to(cuda)
+    vals = {float(loss_on_cd(x, y)) for _ in range(8)}
+    assert len(vals) == 1, vals
+    d1, d2 = chamfer_dist(x, y)
+    ref = (d1.double().sum() + d2.double().sum()).item() * 0.5 / B
+    assert abs(vals.pop() - ref) <= 1.2e-7 * abs(ref)
+    loss, m1, m2 = ChamferCDMetricsFunction.apply(x, y)
+    assert torch.equal(m1, d1) and torch.equal(m2, d2)
+
+
+def test_fused_loss_weight_contract(cuda):
+    """include/rma_b200.h: coef and the per-batch weights of the fused loss are non-negative.  Zero weights are fine, a
+    negative weight poisons the value (NaN) instead of returning a wrong prefix, a negative coef is a bad argument; NaN
+    coordinates give a NaN loss as the reference's mean does."""
+    from rma_net_b200 import ext
+    g = torch.Generator().manual_seed(22)
+    B, N, M = 4, 700, 900
+    x = torch.randn(B, N, 3, generator=g).to(cuda)
+    y = torch.randn(B, M, 3, generator=g).to(cuda)
+    w = torch.tensor([0.0, 1.0, 0.5, 2.0], device=cuda)
+    loss, _, _, d1, d2 = ext.chamfer_cd_forward(x, y, False, False, w, 0.25, True)
+    ref = 0.25 * (w.double() * (d1.double().sum(1) + d2.double().sum(1))).sum().item()
+    assert abs(float(loss) - ref) <= 1.2e-7 * abs(ref)
+    zero = ext.chamfer_cd_forward(x, y, False, False, torch.zeros(B, device=cuda), 0.25)[0]
+    assert float(zero) == 0.0
+    neg = ext.chamfer_cd_forward(x, y, False, False, torch.tensor([1.0, -1.0, 1.0, 1.0], device=cuda), 0.25)[0]
+    assert torch.isnan(neg)
+    with pytest.raises(RuntimeError):
+        ext.chamfer_cd_forward(x, y, False, False, w, -0.25)
+    xn = x.clone()
+    xn[1, 5, 0] = float("nan")
+    assert torch.isnan(ext.chamfer_cd_forward(xn, y, False, False, w, 0.25)[0])
