@@ -90,7 +90,10 @@ int rma_chamfer_search(int B, int N, int M, void* workspace, size_t workspace_by
                        void* stream);
 int rma_chamfer_finalize(int B, int N, int M, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
                          void* workspace, size_t workspace_bytes, const rma_chamfer_opts* opts, void* stream);
-/* Launch shape the search kernel will use for (B,N,M,opts) on the current device (reporting only). */
+/* Launch shape the search kernel will use for (B,N,M,opts) on the current device (reporting only).  On the filter path
+ * the figures describe the VIRTUAL CTAs (groups of 1, 2 or 4 warps with their own shared memory and barrier; `threads`
+ * threads each, `ctas_per_sm` of them inside one physical 256-thread CTA per SM) and `splits` is the longest run of
+ * 32-column work units dealt to one of them. */
 int rma_chamfer_search_config(int B, int N, int M, const rma_chamfer_opts* opts, int* ctas, int* threads, int* splits,
                               int* ctas_per_sm);
 

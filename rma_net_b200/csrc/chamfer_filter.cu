@@ -40,7 +40,8 @@ constexpr int kFWarps = 4;                              // warps per search CTA 
                                                         // (template parameter kW; 1024 / 512 rows per CTA row block), so
                                                         // that no warp of a CTA is left without rows (64 x 1024 ran at
                                                         // 33 % of peak with two of four warps idle)
-constexpr int kFThreads = 32 * kFWarps;                 // threads of the largest search CTA (reporting)
+constexpr int kFThreads = 32 * kFWarps;                 // threads of the largest virtual search CTA (reporting)
+constexpr int kFSearchThreads = 256;                    // threads of a physical search CTA: 8 / kW virtual CTAs, one physical CTA per SM
 static inline int f_warps_for(int nRB) { return nRB >= 3 ? 4 : nRB; }   // 512-row blocks per batch element -> kW
 constexpr int kFColTile = 32;                           // columns per column-direction tile (= lanes)
 constexpr int kFColTop = 2;                             // packed group minima recorded per column and row block
@@ -95,6 +96,56 @@ __device__ __forceinline__ void tl_mark(unsigned* stats, int slot) {
 #define RMA_TL(stats, slot) ((void)0)
 #endif
 
+// t / d for t < 2^31 with m = min(ceil(2^32 / d), 2^32 - 1): umulhi(t, m) is off by at most one either way (the
+// estimate t m / 2^32 lies in [t/d - t/2^32, t/d + t/2^32)), so one multiply-back and two selects make it exact - six
+// instructions against ~20 for the emulated 32-bit division (the resolve had five of them per lane).
+__device__ __forceinline__ unsigned fdiv(unsigned t, unsigned d, unsigned m) {
+  unsigned q = __umulhi(t, m);
+  const int r = (int)(t - q * d);
+  q = r < 0 ? q - 1u : q;
+  q = r >= (int)d ? q + 1u : q;
+  return q;
+}
+
+// How the B*nRBC*nT work units of the search are dealt out to its CTAs (one wave that fills every resident slot; a
+// CTA's share of one row block is a "segment", for which it loads the rows once and writes one set of row records).
+//   mode 0  contiguous runs over the whole unit range: the first nL CTAs take U units, the others Us = U - 1; a run may
+//           cross into the next row block / batch element (the CTA then starts a second segment: row reload, record
+//           flush, a drained pipeline - about one unit's time).  Used when there are more row blocks than CTAs, where a
+//           run spans row blocks anyway, or when forced (rma_chamfer_opts.unit_run, tests).
+//   mode 1  row-block aligned: the first Rhi row blocks are shared by clo + 1 CTAs each, the others by clo; inside a row
+//           block of c CTAs the first nT % c runs are nT / c + 1 units long, the others nT / c.  No CTA crosses a row
+//           block, so every CTA has exactly one segment.  CTAs are dispatched breadth-first in index order (block k and
+//           block k + #SMs share an SM: tools/cta_placement_probe.cu), so the search maps its block index through a
+//           serpentine over the runs SORTED by length (cls_*: up to four classes of equal length) and every SM gets
+//           long runs together with short ones.
+// The host picks the mode with the smaller per-SM maximum (f_make_geometry).
+struct FDeal {
+  int mode;
+  int S;               // SMs (serpentine period)
+  // mode 0
+  int U, Us, nL;
+  unsigned uL;         // nL * U: first unit of the short CTAs
+  unsigned magicU, magicUs;
+  // mode 1
+  int Rhi, clo;
+  int ncls;
+  int cls_base[5];     // first sorted index of class i; cls_base[ncls] = nC
+  int cls_per[4];      // runs of this class per row block
+  int cls_rb0[4];      // first row block of the class
+  int cls_pos0[4];     // first position (segment index inside the row block) of the class
+};
+
+__host__ __device__ __forceinline__ long long f_cta_start(int k, int U, int Us, int nL, unsigned uL) {
+  return k <= nL ? (long long)k * U : (long long)uL + (long long)(k - nL) * Us;
+}
+// mode 1: units [ua, ub) (relative to the row block) of segment `pos` of a row block shared by c CTAs
+__host__ __device__ __forceinline__ void f_aligned_run(int nT, int c, int pos, unsigned& ua, unsigned& ub) {
+  const int q = nT / c, r = nT - q * c;
+  ua = (unsigned)(pos * q + (pos < r ? pos : r));
+  ub = ua + (unsigned)(q + (pos < r ? 1 : 0));
+}
+
 struct FGeometry {
   int B, N, M;
   int nRB;    // 512-row blocks per batch element
@@ -104,33 +155,18 @@ struct FGeometry {
   int nRBC;   // CTA row blocks (RC rows) per batch element
   int nT;     // 32-column work units per batch element (even: Mp is a multiple of the 64-column tile)
   int Mp;     // nT * 32
-  int U;      // work units (CTA row block x 32 columns) per search CTA
+  FDeal d;    // how the units are dealt out to the search CTAs
+  int nC;     // virtual search CTAs (runs)
+  int G;      // physical search CTAs (grid): virtual CTA v = block + layer * G, layer = warp group of the block
+  int maxrun; // units of the longest run
   int Smax;   // max segments (CTAs) that share one CTA row block
   int P;      // row-direction entries per segment: a run of n units touches <= n / 2 + 1 tiles, one entry per 16 tiles
-  unsigned magicN, magicM, magicU;   // ceil(2^32 / d) (clipped to 2^32 - 1): fast exact division in the resolve (fdiv)
+  unsigned magicN, magicM;   // ceil(2^32 / d) (clipped to 2^32 - 1): fast exact division in the resolve (fdiv)
   int rc_shift;                      // log2(RC)
   long long units() const { return (long long)B * nRBC * nT; }
 };
 
-// Work decomposition of the search: the B*nRBC*nT units are dealt out in contiguous runs of U to the CTAs, so every
-// CTA has the same amount of work (+-1 unit) whatever B, N, M are; a run may cross into the next row block / batch
-// element, in which case the CTA reloads its rows ("segment").  U is chosen for a whole number of balanced waves.
-static int f_choose_unit_run(long long units, int nT, int slots) {
-  // cost of w waves ~ w * (U * 32 columns + fixed per-CTA overhead of ~40 column-times), U = ceil(units/(slots*w))
-  double best_cost = 1e300;
-  int best = 1;
-  for (int w = 1; w <= 64; ++w) {
-    long long U = (units + (long long)slots * w - 1) / ((long long)slots * w);
-    if (U < 1) U = 1;
-    const double cost = (double)w * ((double)U * kFUnit + 40.0);
-    if (cost < best_cost * 0.995) { best_cost = cost; best = (int)(U > 0x3fffffff ? 0x3fffffff : U); }
-    if (U <= 2) break;
-  }
-  (void)nT;
-  return best;
-}
-
-static FGeometry f_make_geometry(int B, int N, int M, int slots, int force_run) {
+static FGeometry f_make_geometry(int B, int N, int M, int sms, int occ, int force_run) {
   FGeometry g;
   g.B = B; g.N = N; g.M = M;
   g.nRB = (N + kFRowsPerWarp - 1) / kFRowsPerWarp;
@@ -140,13 +176,126 @@ static FGeometry f_make_geometry(int B, int N, int M, int slots, int force_run) 
   g.nRBC = (g.nRB + g.W - 1) / g.W;
   g.nT = ((M + kFRowTile - 1) / kFRowTile) * (kFRowTile / kFUnit);
   g.Mp = g.nT * kFUnit;
-  g.U = force_run > 0 ? force_run : f_choose_unit_run(g.units(), g.nT, slots);
-  g.Smax = (g.nT + g.U - 1) / g.U + 1;
-  g.P = ((g.U < g.nT ? g.U : g.nT) / 2 + 1 + kFSubTiles - 1) / kFSubTiles;
-  auto magic = [](unsigned d) { const unsigned long long m = ((1ull << 32) + d - 1) / d; return (unsigned)(m > 0xffffffffull ? 0xffffffffull : m); };
-  g.magicN = magic((unsigned)N); g.magicM = magic((unsigned)M); g.magicU = magic((unsigned)g.U);
+  const long long units = g.units();
+  const long long slots = (long long)sms * occ;
+  FDeal& d = g.d;
+  d = FDeal{};
+  int maxrun;
+  if (force_run > 0) {
+    d.U = force_run;
+    const long long nc = (units + force_run - 1) / force_run;
+    g.nC = (int)(nc > 0x7fffffffLL ? 0x7fffffffLL : nc);
+    d.nL = g.nC;
+#ifdef RMA_F_UNIFORM_RUNS   // tools/ A/B only: the round-1 dealing, ceil(units / slots) units for every CTA
+  } else if (true) {
+    const long long U = (units + slots - 1) / slots;
+    d.U = (int)(U < 1 ? 1 : U);
+    g.nC = (int)((units + d.U - 1) / d.U);
+    d.nL = g.nC;
+#endif
+  } else {
+    g.nC = (int)(units < slots ? units : slots);
+    if (g.nC < 1) g.nC = 1;
+    const long long U = (units + g.nC - 1) / g.nC;
+    d.U = (int)(U > 0x3fffffff ? 0x3fffffff : (U < 1 ? 1 : U));
+    d.nL = (int)(units - (long long)g.nC * (d.U - 1));       // in [1, nC]
+  }
+  {
+    const long long G = (long long)g.nC <= slots ? ((long long)g.nC < sms ? g.nC : sms) : ((long long)g.nC + occ - 1) / occ;
+    g.G = (int)(G > 0x7fffffffLL ? 0x7fffffffLL : G);
+  }
+  d.S = g.G;
+  d.Us = d.U > 1 ? d.U - 1 : 1;
+  d.uL = (unsigned)((long long)d.nL * d.U > 0x7fffffffLL ? 0x7fffffffLL : (long long)d.nL * d.U);
+  const int shortest = d.nL < g.nC ? d.Us : d.U;
+  g.Smax = (g.nT + shortest - 1) / shortest + 1;
+  maxrun = d.U;
+  auto magic = [](unsigned dv) { const unsigned long long m = ((1ull << 32) + dv - 1) / dv; return (unsigned)(m > 0xffffffffull ? 0xffffffffull : m); };
+  d.magicU = magic((unsigned)d.U);
+  d.magicUs = magic((unsigned)d.Us);
+
+#ifndef RMA_F_UNIFORM_RUNS
+  // Row-block aligned dealing (mode 1) when every row block can have its own CTAs and the sorted serpentine loads the
+  // SMs no worse than the contiguous runs do (whose row-block crossings cost about one unit's time on the SM that has one).
+  const long long R = (long long)B * g.nRBC;
+  if (force_run <= 0 && (long long)g.nC >= R && g.nC > 1) {
+    const int clo = (int)(g.nC / R), Rhi = (int)(g.nC - (long long)clo * R);
+    struct Cls { int len, per, rb0, pos0; long long count; } c[4];
+    int n = 0;
+    auto add = [&](int rb0, long long nrb, int cc) {
+      if (nrb <= 0 || cc <= 0) return;
+      const int q = g.nT / cc, r = g.nT - q * cc;
+      if (r > 0) c[n++] = {q + 1, r, rb0, 0, nrb * r};
+      if (cc - r > 0 && q > 0) c[n++] = {q, cc - r, rb0, r, nrb * (cc - r)};
+    };
+    add(0, Rhi, clo + 1);
+    add(Rhi, R - Rhi, clo);
+    for (int i = 1; i < n; ++i)                     // insertion sort, longest runs first
+      for (int j = i; j > 0 && c[j].len > c[j - 1].len; --j) { const Cls t = c[j]; c[j] = c[j - 1]; c[j - 1] = t; }
+    long long base[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) base[i + 1] = base[i] + c[i].count;
+    if (base[n] == (long long)g.nC) {               // every CTA has a run (c <= nT in both row-block classes)
+      auto len_sorted = [&](long long sidx) { int i = 0; while (i + 1 < n && sidx >= base[i + 1]) ++i; return c[i].len; };
+      auto serp = [&](int j, int t) -> long long {   // sorted index of the CTA that SM j runs in layer t, or -1
+        const long long lo = (long long)t * g.G, sz = (g.nC - lo) < g.G ? (g.nC - lo) : g.G;
+        if (j >= sz) return -1;
+        return lo + ((t & 1) ? sz - 1 - j : j);
+      };
+      auto sm_load = [&](int j) { long long tot = 0; for (int t = 0; (long long)t * g.G < g.nC; ++t) { const long long x = serp(j, t); if (x >= 0) tot += len_sorted(x); } return tot; };
+      // the load is piecewise constant in j: evaluate next to every class boundary of every layer
+      long long cost1 = sm_load(0);
+      for (int t = 0; (long long)t * g.G < g.nC; ++t)
+        for (int i = 1; i < n; ++i) {
+          const long long bidx = base[i] - (long long)t * g.G;
+          const long long sz = (g.nC - (long long)t * g.G) < g.G ? (g.nC - (long long)t * g.G) : g.G;
+          if (bidx <= 0 || bidx >= sz) continue;
+          const long long jb = (t & 1) ? sz - 1 - bidx : bidx;
+          for (long long jj = jb - 1; jj <= jb + 1; ++jj)
+            if (jj >= 0 && jj < g.G) { const long long v = sm_load((int)jj); if (v > cost1) cost1 = v; }
+        }
+      long long cost0 = 0;
+      for (int t = 0; (long long)t * g.G < g.nC; ++t) cost0 += ((long long)t * g.G < d.nL) ? d.U : d.Us;
+      cost0 += (R > 1) ? 1 : 0;                     // a crossing
+      if (cost1 <= cost0) {
+        d.mode = 1;
+        d.Rhi = Rhi; d.clo = clo; d.ncls = n;
+        for (int i = 0; i < n; ++i) { d.cls_base[i] = (int)base[i]; d.cls_per[i] = c[i].per; d.cls_rb0[i] = c[i].rb0; d.cls_pos0[i] = c[i].pos0; }
+        d.cls_base[n] = g.nC;
+        g.Smax = Rhi > 0 ? clo + 1 : clo;
+        maxrun = c[0].len;
+      }
+    }
+  }
+#endif
+  g.maxrun = maxrun;
+  g.P = ((maxrun < g.nT ? maxrun : g.nT) / 2 + 1 + kFSubTiles - 1) / kFSubTiles;
+  g.magicN = magic((unsigned)N); g.magicM = magic((unsigned)M);
   g.rc_shift = g.W == 4 ? 11 : g.W == 2 ? 10 : 9;
   return g;
+}
+
+// Segments of row block brb: how many CTAs share it (nseg) and, for mode 0, the first of them (kfirst).
+__device__ __forceinline__ void f_rowblock_segments(const FDeal& d, unsigned brb, int nT, int& kfirst, int& nseg) {
+  if (d.mode == 1) {
+    kfirst = 0;
+    nseg = (int)brb < d.Rhi ? d.clo + 1 : d.clo;
+    return;
+  }
+  const unsigned ufirst = brb * (unsigned)nT, ulast = ufirst + (unsigned)nT - 1u;
+  auto cta_of = [&](unsigned u) {
+    return u < d.uL ? fdiv(u, (unsigned)d.U, d.magicU) : (unsigned)d.nL + fdiv(u - d.uL, (unsigned)d.Us, d.magicUs);
+  };
+  kfirst = (int)cta_of(ufirst);
+  nseg = (int)cta_of(ulast) - kfirst + 1;
+}
+// Units [ua, ub), relative to the row block, of its segment number srel.
+__device__ __forceinline__ void f_segment_units(const FDeal& d, unsigned brb, int nT, int kfirst, int nseg, unsigned srel,
+                                                unsigned& ua, unsigned& ub) {
+  if (d.mode == 1) { f_aligned_run(nT, nseg, (int)srel, ua, ub); return; }
+  const unsigned u0 = brb * (unsigned)nT, u1 = u0 + (unsigned)nT;
+  const unsigned ks = (unsigned)f_cta_start(kfirst + (int)srel, d.U, d.Us, d.nL, d.uL);
+  const unsigned ke = (unsigned)f_cta_start(kfirst + (int)srel + 1, d.U, d.Us, d.nL, d.uL);
+  ua = max(ks, u0) - u0; ub = min(ke, u1) - u0;
 }
 
 struct FWorkspace {
@@ -266,23 +415,37 @@ struct FSearchArgs {
   float* rowtop;
   float* colrec;
   unsigned* stats;
-  int N, M, nRB, Npad, nRBC, nT, Mp, U, Smax, P;
+  int N, M, nRB, Npad, nRBC, nT, Mp, nC, Smax, P;
   long long units;
+  FDeal d;
 };
 
+// One physical CTA of 256 threads per SM holds 8 / kW "virtual CTAs" (groups of kW warps: what used to be a CTA of its
+// own, with its own shared memory, mbarriers and named barrier).  Which runs share an SM is then decided by the dealing
+// (FDeal) and not by where the block scheduler happens to put the second CTA of an SM: 296 separate CTAs land
+// breadth-first only approximately (the first 148 blocks cover 142 SMs, tools/cta_placement_probe.cu), and six SMs with
+// two long runs are enough to lose what the balanced dealing gains.
 template <int kW>
-__global__ void __launch_bounds__(32 * kW, RMA_F_MINCTAS * 4 / kW) chamfer_fsearch_kernel(FSearchArgs a) {
-  static_assert(kW == 1 || kW == 2 || kW == 4, "1, 2 or 4 warps per search CTA");
+__global__ void __launch_bounds__(kFSearchThreads, 1) chamfer_fsearch_kernel(FSearchArgs a) {
+  static_assert(kW == 1 || kW == 2 || kW == 4, "1, 2 or 4 warps per virtual search CTA");
   constexpr int kThreads = 32 * kW, kRowsPerCta = kFRowsPerWarp * kW, kChunk = kFChunk * kW / 4;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_all[];
+  const int group = (int)threadIdx.x / kThreads;                       // virtual CTA slot on this SM (layer of the dealing)
+  const int vblock = (int)blockIdx.x + group * (int)gridDim.x;         // virtual CTA index
+  if (vblock >= a.nC) return;                                           // the whole group leaves: its barrier is its own
+  unsigned char* smem_raw = smem_all + (size_t)group * f_smem(kW);
+  auto group_sync = [&]() {
+    if (kW == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kThreads) : "memory");
+  };
+  const int tid = (int)threadIdx.x - group * kThreads, lane = tid & 31, warp = tid >> 5;
   float4* scol = reinterpret_cast<float4*>(smem_raw);                                              // [2][kChunk + 4]
   float* cball = reinterpret_cast<float*>(smem_raw + (size_t)2 * (kChunk + 4) * sizeof(float4));    // [warps][2][32][36]
   u64* mbar = reinterpret_cast<u64*>(smem_raw + f_smem_top(kW));                                   // [2]
   // per-row running (smallest tile minimum, its tile, second smallest): touched once per 64-column tile, so it lives
   // in shared memory ([plane][q][thread] float4, conflict-free) instead of 48 registers
-  float4* stop = reinterpret_cast<float4*>(smem_raw + f_smem_base(kW)) + threadIdx.x;             // [3][4][kThreads]
+  float4* stop = reinterpret_cast<float4*>(smem_raw + f_smem_base(kW)) + tid;                     // [3][4][kThreads]
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* cb = cball + warp * (2 * kFColTile * kFCbStride);
   const float inf = __int_as_float(0x7f800000);
   const unsigned lane_tag = (unsigned)lane;
@@ -291,10 +454,27 @@ __global__ void __launch_bounds__(32 * kW, RMA_F_MINCTAS * 4 / kW) chamfer_fsear
   unsigned rtag_mask = ~kFRowTagMask;
   asm volatile("" : "+r"(rtag_mask));
 
-  long long unit = (long long)blockIdx.x * a.U;
-  const long long unit_end = min(unit + a.U, a.units);
+  long long unit, unit_end;
+  int seg_aligned = 0;
+  if (a.d.mode == 1) {
+    // serpentine over the runs sorted by length: layer `group` of SM blockIdx.x
+    const int G = (int)gridDim.x, lo = group * G, sz = min(G, a.nC - lo);
+    const int sidx = lo + ((group & 1) ? sz - 1 - (int)blockIdx.x : (int)blockIdx.x);
+    int ci = 0;
+    while (ci + 1 < a.d.ncls && sidx >= a.d.cls_base[ci + 1]) ++ci;
+    const int o = sidx - a.d.cls_base[ci];
+    const int rbk = a.d.cls_rb0[ci] + o / a.d.cls_per[ci];
+    seg_aligned = a.d.cls_pos0[ci] + o % a.d.cls_per[ci];
+    unsigned ua, ub;
+    f_aligned_run(a.nT, rbk < a.d.Rhi ? a.d.clo + 1 : a.d.clo, seg_aligned, ua, ub);
+    unit = (long long)rbk * a.nT + ua;
+    unit_end = (long long)rbk * a.nT + ub;
+  } else {
+    unit = f_cta_start(vblock, a.d.U, a.d.Us, a.d.nL, a.d.uL);
+    unit_end = min(f_cta_start(vblock + 1, a.d.U, a.d.Us, a.d.nL, a.d.uL), a.units);
+  }
   if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
-  __syncthreads();
+  group_sync();
   int cur = 0;           // column buffer the next chunk lands in
   unsigned phases = 0;   // bit s: parity the next wait on buffer s expects
   pdl_wait();
@@ -310,13 +490,15 @@ __global__ void __launch_bounds__(32 * kW, RMA_F_MINCTAS * 4 / kW) chamfer_fsear
     const int b = brb / a.nRBC, rbc = brb - b * a.nRBC;
     const int rb = rbc * kW + warp;
     const bool has_rows = rb < a.nRB;   // warp-uniform
-    const int seg = blockIdx.x - (int)(((long long)brb * a.nT) / a.U);   // which of the row block's segments
+    const long long ub0 = (long long)brb * a.nT;                         // the row block's first unit: which CTA holds it?
+    const int seg = a.d.mode == 1 ? seg_aligned                          // which of the row block's segments
+                                  : vblock - (int)(ub0 < (long long)a.d.uL ? ub0 / a.d.U : a.d.nL + (ub0 - a.d.uL) / a.d.Us);
     const int c0 = unit0 * kFUnit;
     const int ncols = nunit * kFUnit;
 
     // Column chunks arrive by TMA bulk copy (one contiguous run of the interleaved pair pack) into a double buffer:
     // the segment's first chunk is in flight while the rows are loaded, chunk k+1 while chunk k is computed.  Both
-    // buffers are free here: every chunk iteration ends with a __syncthreads.
+    // buffers are free here: every chunk iteration ends with a group barrier.
     const float4* cp = a.colpair + ((size_t)b * a.Mp + c0);
     if (tid == 0) bulk_load(scol + cur * (kChunk + 4), cp, (unsigned)min(kChunk, ncols) * 16u, &mbar[cur]);
 
@@ -522,7 +704,7 @@ __global__ void __launch_bounds__(32 * kW, RMA_F_MINCTAS * 4 / kW) chamfer_fsear
           if (++sub_tiles == kFSubTiles) flush_top();
         }
       }
-      __syncthreads();   // chunk fully consumed: a later bulk copy may refill this buffer
+      group_sync();   // chunk fully consumed: a later bulk copy may refill this buffer
     }
 
     if (has_rows) {
@@ -578,17 +760,6 @@ __device__ __forceinline__ float sqdist_q(float x, float y, float z, const float
   d = __fmaf_rn(dy, dy, d);
   d = __fmaf_rn(dz, dz, d);
   return d;
-}
-
-// t / d for t < 2^31 with m = min(ceil(2^32 / d), 2^32 - 1): umulhi(t, m) is off by at most one either way (the
-// estimate t m / 2^32 lies in [t/d - t/2^32, t/d + t/2^32)), so one multiply-back and two selects make it exact - six
-// instructions against ~20 for the emulated 32-bit division (the resolve had five of them per lane).
-__device__ __forceinline__ unsigned fdiv(unsigned t, unsigned d, unsigned m) {
-  unsigned q = __umulhi(t, m);
-  const int r = (int)(t - q * d);
-  q = r < 0 ? q - 1u : q;
-  q = r >= (int)d ? q + 1u : q;
-  return q;
 }
 
 // Tagged row-direction values: a group minimum v is stored as t(v) = (bits(v) & ~3) | group, |t(v) - v| < 4 ulp(v)
@@ -700,15 +871,17 @@ __device__ __forceinline__ void scan_row_entries(const float* top, int nseg, flo
 // minimum is within the guard: an entry whose second smallest is not contributes its one recorded group, otherwise all
 // of its columns.  The lowest column among the lanes that hold the minimum = torch.min's first index.
 __device__ __noinline__ void row_slow_item(const float* __restrict__ rowtop, const float4* __restrict__ colpack, int RC,
-                                           int nRBC, int nT, int U, int Smax, int P, int Mp, int sb, int si, float sthr,
+                                           int nRBC, int nT, const FDeal* __restrict__ dp, int Smax, int P, int Mp,
+                                           int sb, int si, float sthr,
                                            float x, float y, float z, unsigned& out_d, unsigned& out_j, float4& out_q) {
   const unsigned full = 0xffffffffu;
   const float inf = __int_as_float(0x7f800000);
   const int lane = lane_id(), half = lane >> 4, hl = lane & 15;
   const int srbc = si / RC;
   const unsigned sbrb = (unsigned)(sb * nRBC + srbc);
-  const unsigned u0 = sbrb * (unsigned)nT, u1 = u0 + (unsigned)nT;       // the row block's 32-column units [u0, u1)
-  const unsigned kfirst = u0 / (unsigned)U, klast = (u1 - 1u) / (unsigned)U;
+  const FDeal& d = *dp;
+  int kfirst, nsegs;
+  f_rowblock_segments(d, sbrb, nT, kfirst, nsegs);
   const float* top = rowtop + ((size_t)sbrb * Smax * P * 3) * RC + (si - srbc * RC);
   const float4* scq = colpack + (size_t)sb * Mp;
   unsigned bd = 0xffffffffu, bj = 0xffffffffu;
@@ -723,7 +896,7 @@ __device__ __noinline__ void row_slow_item(const float* __restrict__ rowtop, con
       if (d < bd || (d == bd && jc < bj)) { bd = d; bj = jc; bq = q; }
     }
   };
-  const unsigned nent = (klast - kfirst + 1u) * (unsigned)P;
+  const unsigned nent = (unsigned)nsegs * (unsigned)P;
   for (unsigned base = 0; base < nent; base += 32u) {
     // one entry per lane, all in flight; empty entries hold inf
     const unsigned e = base + (unsigned)lane;
@@ -750,8 +923,9 @@ __device__ __noinline__ void row_slow_item(const float* __restrict__ rowtop, con
     }
     while (wholes) {                                  // every column of the entry: 128 per batch, lane <-> 4 columns
       const unsigned he = base + (unsigned)__ffs(wholes) - 1u; wholes &= wholes - 1u;
-      const unsigned k = kfirst + he / (unsigned)P, pe = he % (unsigned)P;
-      const unsigned ua = max(k * (unsigned)U, u0) - u0, ub = min((k + 1u) * (unsigned)U, u1) - u0;   // the segment's 32-column units within the row block
+      const unsigned srel = he / (unsigned)P, pe = he % (unsigned)P;
+      unsigned ua, ub;                                              // the segment's 32-column units within the row block
+      f_segment_units(d, sbrb, nT, kfirst, nsegs, srel, ua, ub);
       const unsigned ta = (ua >> 1) + pe * kFSubTiles;            // first 64-column tile of the entry
       const unsigned tb = min(ta + kFSubTiles, ((ub - 1u) >> 1) + 1u);   // the entry's tiles [ta, tb)
       // the segment's first and last tile may be halves
@@ -842,7 +1016,7 @@ __device__ __noinline__ void col_slow_item(const float* __restrict__ colrec, con
 // SMs x 4 resident CTAs, so every SM carries the same load wherever the block scheduler (or an early programmatic
 // launch behind the search's tail) places the CTAs: with one CTA per 8 items, 512 CTAs on 148 SMs leave some SMs with
 // 4 x 8 items against an average of 27.7.
-__global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGeometry g, FWorkspace w, FinalizeArgs f,
+__global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(const __grid_constant__ FGeometry g, FWorkspace w, FinalizeArgs f,
                                                                              unsigned wbase, unsigned wrem) {
   __shared__ double lsum[kFinWarps];
   // per-warp staging of the 32 items' broadcast data
@@ -889,10 +1063,10 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       b = (int)fdiv(t, (unsigned)g.N, g.magicN); i = (int)(t - (unsigned)b * (unsigned)g.N);
       rp = w.rowpack[(size_t)b * g.Npad + i];
       const int rbc = i >> g.rc_shift, brb = b * g.nRBC + rbc;
-      const int kfirst = (int)fdiv((unsigned)brb * (unsigned)g.nT, (unsigned)g.U, g.magicU);
-      const int klast = (int)fdiv(((unsigned)brb + 1u) * (unsigned)g.nT - 1u, (unsigned)g.U, g.magicU);
+      int kfirst, nsegs;
+      f_rowblock_segments(g.d, (unsigned)brb, g.nT, kfirst, nsegs);
       const float* top = w.rowtop + ((size_t)brb * g.Smax * g.P * 3) * g.RC + (i - rbc * g.RC);
-      const int nseg = (klast - kfirst + 1) * g.P;  // entries: P per segment, consecutive
+      const int nseg = nsegs * g.P;  // entries: P per segment, consecutive
       if (g.W == 4) scan_row_entries<4 * kFRowsPerWarp>(top, nseg, M1, T1, M2);
       else if (g.W == 2) scan_row_entries<2 * kFRowsPerWarp>(top, nseg, M1, T1, M2);
       else scan_row_entries<kFRowsPerWarp>(top, nseg, M1, T1, M2);
@@ -927,7 +1101,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
       const int src = __ffs(slow) - 1; slow &= slow - 1;
       unsigned sd, sj;
       float4 sq;
-      row_slow_item(w.rowtop, w.colpack, g.RC, g.nRBC, g.nT, g.U, g.Smax, g.P, g.Mp, __shfl_sync(full, b, src),
+      row_slow_item(w.rowtop, w.colpack, g.RC, g.nRBC, g.nT, &g.d, g.Smax, g.P, g.Mp, __shfl_sync(full, b, src),
                     __shfl_sync(full, i, src), __shfl_sync(full, thr, src), __shfl_sync(full, rp.x, src),
                     __shfl_sync(full, rp.y, src), __shfl_sync(full, rp.z, src), sd, sj, sq);
       if (lane == src) { best_d = sd; best_j = sj; best_q = sq; }
@@ -1060,7 +1234,7 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(FGe
 bool f_sizes_ok(int B, int N, int M) {
   if (B <= 0 || N <= 0 || M <= 0) return false;
   if ((long long)N > (1LL << 30) || (long long)M > (1LL << 30)) return false;
-  const FGeometry g = f_make_geometry(B, N, M, 296, 1);
+  const FGeometry g = f_make_geometry(B, N, M, 148, 2, 1);
   if ((long long)B * g.Npad >= (1LL << 31) || (long long)B * g.Mp >= (1LL << 31)) return false;
   if ((long long)B * g.nRBC >= (1LL << 24)) return false;
   if ((long long)B * g.nRBC * g.nT >= (1LL << 31)) return false;   // unit indices are 32-bit in the resolve
@@ -1069,43 +1243,40 @@ bool f_sizes_ok(int B, int N, int M) {
 
 // Bytes of the filter's group records alone (the dispatcher's size criterion; device independent): B*N*M/64.
 size_t f_record_bytes(int B, int N, int M) {
-  const FGeometry g = f_make_geometry(B, N, M, 296, 1);
+  const FGeometry g = f_make_geometry(B, N, M, 148, 2, 1);
   return ((size_t)g.B * g.nRB * kFColTop * g.Mp) * sizeof(float);
 }
 
-// SM count and resident search CTAs per SM of the current device.  Immutable device properties, memoised per device
-// (the occupancy query costs ~10 us of host time, which matters for eager callers at ~90 us per step).  The memo is
-// a pure cache of constants: one packed atomic word per device (release / acquire), so concurrent first calls from
-// several threads at worst query twice and store the same value.
-static int f_caps(int* sms, int* occ) {
-  static std::atomic<unsigned> memo[64];   // 0 = empty, else (sms << 8) | occ
+// SM count of the current device (and the one-time shared-memory opt-in of the search kernels).  Immutable device
+// properties, memoised per device (the queries cost ~10 us of host time, which matters for eager callers at ~90 us per
+// step).  The memo is a pure cache of constants: one atomic word per device (release / acquire), so concurrent first
+// calls from several threads at worst query twice and store the same value.
+static int f_caps(int* sms) {
+  static std::atomic<unsigned> memo[64];   // 0 = empty, else the SM count
   int dev = 0;
   RMA_CUDA_TRY(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64) {
     const unsigned m = memo[dev].load(std::memory_order_acquire);
-    if (m) { *sms = (int)(m >> 8); *occ = (int)(m & 0xffu); return 0; }
+    if (m) { *sms = (int)m; return 0; }
   }
   RMA_CUDA_TRY(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
-  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem(4)));
-  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem(2)));
-  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem(1)));
-  // occupancy of the 4-warp CTA; the 2- and 1-warp CTAs use half / a quarter of its registers and shared memory and
-  // are launch-bounded to 2x / 4x as many resident CTAs (the same warps per SM)
-  RMA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, chamfer_fsearch_kernel<4>, kFThreads, f_smem(4)));
-  if (*occ < 1) *occ = 1;
-  if (*occ > 255) *occ = 255;
-  if (dev >= 0 && dev < 64) memo[dev].store(((unsigned)*sms << 8) | (unsigned)*occ, std::memory_order_release);
+  // a physical search CTA carries 8 / kW virtual CTAs, each with its own f_smem(kW) bytes: ~189 KB for every kW
+  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * f_smem(4))));
+  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * f_smem(2))));
+  RMA_CUDA_TRY(cudaFuncSetAttribute(chamfer_fsearch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * f_smem(1))));
+  if (*sms < 1) *sms = 1;
+  if (dev >= 0 && dev < 64) memo[dev].store((unsigned)*sms, std::memory_order_release);
   return 0;
 }
 
-// Geometry for the current device (the unit run depends on SM count x resident CTAs).  Re-derived per call: the
+// Geometry for the current device (the dealing depends on SM count x virtual CTAs per SM).  Re-derived per call: the
 // library keeps no state, and every stage of one forward derives the identical geometry.
 static int f_geometry(int B, int N, int M, int unit_run, FGeometry* g, int* occ_out) {
-  int sms = 0, occ = 0;
-  if (int e = f_caps(&sms, &occ)) return e;
+  int sms = 0;
+  if (int e = f_caps(&sms)) return e;
   const int W = f_warps_for((N + kFRowsPerWarp - 1) / kFRowsPerWarp);
-  occ *= kFWarps / W;                       // resident CTAs per SM for this CTA shape
-  *g = f_make_geometry(B, N, M, sms * occ, unit_run);
+  const int occ = (kFSearchThreads / 32) / W;   // virtual CTAs per physical CTA = per SM
+  *g = f_make_geometry(B, N, M, sms, occ, unit_run);
   if (occ_out) *occ_out = occ;
   return 0;
 }
@@ -1145,9 +1316,9 @@ int f_search_config(int B, int N, int M, int unit_run, int* ctas, int* threads, 
   FGeometry g;
   int occ = 0;
   if (int e = f_geometry(B, N, M, unit_run, &g, &occ)) return e;
-  if (ctas) *ctas = (int)((g.units() + g.U - 1) / g.U);
+  if (ctas) *ctas = g.nC;
   if (threads) *threads = 32 * g.W;
-  if (splits) *splits = g.U;          // for this path: 64-column tiles per CTA
+  if (splits) *splits = g.maxrun;     // for this path: 32-column units of the longest run
   if (ctas_per_sm) *ctas_per_sm = occ;
   return RMA_OK;
 }
@@ -1158,16 +1329,16 @@ int f_launch_search(int B, int N, int M, int unit_run, void* workspace, size_t w
   FSearchArgs a;
   a.rowsoa = w.rowsoa; a.colpair = w.colpair; a.rowtop = w.rowtop; a.colrec = w.colrec; a.stats = w.stats;
   a.N = N; a.M = M; a.nRB = g.nRB; a.Npad = g.Npad; a.nRBC = g.nRBC; a.nT = g.nT; a.Mp = g.Mp;
-  a.U = g.U; a.Smax = g.Smax; a.P = g.P; a.units = g.units();
-  const long long ctas = (a.units + g.U - 1) / g.U;
-  if (ctas > 0x7fffffffLL) return RMA_E_BADARG;
+  a.nC = g.nC; a.d = g.d; a.Smax = g.Smax; a.P = g.P; a.units = g.units();
+  if ((a.units + g.d.U - 1) / g.d.U > 0x7fffffffLL) return RMA_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream_;
+  const unsigned grid = (unsigned)g.G;
   if (g.W == 4)
-    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<4>, (unsigned)ctas, 128u, f_smem(4), st, a));
+    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<4>, grid, (unsigned)kFSearchThreads, 2 * f_smem(4), st, a));
   else if (g.W == 2)
-    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<2>, (unsigned)ctas, 64u, f_smem(2), st, a));
+    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<2>, grid, (unsigned)kFSearchThreads, 4 * f_smem(2), st, a));
   else
-    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<1>, (unsigned)ctas, 32u, f_smem(1), st, a));
+    RMA_CUDA_TRY(launch_dep(pdl_site(2), chamfer_fsearch_kernel<1>, grid, (unsigned)kFSearchThreads, 8 * f_smem(1), st, a));
   return RMA_OK;
 }
 
@@ -1176,8 +1347,8 @@ int f_launch_resolve(int B, int N, int M, int unit_run, const FinalizeArgs& f, v
   FGeometry g; FWorkspace w;
   if (int e = f_setup(B, N, M, unit_run, workspace, workspace_bytes, &g, &w)) return e;
   const long long warps = ((long long)B * N + 31) / 32 + ((long long)B * M + 31) / 32;
-  int sms = 0, occ = 0;
-  if (int e = f_caps(&sms, &occ)) return e;
+  int sms = 0;
+  if (int e = f_caps(&sms)) return e;
   long long grid = grid_for(warps, kFinWarps);            // one CTA per 8 items when that is more than one wave
   const long long wave = (long long)sms * 4;              // resident resolve CTAs (launch bounds: 4 per SM)
   if (grid <= wave) grid = warps < wave ? warps : wave;   // single wave: the same number of CTAs on every SM

@@ -20,7 +20,7 @@ SLOTS = ["prep start", "prep end", "search start", "search end", "resolve entry 
 
 def main():
     wl = sys.argv[1] if len(sys.argv) > 1 else "C2"
-    path = os.path.join(ROOT, "rma_net_b200", "lib", "librma_b200_tl.so")
+    path = os.environ.get("RMA_B200_TL_LIB") or os.path.join(ROOT, "rma_net_b200", "lib", "librma_b200_tl.so")
     lib = _lib.bind(ctypes.CDLL(path))
     lib.rma_debug_timeline_read.restype = ctypes.c_int
     lib.rma_debug_timeline_read.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
