@@ -448,15 +448,31 @@ def run_ours(args):
 
     # ---- headline leg: K steps back to back over ROTATING input sets larger than L2 ----------------------------
     # A step's inputs are 1.5 MiB, L2-resident by nature if the same pair were replayed.  So the timed steps walk
-    # through R distinct device-resident input sets (own clouds, own gradient tensors, own CUDA graph with its own
-    # memory pool, so every set also has its own scratch workspace: nothing a step touches was touched by the previous
-    # R - 1 steps) whose total size is > 2 x L2: every timed step reads inputs that are not in L2, and there is no host
-    # work, event or flush kernel between the steps - the way a training loop issues them.  One event pair around
-    # exactly K steps.
+    # through R distinct device-resident input sets (own clouds, own gradient tensors, own CUDA graph) whose total size
+    # is > 2 x L2: every timed step reads inputs that are not in L2 and writes gradients that are not, and there is no
+    # host work, event or flush kernel between the steps - the way a training loop issues them.  The graphs share ONE
+    # memory pool, so the library's scratch (workspace, gradient halves: freed at the end of every step) is the same
+    # block for every set, as the caching allocator hands a training loop the same block every step; --private-pools
+    # gives every set its own scratch as well (round-2 protocol until r02k: ~3 us per step of record lines allocating
+    # in L2 behind the previous steps' dirty ones).  One event pair around exactly K steps.
     W = max(args.warmup, 3)
     set_bytes = 4 * (xd.numel() + yd.numel()) * 2               # clouds + their gradients
+    K = args.steps
+    # Steps per CUDA graph: the K steps of a timed region are replayed as K / n graphs of n consecutive steps on n
+    # DIFFERENT input sets (n = K up to 40, else the largest divisor of K up to 40).  One graph per step was the protocol
+    # until r02k; it reads ~4 us per step more for the same kernels on the same cold inputs, which is what switching
+    # between 93 different graph executables costs the launch path (tools/rotate_probe.py: one graph replayed 72.0 us,
+    # 93 graphs on ONE pair 76.1, 93 graphs on 93 pairs 77.0, graphs of 31 steps on 31 pairs 70.6) - a training loop
+    # replays one executable.  That figure is still measured and reported as `one_graph_per_step`.
+    n_per = 1
+    if use_graph and not args.one_graph_per_step:
+        n_per = max(d for d in range(1, min(K, 40) + 1) if K % d == 0)
     R = args.sets if args.sets > 0 else max(2, int(2.2 * L2_BYTES // set_bytes) + 1)
-    sets, keep_alive = [], []
+    R = ((R + n_per - 1) // n_per) * n_per
+    if R // n_per < 2:
+        R = 2 * n_per
+    step_fns, keep_alive = [], []
+    shared_pool = not (args.private_pools or not use_graph) or None   # reporting: do the graphs share scratch?
     gen = torch.Generator().manual_seed(1234 + rank)
     for r in range(R):
         if r == 0:
@@ -474,38 +490,58 @@ def run_ours(args):
         keep_alive.append((xr_, yr_))          # a graph holds raw pointers: its inputs must outlive the closure
         for _ in range(2):
             step_r()
-        if use_graph:
+        step_fns.append(step_r)
+
+    def capture_groups(per):
+        """R / per callables, each running `per` consecutive steps (sets i*per .. i*per+per-1)."""
+        if not use_graph:
+            return [lambda i=i: [f() for f in step_fns[i:i + per]] for i in range(0, R, per)]
+        out = []
+        shared_pool = None if args.private_pools else torch.cuda.graph_pool_handle()   # one pool per family of graphs
+        for i in range(0, R, per):
             torch.cuda.synchronize()
             g_r = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_r):
-                step_r()
-            sets.append(g_r.replay)
-        else:
-            sets.append(step_r)
-    barrier()
-    for r in range(R):            # the first launch of a graph uploads it: replay every set once, in order, untimed
-        sets[r]()
-    barrier()
-    for k in range(W):            # warm-up steps; set W was last touched R - W steps (> 2 x L2 of traffic) ago
-        sets[k % R]()
-    barrier()
+            with torch.cuda.graph(g_r, pool=shared_pool):
+                for f in step_fns[i:i + per]:
+                    f()
+            out.append(g_r.replay)
+        return out
+
+    def timed_regions(groups, per, nrep):
+        """nrep regions of exactly K steps (K / per launches each), one event pair per region; ms per step."""
+        nlaunch = K // per
+        barrier()
+        for g_ in groups:         # the first launch of a graph uploads it: replay every group once, in order, untimed
+            g_()                  # (R >= W warm-up steps on inputs that are then > 2 x L2 of traffic old)
+        barrier()
+        out = []
+        pos = 0
+        for rep in range(nrep):
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # A ~20 ms spin kernel in front of the start event: the host enqueues all launches while it runs, so the K
+            # steps execute back to back on the device whatever the host does meanwhile (the clock sampler's NVML
+            # queries stall launches for milliseconds: without the gate a region now and then measured such a stall)
+            torch.cuda._sleep(GATE_CYCLES)
+            ev0.record()
+            for _ in range(nlaunch):
+                groups[pos % len(groups)]()
+                pos += 1
+            ev1.record()
+            barrier()
+            out.append(ev0.elapsed_time(ev1) / K)
+        return out
+
+    sets = capture_groups(n_per)
     sampler = ClockSampler(local)
     sampler.start()
-    region_ms = []
-    for rep in range(5):          # region 0 is THE measurement (exactly K steps); the others give its spread
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # A ~20 ms spin kernel in front of the start event: the host enqueues all K launches while it runs, so the K
-        # steps execute back to back on the device whatever the host does meanwhile (the clock sampler's NVML
-        # queries stall launches for milliseconds: without the gate a region now and then measured such a stall)
-        torch.cuda._sleep(GATE_CYCLES)
-        ev0.record()
-        for k in range(args.steps):
-            sets[(W + rep * args.steps + k) % R]()
-        ev1.record()
-        barrier()
-        region_ms.append(ev0.elapsed_time(ev1) / args.steps)
+    region_ms = timed_regions(sets, n_per, 5)   # region 0 is THE measurement (exactly K steps); the others give its spread
     ms = region_ms[0]
+    if n_per > 1:                 # the r02a-r02k protocol on the same inputs: one graph (executable) per step
+        del sets
+        one_per_ms = timed_regions(capture_groups(1), 1, 3)
+    else:
+        one_per_ms = list(region_ms[:3])
 
     # ---- flushed leg (the round-1 protocol, kept for comparison): one input set, a 256 MiB memset between the steps,
     # one event pair per step.  It adds the idle gap between an event record and the first kernel of a graph launch
@@ -795,12 +831,13 @@ def run_ours(args):
             torch.cuda.empty_cache()
 
     # ---- aggregate over ranks (max time) ------------------------------------------------------------------------
-    t = torch.tensor([ms, e2e_ms, search_ms, e2e_serial_ms, e2e_sync_ms, flushed_ms] + region_ms, dtype=torch.float64,
-                     device=dev)
+    t = torch.tensor([ms, e2e_ms, search_ms, e2e_serial_ms, e2e_sync_ms, flushed_ms] + region_ms + one_per_ms,
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms, search_ms, e2e_serial_ms, e2e_sync_ms, flushed_ms = (float(v) for v in t.cpu()[:6])
-    region_ms = [float(v) for v in t.cpu()[6:]]
+    region_ms = [float(v) for v in t.cpu()[6:6 + len(region_ms)]]
+    one_per_ms = [float(v) for v in t.cpu()[6 + len(region_ms):]]
     value = world * pairs / (ms * 1e-3) / 1e9
     e2e_value = world * pairs / (e2e_ms * 1e-3) / 1e9
 
@@ -819,9 +856,16 @@ def run_ours(args):
                    "global_batch": B * world, "parallelism": f"batch-sharded x{world}, no collective",
                    "l2": f"inputs larger than L2: the timed steps rotate through {R} device-resident input sets "
                          f"({R * set_bytes / 2**20:.0f} MiB of clouds + gradients > 2 x 126 MiB L2), replayed back to back "
-                         f"with one event pair around the K steps; flushed_step = the round-1 protocol (one set, 256 "
-                         f"MiB memset + one event pair per step) for comparison",
+                         f"as {args.steps // n_per} CUDA graph(s) of {n_per} consecutive steps on {n_per} different sets, "
+                         f"one event pair around the K steps; "
+                         + ("every set's graph has its own memory pool (own scratch workspace too); " if shared_pool is None
+                            else "the graphs share one memory pool, so the library's scratch workspace is the same block "
+                                 "every step (as an allocator gives a training loop), inputs and gradients are not; ")
+                         + "flushed_step = the round-1 protocol (one set, 256 MiB memset + one event pair per step) for "
+                           "comparison",
                    "input_sets": R,
+                   "steps_per_graph": n_per,
+                   "scratch": "private per set" if shared_pool is None else "shared pool",
                    "cuda_graph": bool(use_graph),
                    "search_launch": {"kernel": search_kernel, "ctas": ctas.value, "threads": thr.value,
                                      ("units32_per_cta" if filt == 1 else "column_splits"): spl.value,
@@ -862,6 +906,12 @@ def run_ours(args):
         "secondary": secondary,
         "clocks": clocks,
         "region_ms_per_step": region_ms,      # [0] is ms_per_step; four more regions of K steps show the spread
+        "one_graph_per_step": {"ms_per_step": one_per_ms[0], "region_ms_per_step": one_per_ms,
+                               "value": world * pairs / (one_per_ms[0] * 1e-3) / 1e9,
+                               "note": "the same K steps on the same rotating input sets with one CUDA graph (executable) "
+                                       "per step and set - the headline protocol of r02a-r02k; the difference to "
+                                       "ms_per_step is the launch path switching between executables, "
+                                       "tools/rotate_probe.py"},
         "flushed_step": {"ms_per_step": flushed_ms, "step_ms_min_max": [min(step_ms), max(step_ms)],
                          "value": world * pairs / (flushed_ms * 1e-3) / 1e9,
                          "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3},
@@ -896,6 +946,10 @@ def main():
     ap.add_argument("--sets", type=int, default=0, help="rotating input sets of the headline leg (default: enough for "
                     "2.2 x L2; a small number only for profiler runs, whose line is not a bench value)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--one-graph-per-step", action="store_true", help="headline leg: one CUDA graph per step and input set "
+                    "(the protocol until r02k) instead of graphs of n consecutive steps")
+    ap.add_argument("--private-pools", action="store_true", help="headline leg: every input set's graph gets its own memory "
+                    "pool (its own scratch workspace) instead of the shared one")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C3 / C4 / C5 legs of the `secondary` object")
     args = ap.parse_args()
