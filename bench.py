@@ -651,9 +651,14 @@ def run_ours(args):
             torch.cuda.current_stream().synchronize()
             return float(loss_pin)
 
-    for _ in range(3):
-        e2e_step()
+    # Every e2e region below: barrier, then W warm-up steps of the same loop, then - without another synchronisation in
+    # between - the start event and exactly K timed steps.  (With the barrier directly in front of the start event the
+    # first step of a region started on an idle GPU; on some boxes that cost ~1.2 ms per region, i.e. 60 us per step at
+    # K = 20 and 6 us at K = 200.)
+    E2E_W = max(args.warmup, 3)
     barrier()
+    for _ in range(E2E_W):
+        e2e_step()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -678,12 +683,21 @@ def run_ours(args):
 
         loss_pins = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
 
+        d2h_stream = torch.cuda.Stream()
+
         def compute(i):
+            # the 4-byte D2H copy of the loss is issued as soon as the forward has produced it, on a side stream (a
+            # parallel branch of the captured graph), so that the copy engine's latency runs beside the backward
+            # kernels instead of behind them
             xs[i].grad = None
             ys[i].grad = None
             loss = loss_on_cd(xs[i], ys[i])
+            cur = torch.cuda.current_stream()
+            d2h_stream.wait_stream(cur)
+            with torch.cuda.stream(d2h_stream):
+                loss_pins[i].copy_(loss.detach(), non_blocking=True)
             loss.backward()
-            loss_pins[i].copy_(loss.detach(), non_blocking=True)
+            cur.wait_stream(d2h_stream)
 
         graphs = []
         for i in range(2):
@@ -742,6 +756,7 @@ def run_ours(args):
             reps_ms = []
             for _ in range(E2E_REPS):
                 barrier()
+                run_pipelined(E2E_W, lag=lag)
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
                 pipelined_loss = run_pipelined(args.steps, ev0, lag=lag)
@@ -790,6 +805,7 @@ def run_ours(args):
         fused_ms = []
         for _ in range(E2E_REPS):
             barrier()
+            run_fused(E2E_W)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
             fused_loss = run_fused(args.steps)
