@@ -579,3 +579,41 @@ def test_fused_loss_weight_contract(cuda):
     xn = x.clone()
     xn[1, 5, 0] = float("nan")
     assert torch.isnan(ext.chamfer_cd_forward(xn, y, False, False, w, 0.25)[0])
+
+
+def test_alternating_inputs_through_one_workspace(cuda):
+    """The resolve reads its item's pack entry before its dependency wait (csrc/chamfer_filter.cu): results must follow
+    the inputs when two different pairs alternate through the same workspace and output buffers, step after step."""
+    from rma_net_b200.model.loss import chamfer_dist_with_idx, loss_on_cd
+    g = torch.Generator().manual_seed(33)
+    B, N, M = 8, 2048, 1536
+    pairs = [((torch.rand(B, N, 3, generator=g) * 2 - 1).to(cuda), (torch.rand(B, M, 3, generator=g) * 2 - 1).to(cuda))
+             for _ in range(2)]
+    ref = [[t.clone() for t in chamfer_dist_with_idx(x, y)] for x, y in pairs]
+    ref_loss = [float(loss_on_cd(x, y)) for x, y in pairs]
+    assert not torch.equal(ref[0][2], ref[1][2])
+    graphs = []
+    outs = []
+    for x, y in pairs:                    # the caching allocator hands both captures the same workspace block
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            chamfer_dist_with_idx(x, y)
+        torch.cuda.synchronize()
+    pool = torch.cuda.graph_pool_handle()
+    for x, y in pairs:
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, pool=pool):
+            o = chamfer_dist_with_idx(x, y)
+            l = loss_on_cd(x, y)
+        graphs.append(gr)
+        outs.append((o, l))
+    for it in range(40):
+        k = it & 1
+        graphs[k].replay()
+        graphs[k ^ 1].replay()
+        graphs[k].replay()
+        torch.cuda.synchronize()
+        o, l = outs[k]
+        for a, b_ in zip(o, ref[k]):
+            assert torch.equal(a, b_), it
+        assert float(l) == ref_loss[k]
