@@ -97,6 +97,14 @@ int rma_chamfer_finalize(int B, int N, int M, float* dist1, float* dist2, int32_
 int rma_chamfer_search_config(int B, int N, int M, const rma_chamfer_opts* opts, int* ctas, int* threads, int* splits,
                               int* ctas_per_sm);
 
+/* Host-only diagnostic (no device needed): checks the filter path's work decomposition for (B,N,M,opts) as it would be
+ * derived on a device with `sms` SMs - every work unit covered by exactly one run, segment indices and record counts
+ * inside what the workspace is carved for, search and resolve agreeing on every row block's segments.  Returns the
+ * number of inconsistencies (0 = consistent) or -1 for unsupported sizes; *mode = 0 contiguous / 1 row-block aligned,
+ * load_min_max[0..1] = fewest / most work units on one SM. */
+int rma_chamfer_dealing_selfcheck(int B, int N, int M, int sms, const rma_chamfer_opts* opts, int* mode,
+                                  int64_t* load_min_max);
+
 /* Fused loss_on_cd (model/loss.py:200-205 on top of chamfer_dist): in the same three launches,
  *   *loss = 0.5 * (sum dist1 + sum dist2) / B                       (device scalar, overwritten)
  * and its gradient, split so that only the scattered half needs atomics:

@@ -27,6 +27,7 @@ SIGNATURES = {
     "rma_b200_device_info": (c_int, [_P, _P, _P, _P]),
     "rma_chamfer_workspace_bytes": (c_size_t, [c_int, c_int, c_int, _O]),
     "rma_chamfer_path": (c_int, [c_int, c_int, c_int, _O]),
+    "rma_chamfer_dealing_selfcheck": (c_int, [c_int, c_int, c_int, c_int, _O, _P, _P]),
     "rma_chamfer_guard_stats": (c_int, [c_int, c_int, c_int, _P, _O, _P, _P]),
     "rma_chamfer_forward": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, c_int, c_int, c_int,
                                     _P, _P, _P, _P, _P, c_size_t, _O, _P]),

@@ -607,6 +607,7 @@ int f_launch_search(int B, int N, int M, int unit_run, void* workspace, size_t w
 int f_launch_resolve(int B, int N, int M, int unit_run, const FinalizeArgs& f, void* workspace,
                      size_t workspace_bytes, void* stream_);
 int f_read_stats(void* workspace, int B, int N, int M, int unit_run, unsigned* out4, void* stream_);
+int f_dealing_selfcheck(int B, int N, int M, int sms, int unit_run, int* mode_out, long long* load2_out);
 }  // namespace rma
 
 // Which search runs: the filter path whenever its group records (B*N*M/64 bytes) stay below the cap, else the
@@ -682,6 +683,15 @@ size_t rma_chamfer_workspace_bytes(int B, int N, int M, const rma_chamfer_opts* 
   size_t bytes = carve(g, nullptr).bytes;
   if (use_filter(B, N, M, o)) { const size_t fb = f_workspace_bytes(B, N, M, o.unit_run); if (fb > bytes) bytes = fb; }
   return bytes;
+}
+
+int rma_chamfer_dealing_selfcheck(int B, int N, int M, int sms, const rma_chamfer_opts* opts, int* mode,
+                                  int64_t* load_min_max) {
+  const ChamferOpts o = make_opts(opts);
+  long long l2[2] = {0, 0};
+  const int r = f_dealing_selfcheck(B, N, M, sms, o.unit_run, mode, l2);
+  if (load_min_max) { load_min_max[0] = l2[0]; load_min_max[1] = l2[1]; }
+  return r;
 }
 
 int rma_chamfer_path(int B, int N, int M, const rma_chamfer_opts* opts) {

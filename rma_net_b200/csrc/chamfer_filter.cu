@@ -27,6 +27,7 @@
 //   guard_row / guard_col below evaluate these bounds with >= 1% slack plus an absolute 1e-30 for underflow.
 #include <atomic>
 #include <type_traits>
+#include <vector>
 
 #include "chamfer_common.cuh"
 #include "../../include/rma_b200.h"
@@ -99,8 +100,12 @@ __device__ __forceinline__ void tl_mark(unsigned* stats, int slot) {
 // t / d for t < 2^31 with m = min(ceil(2^32 / d), 2^32 - 1): umulhi(t, m) is off by at most one either way (the
 // estimate t m / 2^32 lies in [t/d - t/2^32, t/d + t/2^32)), so one multiply-back and two selects make it exact - six
 // instructions against ~20 for the emulated 32-bit division (the resolve had five of them per lane).
-__device__ __forceinline__ unsigned fdiv(unsigned t, unsigned d, unsigned m) {
+__host__ __device__ __forceinline__ unsigned fdiv(unsigned t, unsigned d, unsigned m) {
+#ifdef __CUDA_ARCH__
   unsigned q = __umulhi(t, m);
+#else
+  unsigned q = (unsigned)(((unsigned long long)t * m) >> 32);
+#endif
   const int r = (int)(t - q * d);
   q = r < 0 ? q - 1u : q;
   q = r >= (int)d ? q + 1u : q;
@@ -275,7 +280,7 @@ static FGeometry f_make_geometry(int B, int N, int M, int sms, int occ, int forc
 }
 
 // Segments of row block brb: how many CTAs share it (nseg) and, for mode 0, the first of them (kfirst).
-__device__ __forceinline__ void f_rowblock_segments(const FDeal& d, unsigned brb, int nT, int& kfirst, int& nseg) {
+__host__ __device__ __forceinline__ void f_rowblock_segments(const FDeal& d, unsigned brb, int nT, int& kfirst, int& nseg) {
   if (d.mode == 1) {
     kfirst = 0;
     nseg = (int)brb < d.Rhi ? d.clo + 1 : d.clo;
@@ -289,13 +294,38 @@ __device__ __forceinline__ void f_rowblock_segments(const FDeal& d, unsigned brb
   nseg = (int)cta_of(ulast) - kfirst + 1;
 }
 // Units [ua, ub), relative to the row block, of its segment number srel.
-__device__ __forceinline__ void f_segment_units(const FDeal& d, unsigned brb, int nT, int kfirst, int nseg, unsigned srel,
-                                                unsigned& ua, unsigned& ub) {
+__host__ __device__ __forceinline__ void f_segment_units(const FDeal& d, unsigned brb, int nT, int kfirst, int nseg,
+                                                         unsigned srel, unsigned& ua, unsigned& ub) {
   if (d.mode == 1) { f_aligned_run(nT, nseg, (int)srel, ua, ub); return; }
   const unsigned u0 = brb * (unsigned)nT, u1 = u0 + (unsigned)nT;
   const unsigned ks = (unsigned)f_cta_start(kfirst + (int)srel, d.U, d.Us, d.nL, d.uL);
   const unsigned ke = (unsigned)f_cta_start(kfirst + (int)srel + 1, d.U, d.Us, d.nL, d.uL);
-  ua = max(ks, u0) - u0; ub = min(ke, u1) - u0;
+  ua = (ks > u0 ? ks : u0) - u0; ub = (ke < u1 ? ke : u1) - u0;
+}
+// The run of virtual CTA (block, layer) of a grid of G physical CTAs: units [unit, unit_end) and, in aligned mode, its
+// segment index inside its row block.  Shared by the search kernel and the host-side self-check.
+__host__ __device__ __forceinline__ void f_virtual_run(const FDeal& d, int nT, int nC, long long units, int G, int block,
+                                                       int layer, long long& unit, long long& unit_end, int& seg_aligned) {
+  seg_aligned = 0;
+  if (d.mode == 1) {
+    // serpentine over the runs sorted by length: layer `layer` of the SM that runs physical CTA `block`
+    const int lo = layer * G, rest = nC - lo, sz = G < rest ? G : rest;
+    const int sidx = lo + ((layer & 1) ? sz - 1 - block : block);
+    int ci = 0;
+    while (ci + 1 < d.ncls && sidx >= d.cls_base[ci + 1]) ++ci;
+    const int o = sidx - d.cls_base[ci];
+    const int rbk = d.cls_rb0[ci] + o / d.cls_per[ci];
+    seg_aligned = d.cls_pos0[ci] + o % d.cls_per[ci];
+    unsigned ua, ub;
+    f_aligned_run(nT, rbk < d.Rhi ? d.clo + 1 : d.clo, seg_aligned, ua, ub);
+    unit = (long long)rbk * nT + ua;
+    unit_end = (long long)rbk * nT + ub;
+  } else {
+    const int v = block + layer * G;
+    unit = f_cta_start(v, d.U, d.Us, d.nL, d.uL);
+    const long long e = f_cta_start(v + 1, d.U, d.Us, d.nL, d.uL);
+    unit_end = e < units ? e : units;
+  }
 }
 
 struct FWorkspace {
@@ -455,24 +485,8 @@ __global__ void __launch_bounds__(kFSearchThreads, 1) chamfer_fsearch_kernel(FSe
   asm volatile("" : "+r"(rtag_mask));
 
   long long unit, unit_end;
-  int seg_aligned = 0;
-  if (a.d.mode == 1) {
-    // serpentine over the runs sorted by length: layer `group` of SM blockIdx.x
-    const int G = (int)gridDim.x, lo = group * G, sz = min(G, a.nC - lo);
-    const int sidx = lo + ((group & 1) ? sz - 1 - (int)blockIdx.x : (int)blockIdx.x);
-    int ci = 0;
-    while (ci + 1 < a.d.ncls && sidx >= a.d.cls_base[ci + 1]) ++ci;
-    const int o = sidx - a.d.cls_base[ci];
-    const int rbk = a.d.cls_rb0[ci] + o / a.d.cls_per[ci];
-    seg_aligned = a.d.cls_pos0[ci] + o % a.d.cls_per[ci];
-    unsigned ua, ub;
-    f_aligned_run(a.nT, rbk < a.d.Rhi ? a.d.clo + 1 : a.d.clo, seg_aligned, ua, ub);
-    unit = (long long)rbk * a.nT + ua;
-    unit_end = (long long)rbk * a.nT + ub;
-  } else {
-    unit = f_cta_start(vblock, a.d.U, a.d.Us, a.d.nL, a.d.uL);
-    unit_end = min(f_cta_start(vblock + 1, a.d.U, a.d.Us, a.d.nL, a.d.uL), a.units);
-  }
+  int seg_aligned;
+  f_virtual_run(a.d, a.nT, a.nC, a.units, (int)gridDim.x, (int)blockIdx.x, group, unit, unit_end, seg_aligned);
   if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
   group_sync();
   int cur = 0;           // column buffer the next chunk lands in
@@ -1368,6 +1382,62 @@ int f_launch_resolve(int B, int N, int M, int unit_run, const FinalizeArgs& f, v
   RMA_CUDA_TRY(launch_dep(pdl_site(4), chamfer_fresolve_kernel, (unsigned)grid, (unsigned)(kFinWarps * 32), 0,
                           (cudaStream_t)stream_, g, w, f, (unsigned)(warps / grid), (unsigned)(warps % grid)));
   return RMA_OK;
+}
+
+// Host-only self-check of the dealing for a device with `sms` SMs: every unit is covered by exactly one run, no run of
+// the aligned mode crosses a row block, segment indices and entry counts stay inside what the workspace is carved for,
+// and the resolve's view of a row block's segments (f_rowblock_segments / f_segment_units) is the search's.  Returns
+// the number of inconsistencies (0 = consistent), -1 for unsupported sizes; load[0..1] = min / max units per SM.
+int f_dealing_selfcheck(int B, int N, int M, int sms, int unit_run, int* mode_out, long long* load2_out) {
+  if (sms < 1 || !f_sizes_ok(B, N, M)) return -1;
+  const int W = f_warps_for((N + kFRowsPerWarp - 1) / kFRowsPerWarp);
+  const int occ = (kFSearchThreads / 32) / W;
+  const FGeometry g = f_make_geometry(B, N, M, sms, occ, unit_run);
+  const long long units = g.units();
+  if (units > (1LL << 26)) return -1;
+  std::vector<unsigned char> cover((size_t)units, 0);
+  std::vector<long long> load((size_t)g.G, 0);
+  int bad = 0;
+  for (int layer = 0; layer < occ || (long long)layer * g.G < g.nC; ++layer) {
+    if ((long long)layer * g.G >= g.nC) break;
+    for (int block = 0; block < g.G; ++block) {
+      if (block + (long long)layer * g.G >= g.nC) continue;
+      if (layer >= occ) { ++bad; continue; }          // more layers than a physical CTA has warp groups
+      long long unit, unit_end; int seg_aligned;
+      f_virtual_run(g.d, g.nT, g.nC, units, g.G, block, layer, unit, unit_end, seg_aligned);
+      if (unit < 0 || unit_end > units || unit_end < unit || unit_end - unit > g.maxrun) { ++bad; continue; }
+      if (unit_end == unit && unit_run <= 0) ++bad;   // only a forced run length may leave the last CTA empty
+      load[(size_t)block] += unit_end - unit;
+      for (long long u = unit; u < unit_end; ++u) if (++cover[(size_t)u] != 1) ++bad;
+      int nsegments = 0;
+      while (unit < unit_end) {                       // the kernel's walk over the run's segments
+        const int brb = (int)(unit / g.nT), unit0 = (int)(unit - (long long)brb * g.nT);
+        const long long left = unit_end - unit;
+        const int nunit = (int)((long long)(g.nT - unit0) < left ? (long long)(g.nT - unit0) : left);
+        unit += nunit;
+        ++nsegments;
+        int kfirst, nsegs;
+        f_rowblock_segments(g.d, (unsigned)brb, g.nT, kfirst, nsegs);
+        const int v = block + layer * g.G;
+        const int seg = g.d.mode == 1 ? seg_aligned : v - kfirst;
+        if (seg < 0 || seg >= nsegs || nsegs > g.Smax) { ++bad; continue; }
+        unsigned ua, ub;
+        f_segment_units(g.d, (unsigned)brb, g.nT, kfirst, nsegs, (unsigned)seg, ua, ub);
+        if ((int)ua != unit0 || (int)ub != unit0 + nunit) ++bad;
+        const int tiles = ((unit0 + nunit - 1) >> 1) - (unit0 >> 1) + 1;
+        if (tiles > g.P * kFSubTiles) ++bad;
+      }
+      if (g.d.mode == 1 && nsegments != 1) ++bad;
+    }
+  }
+  for (long long u = 0; u < units; ++u) if (cover[(size_t)u] != 1) ++bad;
+  if (mode_out) *mode_out = g.d.mode;
+  if (load2_out) {
+    long long lo = load[0], hi = load[0];
+    for (long long v : load) { lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
+    load2_out[0] = lo; load2_out[1] = hi;
+  }
+  return bad;
 }
 
 int f_read_stats(void* workspace, int B, int N, int M, int unit_run, unsigned* out4_host, void* stream_) {
