@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RMA_B200_ABI_VERSION 2
+#define RMA_B200_ABI_VERSION 3
 
 #define RMA_OK 0
 #define RMA_E_BADARG (-1)     /* null pointer / non-positive size / size overflow */
@@ -65,6 +65,11 @@ typedef struct rma_chamfer_opts {
   int32_t path;               /* RMA_CHAMFER_PATH_*: force one search implementation (parity tests, A/B timing) */
   int32_t unit_run;           /* > 0: 32-column work units per search CTA (filter path) / column splits (exact path) */
   int64_t record_cap_bytes;   /* > 0: switch-over size of the automatic choice */
+  int32_t y_batch_period;     /* > 0 (ABI 3; rma_chamfer_cd_forward* and rma_chamfer_prep only): y holds y_batch_period
+                                 batch elements and batch element b of the call uses y[b % y_batch_period] - the stage
+                                 loop's repeated target (loss.py:260-267) without materialising T copies of it.  B must be
+                                 a multiple; idx / dist / gradient outputs stay per batch element of the call */
+  int32_t reserved_;
 } rma_chamfer_opts;
 size_t rma_chamfer_workspace_bytes(int B, int N, int M, const rma_chamfer_opts* opts);
 /* RMA_CHAMFER_PATH_EXACT or RMA_CHAMFER_PATH_FILTER: what (B,N,M,opts) runs (< 0: bad sizes). */

@@ -14,7 +14,8 @@ _I64 = c_int64
 
 class ChamferOpts(ctypes.Structure):
     """`rma_chamfer_opts` of include/rma_b200.h: per-call choice of the search implementation (no library state)."""
-    _fields_ = [("path", c_int32), ("unit_run", c_int32), ("record_cap_bytes", c_int64)]
+    _fields_ = [("path", c_int32), ("unit_run", c_int32), ("record_cap_bytes", c_int64),
+                ("y_batch_period", c_int32), ("reserved_", c_int32)]
 
 
 PATH_AUTO, PATH_EXACT, PATH_FILTER = 0, 1, 2

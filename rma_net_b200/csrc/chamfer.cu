@@ -40,6 +40,7 @@ struct Geometry {
   int Npad;   // nRB * 512
   int nRBC;   // CTA row blocks (2048 rows) per batch element
   int Mp;     // padded column count: roundup(M, 32) + 32
+  int yper;   // > 0: batch element b reads y[b % yper] (rma_chamfer_opts.y_batch_period)
   __host__ __device__ size_t rowpack_floats() const { return (size_t)B * Npad * 3; }
   __host__ __device__ size_t colpack_float4() const { return (size_t)B * Mp; }
 };
@@ -51,6 +52,7 @@ static Geometry make_geometry(int B, int N, int M) {
   g.Npad = g.nRB * kRowsPerWarp;
   g.nRBC = (g.nRB + kSearchWarps - 1) / kSearchWarps;
   g.Mp = (M + kTile - 1) / kTile * kTile + kTile;
+  g.yper = 0;
   return g;
 }
 
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(256) chamfer_prep_kernel(
       const int b = (int)(u / g.Mp), j = (int)(u % g.Mp);
       float nx = kColSentinelNeg, ny = kColSentinelNeg, nz = kColSentinelNeg;
       if (j < g.M) {
-        const float* s = y + b * ysb + j * ysn;
+        const float* s = y + (g.yper > 0 ? b % g.yper : b) * ysb + j * ysn;
         nx = -s[0]; ny = -s[ysc]; nz = -s[2 * ysc];
         if (zero_gy) zero_gy[(long long)b * g.M + j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -600,7 +602,7 @@ bool f_sizes_ok(int B, int N, int M);
 size_t f_record_bytes(int B, int N, int M);
 size_t f_workspace_bytes(int B, int N, int M, int unit_run);
 int f_launch_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc, const float* y, int64_t ysb, int64_t ysn,
-                  int64_t ysc, int B, int N, int M, int unit_run, void* workspace, size_t workspace_bytes,
+                  int64_t ysc, int B, int N, int M, int unit_run, int y_period, void* workspace, size_t workspace_bytes,
                   float* zero_loss, float4* zero_gx, float4* zero_gy, void* stream_);
 int f_search_config(int B, int N, int M, int unit_run, int* ctas, int* threads, int* splits, int* ctas_per_sm);
 int f_launch_search(int B, int N, int M, int unit_run, void* workspace, size_t workspace_bytes, void* stream_);
@@ -626,14 +628,16 @@ struct ChamferOpts {
   int path;        // RMA_CHAMFER_PATH_*
   int unit_run;    // 0 = automatic
   size_t cap;      // filter record cap in bytes
+  int y_period;    // 0 = every batch element has its own y
 };
 
 static ChamferOpts make_opts(const rma_chamfer_opts* o) {
-  ChamferOpts r = {RMA_CHAMFER_PATH_AUTO, 0, g_default_record_cap};
+  ChamferOpts r = {RMA_CHAMFER_PATH_AUTO, 0, g_default_record_cap, 0};
   if (o) {
     if (o->path == RMA_CHAMFER_PATH_EXACT || o->path == RMA_CHAMFER_PATH_FILTER) r.path = o->path;
     if (o->unit_run > 0) r.unit_run = o->unit_run;
     if (o->record_cap_bytes > 0) r.cap = (size_t)o->record_cap_bytes;
+    if (o->y_batch_period > 0) r.y_period = o->y_batch_period;
   }
   return r;
 }
@@ -721,11 +725,13 @@ static int launch_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
                        const float* y, int64_t ysb, int64_t ysn, int64_t ysc, int B, int N, int M,
                        const ChamferOpts& o, void* workspace, size_t workspace_bytes, float* zero_loss,
                        float4* zero_gx, float4* zero_gy, void* stream_) {
+  if (o.y_period > 0 && (B <= 0 || B % o.y_period != 0)) return RMA_E_BADARG;
   if (x && y && sizes_ok(B, N, M) && use_filter(B, N, M, o))
-    return f_launch_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, o.unit_run, workspace, workspace_bytes,
+    return f_launch_prep(x, xsb, xsn, xsc, y, ysb, ysn, ysc, B, N, M, o.unit_run, o.y_period, workspace, workspace_bytes,
                          zero_loss, zero_gx, zero_gy, stream_);
   Geometry g; Workspace w;
   if (int e = forward_setup(x, y, B, N, M, workspace, workspace_bytes, &g, &w)) return e;
+  g.yper = o.y_period;
   const long long slots = (long long)B * (g.Npad + g.Mp);
   RMA_CUDA_TRY(launch_pdl(chamfer_prep_kernel, (unsigned)grid_for(slots, 256), 256u, 0, (cudaStream_t)stream_,
                           x, (long long)xsb, (long long)xsn, (long long)xsc, y, (long long)ysb, (long long)ysn,

@@ -164,6 +164,7 @@ struct FGeometry {
   int nC;     // virtual search CTAs (runs)
   int G;      // physical search CTAs (grid): virtual CTA v = block + layer * G, layer = warp group of the block
   int maxrun; // units of the longest run
+  int yper;   // > 0: batch element b reads y[b % yper] (rma_chamfer_opts.y_batch_period); prep only
   int Smax;   // max segments (CTAs) that share one CTA row block
   int P;      // row-direction entries per segment: a run of n units touches <= n / 2 + 1 tiles, one entry per 16 tiles
   unsigned magicN, magicM;   // ceil(2^32 / d) (clipped to 2^32 - 1): fast exact division in the resolve (fdiv)
@@ -273,6 +274,7 @@ static FGeometry f_make_geometry(int B, int N, int M, int sms, int occ, int forc
   }
 #endif
   g.maxrun = maxrun;
+  g.yper = 0;
   g.P = ((maxrun < g.nT ? maxrun : g.nT) / 2 + 1 + kFSubTiles - 1) / kFSubTiles;
   g.magicN = magic((unsigned)N); g.magicM = magic((unsigned)M);
   g.rc_shift = g.W == 4 ? 11 : g.W == 2 ? 10 : 9;
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(256) chamfer_fprep_kernel(
       const int b = (int)(u / g.Mp), j = (int)(u % g.Mp);
       float4 v = make_float4(0.f, 0.f, 0.f, kFBig);
       if (j < g.M) {
-        const float* s = y + b * ysb + j * ysn;
+        const float* s = y + (g.yper > 0 ? b % g.yper : b) * ysb + j * ysn;
         const float px = s[0], py = s[ysc], pz = s[2 * ysc];
         v = make_float4(-2.f * px, -2.f * py, -2.f * pz, norm2_rn(px, py, pz));
         if (zero_gy) zero_gy[(long long)b * g.M + j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1326,11 +1328,12 @@ static int f_setup(int B, int N, int M, int unit_run, void* workspace, size_t wo
 
 int f_launch_prep(const float* x, int64_t xsb, int64_t xsn, int64_t xsc,
                   const float* y, int64_t ysb, int64_t ysn, int64_t ysc, int B, int N, int M, int unit_run,
-                  void* workspace, size_t workspace_bytes, float* zero_loss, float4* zero_gx, float4* zero_gy,
-                  void* stream_) {
+                  int y_period, void* workspace, size_t workspace_bytes, float* zero_loss, float4* zero_gx,
+                  float4* zero_gy, void* stream_) {
   if (!x || !y) return RMA_E_BADARG;
   FGeometry g; FWorkspace w;
   if (int e = f_setup(B, N, M, unit_run, workspace, workspace_bytes, &g, &w)) return e;
+  g.yper = y_period;
   const long long slots = (long long)B * (g.Npad + g.Mp);
   RMA_CUDA_TRY(launch_dep(pdl_site(1), chamfer_fprep_kernel, (unsigned)grid_for(slots, 256), 256u, 0, (cudaStream_t)stream_,
                           x, (long long)xsb, (long long)xsn, (long long)xsc, y, (long long)ysb, (long long)ysn,

@@ -138,24 +138,37 @@ def chamfer_backward(points_x, points_y, idx1, idx2, g1, g2, need_x: bool = True
 
 def chamfer_cd_forward(points_x: torch.Tensor, points_y: torch.Tensor, need_x: bool, need_y: bool,
                        batch_weight: Optional[torch.Tensor] = None, coef: Optional[float] = None,
-                       want_dist: bool = False):
+                       want_dist: bool = False, y_period: int = 0):
     """Fused loss_on_cd: returns (loss 0-dim, gx_parts, gy_parts); g*_parts = (own [.,.,3], scat [.,.,4]) or None,
     with d loss/d cloud = own + scat[..., :3] (combined and scaled by chamfer_cd_backward).
     loss = coef * sum_b batch_weight[b] * (sum dist1[b] + sum dist2[b]); defaults: weights 1, coef 0.5 / B.
     want_dist=True appends (dist1 [B,N], dist2 [B,M]) — the unweighted distances, for the metric callers
-    (train_view.py:376-380) that would otherwise repeat the forward."""
+    (train_view.py:376-380) that would otherwise repeat the forward.
+    y_period > 0: points_y holds y_period clouds and batch element b of points_x is matched against
+    points_y[b % y_period] (the stage loop's shared target, rma_chamfer_opts.y_batch_period); every output, the
+    gradient halves of points_y included, stays per batch element of points_x ([B,M,.])."""
     _check_points("points_x", points_x)
     _check_points("points_y", points_y)
     _same_device(points_x, points_y)
     B, N, M = points_x.shape[0], points_x.shape[1], points_y.shape[1]
-    if points_y.shape[0] != B:
+    y_period = int(y_period or 0)
+    if y_period:
+        if points_y.shape[0] != y_period or B % y_period != 0:
+            raise RuntimeError(f"y_period={y_period}: points_y must hold {y_period} clouds and divide the batch of {B}")
+    elif points_y.shape[0] != B:
         raise RuntimeError(f"batch sizes differ: {B} vs {points_y.shape[0]}")
     if B == 0 or N == 0 or M == 0:
         raise RuntimeError("chamfer_dist needs non-empty point sets (min over an empty dimension)")
     lib = _lib.load()
     dev = points_x.device
+    opts = _opts()
+    if y_period:
+        cur = getattr(_tls, "opts", None)
+        o = _lib.ChamferOpts(cur.path if cur else _lib.PATH_AUTO, cur.unit_run if cur else 0,
+                             cur.record_cap_bytes if cur else 0, y_period, 0)
+        opts = ctypes.byref(o)
     with torch.cuda.device(dev):
-        wsb = lib.rma_chamfer_workspace_bytes(B, N, M, _opts())
+        wsb = lib.rma_chamfer_workspace_bytes(B, N, M, opts)
         if wsb == 0:
             raise RuntimeError(f"problem size not supported: B={B}, N={N}, M={M}")
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
@@ -175,7 +188,7 @@ def chamfer_cd_forward(points_x: torch.Tensor, points_y: torch.Tensor, need_x: b
                                         _ptr(loss), _ptr(d1), _ptr(d2), None, None,
                                         _ptr(gx[0] if gx else None), _ptr(gx[1] if gx else None),
                                         _ptr(gy[0] if gy else None), _ptr(gy[1] if gy else None),
-                                        _ptr(ws), wsb, _opts(), _stream())
+                                        _ptr(ws), wsb, opts, _stream())
         _lib.check(rc, "rma_chamfer_cd_forward_weighted")
     if want_dist:
         return loss, gx, gy, d1, d2

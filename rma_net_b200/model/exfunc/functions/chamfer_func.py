@@ -31,10 +31,13 @@ class ChamferCDFunction(torch.autograd.Function):
     w.r.t. both clouds come out of the forward's three launches; backward is one combine-and-scale launch."""
 
     @staticmethod
-    def forward(ctx, deformation_p, p1, batch_weight=None, coef=None):
+    def forward(ctx, deformation_p, p1, batch_weight=None, coef=None, y_period=0):
+        """y_period > 0: p1 holds y_period clouds shared by the batch elements b, b + y_period, ... of deformation_p
+        (the stage loop's target, not repeated); its gradient is the sum over the batch elements that used it."""
         need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        loss, gx, gy = ext.chamfer_cd_forward(deformation_p, p1, need_x, need_y, batch_weight, coef)
+        loss, gx, gy = ext.chamfer_cd_forward(deformation_p, p1, need_x, need_y, batch_weight, coef, y_period=y_period)
         ctx.has = (gx is not None, gy is not None)
+        ctx.y_period = int(y_period or 0)
         ctx.save_for_backward(*[t for pair in (gx, gy) if pair is not None for t in pair])
         return loss
 
@@ -44,8 +47,11 @@ class ChamferCDFunction(torch.autograd.Function):
         gx = (saved.pop(0), saved.pop(0)) if ctx.has[0] else None
         gy = (saved.pop(0), saved.pop(0)) if ctx.has[1] else None
         if gx is None and gy is None:
-            return None, None, None, None
-        return ext.chamfer_cd_backward(gx, gy, grad_loss) + (None, None)
+            return None, None, None, None, None
+        ox, oy = ext.chamfer_cd_backward(gx, gy, grad_loss)
+        if oy is not None and ctx.y_period:
+            oy = oy.view(-1, ctx.y_period, oy.shape[1], 3).sum(0)
+        return ox, oy, None, None, None
 
 
 class ChamferCDMetricsFunction(torch.autograd.Function):
@@ -53,11 +59,12 @@ class ChamferCDMetricsFunction(torch.autograd.Function):
     (non-differentiable), so that the metric callers (reference train_view.py:376-380) do not repeat the search."""
 
     @staticmethod
-    def forward(ctx, deformation_p, p1, batch_weight=None, coef=None):
+    def forward(ctx, deformation_p, p1, batch_weight=None, coef=None, y_period=0):
         need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         loss, gx, gy, d1, d2 = ext.chamfer_cd_forward(deformation_p, p1, need_x, need_y, batch_weight, coef,
-                                                      want_dist=True)
+                                                      want_dist=True, y_period=y_period)
         ctx.has = (gx is not None, gy is not None)
+        ctx.y_period = int(y_period or 0)
         ctx.save_for_backward(*[t for pair in (gx, gy) if pair is not None for t in pair])
         ctx.mark_non_differentiable(d1, d2)
         return loss, d1, d2

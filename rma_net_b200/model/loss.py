@@ -79,7 +79,7 @@ def stack_stages(deformation_points_list):
 def loss_cd_stages_fused(deformation_points_list, target_points, gamma=0.8, weight_cd=1.0, return_dist=False,
                          stacked=None):
     """The same value and gradients as loss_cd_stages, with all T stages in ONE chamfer call: the stage outputs are
-    stacked into a [T*B,N,3] batch, the target is repeated, and the stage weights gamma^(T-i-1) * weight_cd enter the
+    stacked into a [T*B,N,3] batch against the ONE target (y_batch_period = B: no copies of it), and the stage weights gamma^(T-i-1) * weight_cd enter the
     fused kernel as per-batch-element weights (rma_chamfer_cd_forward_weighted).  4 launches instead of 4*T.
     return_dist=True -> (loss, dist1 [T,B,N], dist2 [T,B,M]): the unweighted distances of the same forward, for
     stage_chamfer_errors.  stacked: the [T,B,N,3] tensor of stack_stages, if the caller already has it."""
@@ -87,11 +87,11 @@ def loss_cd_stages_fused(deformation_points_list, target_points, gamma=0.8, weig
     B = target_points.shape[0]
     x_all = stack_stages(deformation_points_list) if stacked is None else stacked
     x_all = x_all.reshape(iter_time * B, x_all.shape[2], 3)
-    y_all = target_points.unsqueeze(0).expand(iter_time, -1, -1, -1).reshape(iter_time * B, target_points.shape[1], 3)
+    # the target is NOT repeated T times: batch element t * B + b of the stack reads target_points[b] (y_period = B)
     w = _stage_weights(iter_time, B, float(gamma), float(weight_cd), target_points.device)
     if not return_dist:
-        return ChamferCDFunction.apply(x_all, y_all, w, 0.5 / B)
-    loss, d1, d2 = ChamferCDMetricsFunction.apply(x_all, y_all, w, 0.5 / B)
+        return ChamferCDFunction.apply(x_all, target_points, w, 0.5 / B, B)
+    loss, d1, d2 = ChamferCDMetricsFunction.apply(x_all, target_points, w, 0.5 / B, B)
     return loss, d1.view(iter_time, B, -1), d2.view(iter_time, B, -1)
 
 

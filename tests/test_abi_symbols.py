@@ -46,7 +46,7 @@ def test_library_exports_nothing_but_the_header():
 def test_ctypes_table_matches_header():
     assert sorted(_lib.SIGNATURES) == _declared()
     lib = _lib.load()
-    assert lib.rma_b200_abi_version() == 2
+    assert lib.rma_b200_abi_version() == 3
     assert b"workspace" in lib.rma_b200_error_string(-2)
 
 

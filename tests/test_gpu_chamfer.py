@@ -617,3 +617,24 @@ def test_alternating_inputs_through_one_workspace(cuda):
         for a, b_ in zip(o, ref[k]):
             assert torch.equal(a, b_), it
         assert float(l) == ref_loss[k]
+
+
+def test_shared_target_period_equals_repeated_target(cuda, chamfer_path):
+    """rma_chamfer_opts.y_batch_period: batch element b reads y[b % period]; everything the call returns is bit-identical
+    to the call on the target repeated T times, and a batch that the period does not divide is a bad argument."""
+    from rma_net_b200 import ext
+    g = torch.Generator().manual_seed(41)
+    T, B, N, M = 3, 4, 1100, 900
+    x = (torch.rand(T * B, N, 3, generator=g) * 2 - 1).to(cuda)
+    y = (torch.rand(B, M, 3, generator=g) * 2 - 1).to(cuda)
+    w = torch.rand(T * B, generator=g).to(cuda)
+    rep = y.repeat(T, 1, 1)
+    a = ext.chamfer_cd_forward(x, rep, True, True, w, 0.125, True)
+    b_ = ext.chamfer_cd_forward(x, y, True, True, w, 0.125, True, y_period=B)
+    assert float(a[0]) == float(b_[0])
+    for pa, pb in zip((a[1][0], a[2][0]) + a[3:], (b_[1][0], b_[2][0]) + b_[3:]):   # own terms, dist1, dist2
+        assert torch.equal(pa, pb)
+    for pa, pb in zip((a[1][1], a[2][1]), (b_[1][1], b_[2][1])):                    # scattered terms: float atomics,
+        assert (pa - pb).abs().max() <= 1e-6 * pa.abs().max()                        # the order of the adds is not fixed
+    with pytest.raises(RuntimeError):
+        ext.chamfer_cd_forward(x[:-1], y, True, False, None, None, False, y_period=B)
