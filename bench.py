@@ -466,7 +466,8 @@ def run_ours(args):
     # replays one executable.  That figure is still measured and reported as `one_graph_per_step`.
     n_per = 1
     if use_graph and not args.one_graph_per_step:
-        n_per = max(d for d in range(1, min(K, 40) + 1) if K % d == 0)
+        cap = args.steps_per_graph if args.steps_per_graph > 0 else 40
+        n_per = max(d for d in range(1, min(K, cap) + 1) if K % d == 0)
     R = args.sets if args.sets > 0 else max(2, int(2.2 * L2_BYTES // set_bytes) + 1)
     R = ((R + n_per - 1) // n_per) * n_per
     if R // n_per < 2:
@@ -523,6 +524,9 @@ def run_ours(args):
             # steps execute back to back on the device whatever the host does meanwhile (the clock sampler's NVML
             # queries stall launches for milliseconds: without the gate a region now and then measured such a stall)
             torch.cuda._sleep(GATE_CYCLES)
+            for _ in range(-(-W // per)):     # >= W warm-up steps of the same kind directly in front of the start
+                groups[pos % len(groups)]()   # event (other input sets): the first steps behind the idle spin ran
+                pos += 1                      # ~1.5 us per step slower at K = 20
             ev0.record()
             for _ in range(nlaunch):
                 groups[pos % len(groups)]()
@@ -964,6 +968,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--one-graph-per-step", action="store_true", help="headline leg: one CUDA graph per step and input set "
                     "(the protocol until r02k) instead of graphs of n consecutive steps")
+    ap.add_argument("--steps-per-graph", type=int, default=0, help="headline leg: cap on the steps captured per CUDA graph "
+                    "(default 40; the largest divisor of K below the cap is used)")
     ap.add_argument("--private-pools", action="store_true", help="headline leg: every input set's graph gets its own memory "
                     "pool (its own scratch workspace) instead of the shared one")
     ap.add_argument("--no-cpu-baseline", action="store_true")
