@@ -54,9 +54,11 @@ WORKLOADS = {
     "S16x2048": (16, 2048, 2048, 5, "uniform"),
     "S64x1024": (64, 1024, 1024, 6, "uniform"),
     "S28x2048": (28, 2048, 2048, 7, "uniform"),
-    # one rank's shard of C5 at 4 / 8 GPUs (tools/ only): 2^18 / 2^17 sources against 2^20 targets
+    # one rank's shard of C5 at 1 / 2 / 4 / 8 GPUs (tools/ only): 2^20 .. 2^17 sources against 2^20 targets
     "C5s4": (1, 262144, 1048576, 4, "uniform"),
     "C5s8": (1, 131072, 1048576, 4, "uniform"),
+    "C5s2": (1, 524288, 1048576, 4, "uniform"),
+    "C5s1": (1, 1048576, 1048576, 4, "uniform"),
 }
 GATE_CYCLES = 40_000_000    # ~20 ms at 1.9 GHz: see the headline leg in run_ours
 L2_BYTES = 126 << 20        # B200 L2 (guides/B200_PROFILING.md)

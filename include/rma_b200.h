@@ -55,8 +55,8 @@ int rma_b200_device_info(int* sm_count, int* clock_khz, int* cc_major, int* cc_m
  * Per-call options (`opts`, may be NULL = all defaults; the SAME opts must be passed to workspace_bytes and to every
  * stage that works on that workspace).  Two search implementations return identical results: the filter + exact
  * resolve path (default) and the exact difference-form path, which takes over when the filter's group records
- * (B*N*M/64 bytes) would exceed record_cap_bytes (default 4 GiB, or RMA_B200_FILTER_RECORD_CAP_MB read once at load
- * time).  Everything is decided from the call's own arguments: the library keeps no mutable state between calls.
+ * (B*N*M/64 bytes) would exceed record_cap_bytes (default 16 GiB = one 2^20 x 2^20 pair, whose filter workspace is 40 GiB; or
+ * RMA_B200_FILTER_RECORD_CAP_MB read once at load time).  Everything is decided from the call's own arguments: the library keeps no mutable state between calls.
  */
 #define RMA_CHAMFER_PATH_AUTO 0
 #define RMA_CHAMFER_PATH_EXACT 1

@@ -615,13 +615,15 @@ int f_dealing_selfcheck(int B, int N, int M, int sms, int unit_run, int* mode_ou
 // Which search runs: the filter path whenever its group records (B*N*M/64 bytes) stay below the cap, else the
 // exact path (huge single pairs, SURVEY.md config C5 on few GPUs).  Both return identical results.  Every choice is
 // a function of the call's own arguments (sizes + rma_chamfer_opts): the library keeps no mutable state.
-// Default record cap: 4 GiB (C5 sharded over 4 or 8 GPUs stays on the filter path); the environment variable
-// RMA_B200_FILTER_RECORD_CAP_MB, read once when the library is loaded, changes the default (180 GB of HBM make tens
-// of GB reasonable for a single huge pair).
+// Default record cap: 16 GiB - C5 (one pair of 2^20 x 2^20 points) on ONE GPU is exactly at it and runs the filter path
+// with a 40 GiB workspace (records 16 GiB + row entries 25 GiB) out of 180 GB of HBM: 204 ms of search at 87 % of the
+// FP32 FMA peak against 238 ms on the exact path.  It was 4 GiB until r02n (the filter path only from 4 GPUs upward).
+// The environment variable RMA_B200_FILTER_RECORD_CAP_MB, read once when the library is loaded, changes the default;
+// callers short of memory pass record_cap_bytes or RMA_CHAMFER_PATH_EXACT per call (workspace 2.8 MiB per 2^16 points).
 static const size_t g_default_record_cap = [] {
   const char* e = std::getenv("RMA_B200_FILTER_RECORD_CAP_MB");
   const long long mb = e ? std::atoll(e) : 0;
-  return mb > 0 ? (size_t)mb << 20 : (size_t)4 << 30;
+  return mb > 0 ? (size_t)mb << 20 : (size_t)16 << 30;
 }();
 
 struct ChamferOpts {

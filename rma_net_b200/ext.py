@@ -85,6 +85,33 @@ def chamfer_path(B: int, N: int, M: int) -> str:
     return "filter" if rc == _lib.PATH_FILTER else "exact"
 
 
+def _alloc_workspace(lib, B: int, N: int, M: int, dev, y_period: int = 0):
+    """(workspace tensor, bytes, opts pointer, keep-alive) for one chamfer call under the current options.  The filter
+    path of a single huge pair wants tens of GB (40 GiB for 2^20 x 2^20: include/rma_b200.h); if torch cannot give that,
+    the same call runs on the exact path - identical results, a few MiB of workspace - instead of failing."""
+    cur = getattr(_tls, "opts", None)
+    o = None
+    if cur is not None or y_period:
+        o = _lib.ChamferOpts(cur.path if cur else _lib.PATH_AUTO, cur.unit_run if cur else 0,
+                             cur.record_cap_bytes if cur else 0, int(y_period), 0)
+    opts = ctypes.byref(o) if o is not None else None
+    wsb = lib.rma_chamfer_workspace_bytes(B, N, M, opts)
+    if wsb == 0:
+        raise RuntimeError(f"problem size not supported: B={B}, N={N}, M={M}")
+    try:
+        return torch.empty(wsb, dtype=torch.uint8, device=dev), wsb, opts, o
+    except torch.OutOfMemoryError:
+        if wsb < (1 << 30) or (cur is not None and cur.path == _lib.PATH_FILTER):
+            raise
+        import warnings
+        warnings.warn(f"rma_net_b200: {wsb / 2**30:.1f} GiB of filter-path workspace for B={B}, N={N}, M={M} do not fit; "
+                      "running the exact search path (same results)")
+        o = _lib.ChamferOpts(_lib.PATH_EXACT, 0, 0, int(y_period), 0)
+        opts = ctypes.byref(o)
+        wsb = lib.rma_chamfer_workspace_bytes(B, N, M, opts)
+        return torch.empty(wsb, dtype=torch.uint8, device=dev), wsb, opts, o
+
+
 def chamfer_forward(points_x: torch.Tensor, points_y: torch.Tensor, want_idx: bool = True):
     """[B,N,3], [B,M,3] (any strides) -> dist1 [B,N], dist2 [B,M], idx1 [B,N] int32, idx2 [B,M] int32."""
     _check_points("points_x", points_x)
@@ -97,11 +124,8 @@ def chamfer_forward(points_x: torch.Tensor, points_y: torch.Tensor, want_idx: bo
         raise RuntimeError("chamfer_dist needs non-empty point sets (min over an empty dimension)")
     lib = _lib.load()
     with torch.cuda.device(points_x.device):
-        wsb = lib.rma_chamfer_workspace_bytes(B, N, M, _opts())
-        if wsb == 0:
-            raise RuntimeError(f"problem size not supported: B={B}, N={N}, M={M}")
         dev = points_x.device
-        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        ws, wsb, opts, _keep = _alloc_workspace(lib, B, N, M, dev)
         dist1 = torch.empty((B, N), dtype=torch.float32, device=dev)
         dist2 = torch.empty((B, M), dtype=torch.float32, device=dev)
         idx1 = torch.empty((B, N), dtype=torch.int32, device=dev) if want_idx else None
@@ -109,7 +133,7 @@ def chamfer_forward(points_x: torch.Tensor, points_y: torch.Tensor, want_idx: bo
         xs, ys = points_x.stride(), points_y.stride()
         rc = lib.rma_chamfer_forward(_ptr(points_x), xs[0], xs[1], xs[2], _ptr(points_y), ys[0], ys[1], ys[2],
                                      B, N, M, _ptr(dist1), _ptr(dist2), _ptr(idx1), _ptr(idx2),
-                                     _ptr(ws), wsb, _opts(), _stream())
+                                     _ptr(ws), wsb, opts, _stream())
         _lib.check(rc, "rma_chamfer_forward")
     return dist1, dist2, idx1, idx2
 
@@ -161,17 +185,8 @@ def chamfer_cd_forward(points_x: torch.Tensor, points_y: torch.Tensor, need_x: b
         raise RuntimeError("chamfer_dist needs non-empty point sets (min over an empty dimension)")
     lib = _lib.load()
     dev = points_x.device
-    opts = _opts()
-    if y_period:
-        cur = getattr(_tls, "opts", None)
-        o = _lib.ChamferOpts(cur.path if cur else _lib.PATH_AUTO, cur.unit_run if cur else 0,
-                             cur.record_cap_bytes if cur else 0, y_period, 0)
-        opts = ctypes.byref(o)
     with torch.cuda.device(dev):
-        wsb = lib.rma_chamfer_workspace_bytes(B, N, M, opts)
-        if wsb == 0:
-            raise RuntimeError(f"problem size not supported: B={B}, N={N}, M={M}")
-        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        ws, wsb, opts, _keep = _alloc_workspace(lib, B, N, M, dev, y_period)
         loss = torch.empty((), dtype=torch.float32, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
         gx = (torch.empty((B, N, 3), **f32), torch.empty((B, N, 4), **f32)) if need_x else None

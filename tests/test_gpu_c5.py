@@ -32,14 +32,14 @@ def exact_result(clouds):
 
 def test_c5_filter_equals_exact(clouds, exact_result):
     """2^40 pairs through both search implementations: identical distances and indices.  The filter's group records are
-    B*N*M/64 = 16 GiB here, above the default 4 GiB cap (the automatic choice is the exact path on 1-2 GPUs), so the
-    cap is raised per call."""
+    B*N*M/64 = 16 GiB here, exactly the default cap: the automatic choice is the filter path (40 GiB workspace); a
+    lower per-call cap sends the same call to the exact path."""
     from rma_net_b200 import ext
     _, _, xd, yd = clouds
-    assert ext.chamfer_path(1, N, M) == "exact"               # automatic choice at this size on one GPU
-    with ext.chamfer_options(path="auto", record_cap_bytes=64 << 30):
-        assert ext.chamfer_path(1, N, M) == "filter"
-        got = ext.chamfer_forward(xd, yd)
+    with ext.chamfer_options(path="auto", record_cap_bytes=4 << 30):
+        assert ext.chamfer_path(1, N, M) == "exact"
+    assert ext.chamfer_path(1, N, M) == "filter"              # automatic choice at this size on one GPU
+    got = ext.chamfer_forward(xd, yd)
     for a, b in zip(got, exact_result):
         assert torch.equal(a, b)
 
