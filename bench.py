@@ -597,6 +597,25 @@ def run_ours(args):
         if it >= 3:
             k_ms.append(e0.elapsed_time(e1))
     search_ms = sum(k_ms) / len(k_ms)
+    # the same kernel, 8 launches back to back between one event pair (no event / launch gap per launch, records
+    # overwritten in place): what a launch costs inside a step, where the device timeline has it at 54.3 us
+    # (profiles/r02n_step_timeline_C2.json).  Reported beside `frac`, which stays the flushed single launch.
+    kb_ms = []
+    for it in range(4):
+        flush.zero_()
+        _lib.check(lib.rma_chamfer_prep(P(xd), xs_[0], xs_[1], xs_[2], P(yd), ys_[0], ys_[1], ys_[2], B, N, M,
+                                        P(ws), wsb, None, stream), "prep")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(8):
+            _lib.check(lib.rma_chamfer_search(B, N, M, P(ws), wsb, None, stream), "search")
+        e1.record()
+        _lib.check(lib.rma_chamfer_finalize(B, N, M, P(d1), P(d2), P(i1), P(i2), P(ws), wsb, None, stream),
+                   "finalize")
+        torch.cuda.synchronize()
+        if it >= 1:
+            kb_ms.append(e0.elapsed_time(e1) / 8)
+    search_b2b_ms = sum(kb_ms) / len(kb_ms)
     clocks = sampler.stop()
     # which search implementation ran for this size, and how often the filter's guard sent an item to the slow path
     stats = (ctypes.c_uint * 4)()
@@ -911,13 +930,15 @@ def run_ours(args):
         "roofline": {"bound": "fp32_fma", "kernel": search_kernel, "achieved": achieved_tflops,
                      "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
                      # the north-star quantity: the same algorithmic FLOP over the WHOLE fwd+bwd step (prep + search +
-                     # resolve + backward), L2 flushed before every step
+                     # resolve + backward) of the headline leg (inputs rotating through > 2 x L2)
                      "step_frac": FLOP_PER_PAIR * pairs / (ms * 1e-3) / 1e12 / peak_tflops,
                      "step_frac_flushed_protocol": FLOP_PER_PAIR * pairs / (flushed_ms * 1e-3) / 1e12 / peak_tflops,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch cannot be measured inside
                      # this run (it needs ncu): taken from the committed ncu --set full capture named in
                      # traffic_source, for this workload and search kernel only
                      **search_traffic(name, search_kernel), "kernel_ms": search_ms,
+                     "kernel_ms_back_to_back": search_b2b_ms,
+                     "frac_back_to_back": FLOP_PER_PAIR * pairs / (search_b2b_ms * 1e-3) / 1e12 / peak_tflops,
                      "note": ("achieved = ALGORITHMIC 12 FLOP (6 FMA) per point-pair (SURVEY.md section 8d) / kernel "
                               "time.  The filter kernel itself issues 3 FFMA + 1 FADD + 2 min per pair (its exact "
                               "re-evaluation of the candidates runs in the resolve kernel), so frac is a fraction "
