@@ -1044,7 +1044,6 @@ __global__ void __launch_bounds__(kFinWarps * 32, 4) chamfer_fresolve_kernel(con
   const unsigned nrow = (unsigned)g.B * (unsigned)g.N, ncol = (unsigned)g.B * (unsigned)g.M;
   const unsigned row_warps = (nrow + 31u) / 32u;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
-  const int half = lane >> 4, hl = lane & 15;
   const unsigned total_warps = row_warps + (ncol + 31u) / 32u;
   // CTA c takes wbase = total / grid items, the first wrem = total % grid CTAs one more (computed on the host: a 64-bit
   // division here costs ~100 instructions per thread)
