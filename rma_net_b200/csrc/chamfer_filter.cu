@@ -127,7 +127,6 @@ __host__ __device__ __forceinline__ unsigned fdiv(unsigned t, unsigned d, unsign
 // The host picks the mode with the smaller per-SM maximum (f_make_geometry).
 struct FDeal {
   int mode;
-  int S;               // SMs (serpentine period)
   // mode 0
   int U, Us, nL;
   unsigned uL;         // nL * U: first unit of the short CTAs
@@ -210,7 +209,6 @@ static FGeometry f_make_geometry(int B, int N, int M, int sms, int occ, int forc
     const long long G = (long long)g.nC <= slots ? ((long long)g.nC < sms ? g.nC : sms) : ((long long)g.nC + occ - 1) / occ;
     g.G = (int)(G > 0x7fffffffLL ? 0x7fffffffLL : G);
   }
-  d.S = g.G;
   d.Us = d.U > 1 ? d.U - 1 : 1;
   d.uL = (unsigned)((long long)d.nL * d.U > 0x7fffffffLL ? 0x7fffffffLL : (long long)d.nL * d.U);
   const int shortest = d.nL < g.nC ? d.Us : d.U;
